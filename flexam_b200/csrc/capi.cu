@@ -1,0 +1,86 @@
+// Library-level C-ABI entry points and the host helpers the kernel translation units share.
+#include <stdarg.h>
+#include <string.h>
+
+#include "host_common.h"
+
+namespace fx {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int cached_dev = -1;
+  static int cached = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || sym == nullptr) {
+      set_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+      return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return false;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                  reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
+                  reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims[0..1]=%llu,%llu stride1=%llu box=%u,%u",
+              static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+              (unsigned long long)strides_bytes[0], box[0], box[1]);
+    return false;
+  }
+  return true;
+}
+
+}  // namespace fx
+
+extern "C" int fx_abi_version(void) { return FX_ABI_VERSION; }
+extern "C" const char* fx_last_error(void) { return fx::g_err; }
+
+extern "C" int fx_check_device(int device) {
+  int major = 0, minor = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+  if (e != cudaSuccess) {
+    fx::set_error("fx_check_device(%d): %s", device, cudaGetErrorString(e));
+    return FX_ERR_CUDA;
+  }
+  if (major != 10) {
+    fx::set_error("fx_check_device(%d): compute capability %d.%d, library is built for sm_100a only", device, major,
+                  minor);
+    return FX_ERR_ARCH;
+  }
+  return FX_OK;
+}

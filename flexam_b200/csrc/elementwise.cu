@@ -1,0 +1,338 @@
+// HBM-bound row kernels of the DiT block: LayerNorm + adaLN modulation, LayerNorm + affine, full-width
+// RMSNorm (+ 3-axis RoPE), and the sampler's fused CFG/Euler update. One warp owns one row, keeps it in
+// registers (single global read), reduces with shuffles and writes 8/16-byte vectors.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace fx {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// -------------------------------------------------------------------------------------------------
+// LayerNorm (no affine) with either adaLN modulation (MODE 0) or bf16 gamma/beta (MODE 1)
+//   WanAttentionBlock.forward :444-453,:464-465; Head.forward :493-507; norm3 :405-407,:461
+// -------------------------------------------------------------------------------------------------
+struct LnParams {
+  const float* x;
+  __nv_bfloat16* out;
+  int M, D;
+  float eps;
+  // MODE 0
+  const float* shift_mod;
+  const float* scale_mod;
+  const float* shift_e;
+  const float* scale_e;
+  long long e_stride;
+  const int* row_idx;
+  const float* dens;
+  long long dens_stride;
+  int rows_per_batch;
+  // MODE 1
+  const __nv_bfloat16* gamma;
+  const __nv_bfloat16* beta;
+};
+
+template <int NV, int MODE>  // NV = float4 vectors per lane = D / 128
+__global__ void __launch_bounds__(256) ln_kernel(const LnParams p) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.M) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<long long>(row) * p.D);
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = xr[i * 32 + lane];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / static_cast<float>(p.D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(p.D) + p.eps);
+
+  uint2* orow = reinterpret_cast<uint2*>(p.out + static_cast<long long>(row) * p.D);
+  if constexpr (MODE == 0) {
+    const long long u = p.row_idx ? p.row_idx[row] : 0;
+    const float4* sh_e = reinterpret_cast<const float4*>(p.shift_e + u * p.e_stride);
+    const float4* sc_e = reinterpret_cast<const float4*>(p.scale_e + u * p.e_stride);
+    const float4* sh_m = reinterpret_cast<const float4*>(p.shift_mod);
+    const float4* sc_m = reinterpret_cast<const float4*>(p.scale_mod);
+    const float4* dn =
+        p.dens ? reinterpret_cast<const float4*>(p.dens + static_cast<long long>(row / p.rows_per_batch) * p.dens_stride)
+               : nullptr;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = i * 32 + lane;
+      const float4 sm = __ldg(sc_m + c), se = __ldg(sc_e + c), hm = __ldg(sh_m + c), he = __ldg(sh_e + c);
+      float4 sc, sh;
+      sc.x = 1.f + (sm.x + se.x); sc.y = 1.f + (sm.y + se.y); sc.z = 1.f + (sm.z + se.z); sc.w = 1.f + (sm.w + se.w);
+      sh.x = hm.x + he.x; sh.y = hm.y + he.y; sh.z = hm.z + he.z; sh.w = hm.w + he.w;
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * sc.x + sh.x;
+      y.y = (v[i].y - mean) * rstd * sc.y + sh.y;
+      y.z = (v[i].z - mean) * rstd * sc.z + sh.z;
+      y.w = (v[i].w - mean) * rstd * sc.w + sh.w;
+      if (dn != nullptr) {
+        const float4 d = __ldg(dn + c);
+        y.x += d.x; y.y += d.y; y.z += d.z; y.w += d.w;
+      }
+      uint2 o;
+      o.x = pack_bf16x2(y.x, y.y);
+      o.y = pack_bf16x2(y.z, y.w);
+      orow[c] = o;
+    }
+  } else {
+    const uint2* gm = reinterpret_cast<const uint2*>(p.gamma);
+    const uint2* bt = reinterpret_cast<const uint2*>(p.beta);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = i * 32 + lane;
+      const uint2 g = __ldg(gm + c), b = __ldg(bt + c);
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * bf16_lo(g.x) + bf16_lo(b.x);
+      y.y = (v[i].y - mean) * rstd * bf16_hi(g.x) + bf16_hi(b.x);
+      y.z = (v[i].z - mean) * rstd * bf16_lo(g.y) + bf16_lo(b.y);
+      y.w = (v[i].w - mean) * rstd * bf16_hi(g.y) + bf16_hi(b.y);
+      uint2 o;
+      o.x = pack_bf16x2(y.x, y.y);
+      o.y = pack_bf16x2(y.z, y.w);
+      orow[c] = o;
+    }
+  }
+}
+
+template <int MODE>
+static int launch_ln(const LnParams& p, cudaStream_t s, const char* name) {
+  const int nv = p.D / 128;
+  const int rows_per_block = 8;
+  const int grid = (p.M + rows_per_block - 1) / rows_per_block;
+#define FX_LN_CASE(NVV)                                   \
+  case NVV:                                               \
+    ln_kernel<NVV, MODE><<<grid, 256, 0, s>>>(p);         \
+    break;
+  switch (nv) {
+    FX_LN_CASE(1) FX_LN_CASE(2) FX_LN_CASE(4) FX_LN_CASE(8) FX_LN_CASE(12) FX_LN_CASE(16) FX_LN_CASE(24)
+    FX_LN_CASE(32) FX_LN_CASE(40)
+    default:
+      set_error("%s: unsupported D=%d (D/128 must be one of 1,2,4,8,12,16,24,32,40)", name, p.D);
+      return FX_ERR_ARG;
+  }
+#undef FX_LN_CASE
+  FX_CHECK_LAUNCH(name);
+  return FX_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Full-width RMSNorm (+ RoPE), in place on bf16 rows.  WanRMSNorm :173-189 at :242-243/:363-364;
+// rope_apply :135-164 with the [22,21,21] frame/row/col split of the 64 complex pairs per head.
+// -------------------------------------------------------------------------------------------------
+struct RmsParams {
+  __nv_bfloat16* x;
+  long long ldx;
+  int M, D;
+  float eps;
+  const __nv_bfloat16* w;
+  const float2* freqs;  // [1024][64] (cos, sin) or nullptr
+  int gf, gh, gw, tok_offset, rows_per_batch;
+};
+
+template <int NV>  // NV = 16-byte vectors (8 bf16) per lane = D / 256
+__global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const RmsParams p) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.M) return;
+  const int lane = threadIdx.x & 31;
+  uint4* xr = reinterpret_cast<uint4*>(p.x + static_cast<long long>(row) * p.ldx);
+  uint4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = xr[i * 32 + lane];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = bf16_lo(u[j]), b = bf16_hi(u[j]);
+      ss += a * a + b * b;
+    }
+  }
+  // r is rounded to bf16 before the multiply, as `.to(x.dtype)` does at :189
+  const float r = bf16_round(rsqrtf(warp_sum(ss) / static_cast<float>(p.D) + p.eps));
+
+  int pos[3] = {0, 0, 0};
+  bool rotate = false;
+  if (p.freqs != nullptr) {
+    const int t = p.tok_offset + row % p.rows_per_batch;
+    if (t < p.gf * p.gh * p.gw) {
+      rotate = true;
+      pos[0] = t / (p.gh * p.gw);
+      const int rem = t - pos[0] * (p.gh * p.gw);
+      pos[1] = rem / p.gw;
+      pos[2] = rem - pos[1] * p.gw;
+    }
+  }
+  const uint4* wr = reinterpret_cast<const uint4*>(p.w);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 32 + lane;  // vector index; elements [8c, 8c+8)
+    const uint4 wv = __ldg(wr + c);
+    const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+    const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+    uint32_t o[4];
+    const int pair0 = (c & 15) * 4;  // first complex pair of this vector inside its 128-wide head
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = bf16_round(bf16_round(bf16_lo(u[j]) * r) * bf16_lo(ww[j]));
+      float b = bf16_round(bf16_round(bf16_hi(u[j]) * r) * bf16_hi(ww[j]));
+      if (rotate) {
+        const int pj = pair0 + j;
+        const int axis = pj < 22 ? 0 : (pj < 43 ? 1 : 2);
+        const float2 cs = __ldg(p.freqs + pos[axis] * 64 + pj);
+        const float re = a * cs.x - b * cs.y;
+        const float im = a * cs.y + b * cs.x;
+        a = re;
+        b = im;
+      }
+      o[j] = pack_bf16x2(a, b);
+    }
+    xr[c] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+__global__ void cfg_euler_kernel(const __nv_bfloat16* vu, const __nv_bfloat16* vc, float guidance, float dsigma,
+                                 float* lat, const float* mask, const __nv_bfloat16* pinned, long long n) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    const float u = __bfloat162float(vu[i]);
+    const float c = __bfloat162float(vc[i]);
+    // the reference combines in the model dtype (bf16, one rounding per tensor op) at pipeline :928; the Euler
+    // update runs in fp32 and is cast back to the model dtype, so `lat` holds bf16-representable values.
+    const float v = bf16_round(u + bf16_round(guidance * bf16_round(c - u)));
+    float x = bf16_round(lat[i] + dsigma * v);
+    if (mask != nullptr) {
+      const float m = mask[i];
+      x = bf16_round(bf16_round((1.f - m) * __bfloat162float(pinned[i])) + bf16_round(m * x));
+    }
+    lat[i] = x;
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* s, __nv_bfloat16* d, long long n) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) d[i] = __float2bfloat16_rn(s[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* s, float* d, long long n) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) d[i] = __bfloat162float(s[i]);
+}
+
+static int ew_grid(long long n) {
+  long long g = (n + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  return static_cast<int>(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace fx
+
+extern "C" int fx_ln_modulate(const float* x, void* out, int M, int D, float eps, const float* shift_mod,
+                              const float* scale_mod, const float* shift_e, const float* scale_e, int64_t e_stride,
+                              const int32_t* row_idx, const float* dens, int64_t dens_stride, int rows_per_batch,
+                              void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(x && out && shift_mod && scale_mod && shift_e && scale_e, "fx_ln_modulate: null pointer");
+  FX_CHECK_ARG(M > 0 && D > 0 && D % 128 == 0, "fx_ln_modulate: bad shape M=%d D=%d", M, D);
+  FX_CHECK_ARG(e_stride % 4 == 0 && dens_stride % 4 == 0 && rows_per_batch > 0, "fx_ln_modulate: bad strides");
+  LnParams p{};
+  p.x = x; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.M = M; p.D = D; p.eps = eps;
+  p.shift_mod = shift_mod; p.scale_mod = scale_mod; p.shift_e = shift_e; p.scale_e = scale_e;
+  p.e_stride = e_stride; p.row_idx = row_idx; p.dens = dens; p.dens_stride = dens_stride;
+  p.rows_per_batch = rows_per_batch;
+  return launch_ln<0>(p, reinterpret_cast<cudaStream_t>(stream), "fx_ln_modulate");
+}
+
+extern "C" int fx_ln_affine(const float* x, void* out, int M, int D, float eps, const void* gamma, const void* beta,
+                            void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(x && out && gamma && beta, "fx_ln_affine: null pointer");
+  FX_CHECK_ARG(M > 0 && D > 0 && D % 128 == 0, "fx_ln_affine: bad shape M=%d D=%d", M, D);
+  LnParams p{};
+  p.x = x; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.M = M; p.D = D; p.eps = eps;
+  p.gamma = reinterpret_cast<const __nv_bfloat16*>(gamma);
+  p.beta = reinterpret_cast<const __nv_bfloat16*>(beta);
+  return launch_ln<1>(p, reinterpret_cast<cudaStream_t>(stream), "fx_ln_affine");
+}
+
+extern "C" int fx_rmsnorm_rope(void* x, int64_t ldx, int M, int D, float eps, const void* weight, const float* freqs,
+                               int gf, int gh, int gw, int tok_offset, int rows_per_batch, void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(x && weight, "fx_rmsnorm_rope: null pointer");
+  FX_CHECK_ARG(M > 0 && D > 0 && D % 256 == 0 && ldx % 8 == 0 && ldx >= D, "fx_rmsnorm_rope: bad shape M=%d D=%d", M,
+               D);
+  if (freqs != nullptr) {
+    FX_CHECK_ARG(gf > 0 && gh > 0 && gw > 0 && gf <= 1024 && gh <= 1024 && gw <= 1024 && rows_per_batch > 0,
+                 "fx_rmsnorm_rope: grid (%d,%d,%d) outside the 1024-entry RoPE table", gf, gh, gw);
+  } else {
+    rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1;
+  }
+  RmsParams p;
+  p.x = reinterpret_cast<__nv_bfloat16*>(x); p.ldx = ldx; p.M = M; p.D = D; p.eps = eps;
+  p.w = reinterpret_cast<const __nv_bfloat16*>(weight);
+  p.freqs = reinterpret_cast<const float2*>(freqs);
+  p.gf = gf; p.gh = gh; p.gw = gw; p.tok_offset = tok_offset; p.rows_per_batch = rows_per_batch;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (M + 7) / 8;
+  switch (D / 256) {
+    case 1: rmsnorm_rope_kernel<1><<<grid, 256, 0, s>>>(p); break;
+    case 2: rmsnorm_rope_kernel<2><<<grid, 256, 0, s>>>(p); break;
+    case 4: rmsnorm_rope_kernel<4><<<grid, 256, 0, s>>>(p); break;
+    case 6: rmsnorm_rope_kernel<6><<<grid, 256, 0, s>>>(p); break;
+    case 8: rmsnorm_rope_kernel<8><<<grid, 256, 0, s>>>(p); break;
+    case 12: rmsnorm_rope_kernel<12><<<grid, 256, 0, s>>>(p); break;
+    case 16: rmsnorm_rope_kernel<16><<<grid, 256, 0, s>>>(p); break;
+    case 20: rmsnorm_rope_kernel<20><<<grid, 256, 0, s>>>(p); break;
+    default:
+      set_error("fx_rmsnorm_rope: unsupported D=%d (D/256 must be one of 1,2,4,6,8,12,16,20)", D);
+      return FX_ERR_ARG;
+  }
+  FX_CHECK_LAUNCH("fx_rmsnorm_rope");
+  return FX_OK;
+}
+
+extern "C" int fx_cfg_euler_step(const void* vu, const void* vc, float guidance, float dsigma, float* lat,
+                                 const float* mask, const void* pinned, int64_t n, void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(vu && vc && lat && n > 0, "fx_cfg_euler_step: null pointer or empty");
+  FX_CHECK_ARG(mask == nullptr || pinned != nullptr, "fx_cfg_euler_step: mask given without pinned latents");
+  cfg_euler_kernel<<<ew_grid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(vu), reinterpret_cast<const __nv_bfloat16*>(vc), guidance, dsigma, lat,
+      mask, reinterpret_cast<const __nv_bfloat16*>(pinned), n);
+  FX_CHECK_LAUNCH("fx_cfg_euler_step");
+  return FX_OK;
+}
+
+extern "C" int fx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(src && dst && n > 0, "fx_cast_f32_to_bf16: null pointer or empty");
+  cast_f32_bf16_kernel<<<ew_grid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  FX_CHECK_LAUNCH("fx_cast_f32_to_bf16");
+  return FX_OK;
+}
+extern "C" int fx_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(src && dst && n > 0, "fx_cast_bf16_to_f32: null pointer or empty");
+  cast_bf16_f32_kernel<<<ew_grid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
+  FX_CHECK_LAUNCH("fx_cast_bf16_to_f32");
+  return FX_OK;
+}

@@ -1,0 +1,346 @@
+// Non-causal flash-attention forward for sm_100a, head_dim 128, bf16 in/out, fp32 softmax statistics.
+//
+// One CTA owns 256 query rows (two 128-row tiles) of one (batch, head) and streams 128-key K/V tiles:
+//   warp 8      TMA producer   Q once, then K_j / V_j into 2-stage rings (SWIZZLE_128B boxes of [128 rows][64 d])
+//   warp 9      MMA issuer     S_w = Q_w K_j^T (SS, both K-major) and O_w += P_w V_j (A = P from TMEM, B = V MN-major)
+//   warps 0-3   softmax for query tile 0: one thread per row, S read from TMEM, P written back over S as bf16
+//   warps 4-7   softmax for query tile 1
+// TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_w aliases the first 64 columns of S_w.
+// While one softmax group works on S_w(j), the tensor core runs the other tile's QK^T / PV, so K/V smem traffic is
+// shared by both tiles and the MMA pipe stays busy. The running maximum is only raised when it grows by more than
+// 2^8 (lazy rescale): the O accumulator is then rescaled in TMEM by the softmax group itself, which is safe because
+// s_full[w] (committed after QK_w(j)) also implies PV_w(j-1) has retired and PV_w(j) is not issued before p_full[w].
+//
+// Replaces attention()/flash_attention() (FlexAM/models/attention_utils.py:174-233) at its two call sites,
+// wan_transformer3d_FlexAM.py:251-256 (self, Lk = all tokens) and :367 (cross, Lk = 512, unmasked).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace fx {
+
+constexpr int kFmhaThreads = 384;  // 3 warpgroups: softmax tile 0, softmax tile 1, {TMA, MMA, 2 idle warps}
+constexpr int kHalfBytes = 128 * 64 * 2;       // one [128 rows][64 d] swizzled sub-tile
+constexpr int kTileBytes = 2 * kHalfBytes;     // [128 rows][128 d]
+constexpr int kFmhaSmem = 2 * kTileBytes /*Q*/ + 2 * kTileBytes /*K ring*/ + 2 * kTileBytes /*V ring*/ + 256 + 1024;
+constexpr float kRescaleThreshold = 8.0f;      // log2 units
+
+struct FmhaParams {
+  __nv_bfloat16* o;
+  long long o_stride_b, o_stride_l;
+  int Lq, Lk;
+  float scale_log2;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kFmhaThreads, 1)
+fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const FmhaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                    // [2 tiles][2 halves][128][64]
+  uint8_t* sK = sQ + 2 * kTileBytes;     // [2 stages][2 halves][128][64]
+  uint8_t* sV = sK + 2 * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * kTileBytes);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* k_full = bars + 1;      // 2
+  uint64_t* k_empty = bars + 3;     // 2
+  uint64_t* v_full = bars + 5;      // 2
+  uint64_t* v_empty = bars + 7;     // 2
+  uint64_t* s_full = bars + 9;      // 2 (per query tile)
+  uint64_t* p_full = bars + 11;     // 2 (per query tile)
+  uint64_t* o_done = bars + 13;     // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256;
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int n_kv = (p.Lk + 127) / 128;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 9 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+    }
+    mbar_init(o_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Register re-partitioning: the data-movement warpgroup (warps 8-11) gives its registers to the two softmax
+  // warpgroups (per SM sub-partition: 2 x 32 x 208 + 32 x 96 <= 16384).
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * kTileBytes);
+      for (int t = 0; t < 2; ++t)
+        for (int hf = 0; hf < 2; ++hf)
+          tma_load_4d(sQ + t * kTileBytes + hf * kHalfBytes, &tmap_q, q_full, hf * 64, head, q0 + t * 128, batch);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_expect_tx(&k_full[s], kTileBytes);
+        for (int hf = 0; hf < 2; ++hf)
+          tma_load_4d(sK + s * kTileBytes + hf * kHalfBytes, &tmap_k, &k_full[s], hf * 64, head, j * 128, batch);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_expect_tx(&v_full[s], kTileBytes);
+        for (int hf = 0; hf < 2; ++hf)
+          tma_load_4d(sV + s * kTileBytes + hf * kHalfBytes, &tmap_v, &v_full[s], hf * 64, head, j * 128, batch);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, false, true);  // B = V is MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t k_addr = smem_u32(sK);
+      const uint32_t v_addr = smem_u32(sV);
+
+      auto issue_qk = [&](int w, int kstage) {
+        const uint32_t a0 = q_addr + w * kTileBytes;
+        const uint32_t b0 = k_addr + kstage * kTileBytes;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t off = (k >> 2) * kHalfBytes + (k & 3) * 32;
+          umma_ss(tmem_base + w * 128, umma_desc_sw128(a0 + off, 16, 1024), umma_desc_sw128(b0 + off, 16, 1024),
+                  idesc_qk, k != 0);
+        }
+      };
+      auto issue_pv = [&](int w, int vstage, bool accumulate) {
+        const uint32_t b0 = v_addr + vstage * kTileBytes;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          // A: 16 keys = 8 packed columns of P_w; B: 16 key rows (2048 B) further down the MN-major V tile
+          umma_ts(tmem_base + 256 + w * 128, tmem_base + w * 128 + k * 8,
+                  umma_desc_sw128(b0 + k * 2048, kHalfBytes, 1024), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+        }
+      };
+
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      umma_commit(&s_full[0]);
+      issue_qk(1, 0);
+      umma_commit(&s_full[1]);
+      umma_commit(&k_empty[0]);
+
+      for (int j = 0; j < n_kv; ++j) {
+        const int vs = j & 1;
+        const int ks_next = (j + 1) & 1;
+        const bool has_next = (j + 1) < n_kv;
+        mbar_wait(&v_full[vs], (j >> 1) & 1);
+        mbar_wait(&p_full[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, vs, j > 0);
+        if (has_next) {
+          mbar_wait(&k_full[ks_next], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_qk(0, ks_next);
+          umma_commit(&s_full[0]);
+        }
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, vs, j > 0);
+        umma_commit(&v_empty[vs]);
+        if (has_next) {
+          issue_qk(1, ks_next);
+          umma_commit(&s_full[1]);
+          umma_commit(&k_empty[ks_next]);
+        }
+      }
+      umma_commit(o_done);
+    }
+    __syncwarp();
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    // ===================== softmax / correction / output: one thread per query row =====================
+    const int w = warp >> 2;         // query tile
+    const int quad = warp & 3;       // TMEM lane quadrant
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t s_tmem = tmem_base + lane_off + w * 128;
+    const uint32_t o_tmem = tmem_base + lane_off + 256 + w * 128;
+    const int row = q0 + w * 128 + quad * 32 + lane;
+
+    float m_used = 0.f;  // reference maximum (log2 domain) that the stored P / O / l are relative to
+    float l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[w], j & 1);
+      tc_fence_after();
+      uint32_t s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+      tmem_wait_ld();
+
+      const int valid = p.Lk - j * 128;  // keys of this tile that exist
+      if (valid < 128) {
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if (c >= valid) s[c] = 0xff800000u;  // -inf
+      }
+      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
+      float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
+#pragma unroll
+      for (int c = 4; c < 128; c += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(s[c]));
+        mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool grow = mx > m_used + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = grow ? mx : m_used;
+          const float f = ex2_approx(m_used - m_new);  // 1 for rows that keep their reference
+          m_used = m_new;
+          l *= f;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld32(o_tmem + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st32(o_tmem + c * 32, o);
+          }
+          tmem_wait_st();
+        }
+      }
+
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + 2 * i]), p.scale_log2, -m_used));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + 2 * i + 1]), p.scale_log2, -m_used));
+          sum0 += e0;
+          sum1 += e1;
+          pk[i] = pack_bf16x2(e0, e1);
+        }
+        tmem_st16(s_tmem + c * 16, pk);
+      }
+      l += sum0 + sum1;
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[w]);
+    }
+
+    // epilogue: O / l -> bf16 -> global
+    mbar_wait(o_done, 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    __nv_bfloat16* orow = p.o + static_cast<long long>(batch) * p.o_stride_b +
+                          static_cast<long long>(row) * p.o_stride_l + head * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      tmem_ld32(o_tmem + c * 32, o);
+      tmem_wait_ld();
+      if (row < p.Lq) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+          v.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+          v.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+          v.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = v;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+static bool make_qkv_tmap(CUtensorMap* m, const void* base, int64_t stride_b, int64_t stride_l, int B, int H, int L) {
+  const uint64_t dims[4] = {128, static_cast<uint64_t>(H), static_cast<uint64_t>(L), static_cast<uint64_t>(B)};
+  const uint64_t strides[3] = {128 * 2, static_cast<uint64_t>(stride_l) * 2, static_cast<uint64_t>(stride_b) * 2};
+  const uint32_t box[4] = {64, 1, 128, 1};
+  return make_tmap_bf16(m, base, 4, dims, strides, box);
+}
+
+}  // namespace fx
+
+extern "C" int fx_fmha_fwd(const void* q, int64_t q_stride_b, int64_t q_stride_l, const void* k, int64_t k_stride_b,
+                           int64_t k_stride_l, const void* v, int64_t v_stride_b, int64_t v_stride_l, void* o,
+                           int64_t o_stride_b, int64_t o_stride_l, int B, int H, int Lq, int Lk, float scale,
+                           void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(q && k && v && o, "fx_fmha_fwd: null pointer");
+  FX_CHECK_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0, "fx_fmha_fwd: empty problem B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
+  FX_CHECK_ARG(H <= 65535 && B <= 65535, "fx_fmha_fwd: H and B must fit a grid dimension");
+  const int64_t strides[8] = {q_stride_b, q_stride_l, k_stride_b, k_stride_l, v_stride_b, v_stride_l, o_stride_b,
+                              o_stride_l};
+  for (int64_t s : strides) FX_CHECK_ARG(s % 8 == 0 && s >= 0, "fx_fmha_fwd: strides must be multiples of 8 elements");
+  FX_CHECK_ARG(q_stride_l >= 128LL * H && k_stride_l >= 128LL * H && v_stride_l >= 128LL * H && o_stride_l >= 128LL * H,
+               "fx_fmha_fwd: row stride smaller than H*128");
+  FX_CHECK_ARG((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                reinterpret_cast<uintptr_t>(o)) % 16 == 0,
+               "fx_fmha_fwd: pointers must be 16-byte aligned");
+
+  CUtensorMap tq, tk, tv;
+  // a batch stride of 0 is not encodable; with B == 1 any non-zero value is equivalent
+  auto bs = [&](int64_t sb, int64_t sl, int L) { return (B == 1 && sb == 0) ? sl * L : sb; };
+  if (!make_qkv_tmap(&tq, q, bs(q_stride_b, q_stride_l, Lq), q_stride_l, B, H, Lq)) return FX_ERR_CUDA;
+  if (!make_qkv_tmap(&tk, k, bs(k_stride_b, k_stride_l, Lk), k_stride_l, B, H, Lk)) return FX_ERR_CUDA;
+  if (!make_qkv_tmap(&tv, v, bs(v_stride_b, v_stride_l, Lk), v_stride_l, B, H, Lk)) return FX_ERR_CUDA;
+
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(fmha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmhaSmem);
+    if (e != cudaSuccess) {
+      set_error("fx_fmha_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return FX_ERR_CUDA;
+    }
+    configured = true;
+  }
+  FmhaParams p;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.o_stride_b = o_stride_b;
+  p.o_stride_l = o_stride_l;
+  p.Lq = Lq;
+  p.Lk = Lk;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((Lq + 255) / 256, H, B);
+  fmha_fwd_kernel<<<grid, kFmhaThreads, kFmhaSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  FX_CHECK_LAUNCH("fx_fmha_fwd");
+  return FX_OK;
+}

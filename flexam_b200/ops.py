@@ -1,0 +1,189 @@
+"""Host-side operator layer: torch tensors in, C-ABI calls out.
+
+PyTorch is used for device memory and streams only; every function below validates its arguments and
+forwards raw pointers + the current CUDA stream to ``libflexam_b200.so`` (``include/flexam_b200.h``).
+Nothing here computes on the host or falls back to torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import lib as _l
+from .lib import FX_EPI_BF16, FX_EPI_F32, FX_EPI_GELU_BF16, FX_EPI_RESID_F32  # noqa: F401
+
+bf16, f32, i32 = torch.bfloat16, torch.float32, torch.int32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str, inner_contig: bool = True) -> None:
+    if not t.is_cuda:
+        raise _l.FlexamNativeError(f"{name}: expected a CUDA tensor (the native path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _l.FlexamNativeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if inner_contig and t.dim() > 0 and t.stride(-1) != 1:
+        raise _l.FlexamNativeError(f"{name}: innermost dimension must be contiguous")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, epilogue: int,
+         gate_mod: Optional[torch.Tensor] = None, gate_e: Optional[torch.Tensor] = None,
+         row_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = epilogue(a[M,K] @ w[N,K]^T + bias). See fx_gemm_bf16."""
+    _req(a, bf16, "gemm.a"), _req(w, bf16, "gemm.w")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K or out.shape[0] != M or out.shape[1] != N:
+        raise _l.FlexamNativeError(f"gemm: shape mismatch a{tuple(a.shape)} w{tuple(w.shape)} out{tuple(out.shape)}")
+    _req(out, bf16 if epilogue in (FX_EPI_BF16, FX_EPI_GELU_BF16) else f32, "gemm.out")
+    if bias is not None:
+        _req(bias, bf16, "gemm.bias")
+    ge_stride = 0
+    if gate_mod is not None:
+        _req(gate_mod, f32, "gemm.gate_mod")
+    if gate_e is not None:
+        _req(gate_e, f32, "gemm.gate_e")
+        ge_stride = gate_e.stride(0) if gate_e.dim() == 2 else 0
+    if row_idx is not None:
+        _req(row_idx, i32, "gemm.row_idx")
+    st = _l.load().fx_gemm_bf16(_p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(out), out.stride(0), M, N, K,
+                                epilogue, _p(gate_mod), _p(gate_e), ge_stride, _p(row_idx), _stream())
+    _l.check(st, "fx_gemm_bf16")
+    return out
+
+
+def ln_modulate(x: torch.Tensor, out: torch.Tensor, eps: float, shift_mod: torch.Tensor, scale_mod: torch.Tensor,
+                shift_e: torch.Tensor, scale_e: torch.Tensor, e_stride: int, row_idx: Optional[torch.Tensor],
+                dens: Optional[torch.Tensor], dens_stride: int, rows_per_batch: int) -> torch.Tensor:
+    _req(x, f32, "ln_modulate.x"), _req(out, bf16, "ln_modulate.out")
+    for n, t in (("shift_mod", shift_mod), ("scale_mod", scale_mod), ("shift_e", shift_e), ("scale_e", scale_e)):
+        _req(t, f32, "ln_modulate." + n)
+    M, D = x.shape
+    st = _l.load().fx_ln_modulate(_p(x), _p(out), M, D, eps, _p(shift_mod), _p(scale_mod), _p(shift_e), _p(scale_e),
+                                  e_stride, _p(row_idx), _p(dens), dens_stride, rows_per_batch, _stream())
+    _l.check(st, "fx_ln_modulate")
+    return out
+
+
+def ln_affine(x: torch.Tensor, out: torch.Tensor, eps: float, gamma: torch.Tensor, beta: torch.Tensor) -> torch.Tensor:
+    _req(x, f32, "ln_affine.x"), _req(out, bf16, "ln_affine.out")
+    _req(gamma, bf16, "ln_affine.gamma"), _req(beta, bf16, "ln_affine.beta")
+    M, D = x.shape
+    _l.check(_l.load().fx_ln_affine(_p(x), _p(out), M, D, eps, _p(gamma), _p(beta), _stream()), "fx_ln_affine")
+    return out
+
+
+def rmsnorm_rope(x: torch.Tensor, weight: torch.Tensor, eps: float, freqs: Optional[torch.Tensor] = None,
+                 grid: Sequence[int] = (0, 0, 0), tok_offset: int = 0, rows_per_batch: int = 0) -> torch.Tensor:
+    """In place on x: bf16 [M, D] view (row stride free)."""
+    _req(x, bf16, "rmsnorm_rope.x"), _req(weight, bf16, "rmsnorm_rope.weight")
+    if freqs is not None:
+        _req(freqs, f32, "rmsnorm_rope.freqs")
+    M, D = x.shape
+    st = _l.load().fx_rmsnorm_rope(_p(x), x.stride(0), M, D, eps, _p(weight), _p(freqs), int(grid[0]), int(grid[1]),
+                                   int(grid[2]), tok_offset, rows_per_batch if rows_per_batch > 0 else M, _stream())
+    _l.check(st, "fx_rmsnorm_rope")
+    return x
+
+
+def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, scale: float) -> torch.Tensor:
+    """q/out: [B, Lq, H, 128] views, k/v: [B, Lk, H, 128] views (bf16, head dim and heads contiguous)."""
+    for n, t in (("q", q), ("k", k), ("v", v), ("out", out)):
+        _req(t, bf16, "fmha." + n)
+        if t.dim() != 4 or t.shape[3] != 128 or t.stride(2) != 128:
+            raise _l.FlexamNativeError(f"fmha.{n}: expected [B, L, H, 128] with contiguous heads, got "
+                                       f"{tuple(t.shape)} strides {t.stride()}")
+    B, Lq, H, _ = q.shape
+    Lk = k.shape[1]
+    st = _l.load().fx_fmha_fwd(_p(q), q.stride(0), q.stride(1), _p(k), k.stride(0), k.stride(1), _p(v), v.stride(0),
+                               v.stride(1), _p(out), out.stride(0), out.stride(1), B, H, Lq, Lk, scale, _stream())
+    _l.check(st, "fx_fmha_fwd")
+    return out
+
+
+def patchify(srcs: Sequence[torch.Tensor], chan_last: Sequence[bool], F: int, H: int, W: int,
+             rows: torch.Tensor) -> torch.Tensor:
+    n = len(srcs)
+    ptrs = (C.c_void_p * n)(*[s.data_ptr() for s in srcs])
+    chans, cl = [], []
+    for s, last in zip(srcs, chan_last):
+        _req(s, bf16, "patchify.src", inner_contig=False)
+        if not s.is_contiguous():
+            raise _l.FlexamNativeError("patchify: sources must be contiguous")
+        chans.append(s.shape[-1] if last else s.shape[0])
+        cl.append(1 if last else 0)
+    _req(rows, bf16, "patchify.rows")
+    st = _l.load().fx_patchify(ptrs, (C.c_int * n)(*chans), (C.c_int * n)(*cl), n, F, H, W, _p(rows), rows.stride(0),
+                               _stream())
+    _l.check(st, "fx_patchify")
+    return rows
+
+
+def unpatchify(head: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """head: bf16 [tokens, >=4C] view; out: bf16 [C, F, H, W] contiguous."""
+    _req(head, bf16, "unpatchify.head"), _req(out, bf16, "unpatchify.out")
+    Cc, F, H, W = out.shape
+    _l.check(_l.load().fx_unpatchify(_p(head), head.stride(0), _p(out), Cc, F, H, W, _stream()), "fx_unpatchify")
+    return out
+
+
+def sinusoid(t: torch.Tensor, dim: int) -> torch.Tensor:
+    _req(t, f32, "sinusoid.t")
+    out = torch.empty((t.numel(), dim), dtype=f32, device=t.device)
+    _l.check(_l.load().fx_sinusoid(_p(t), _p(out), t.numel(), dim, _stream()), "fx_sinusoid")
+    return out
+
+
+def linear_f32(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act_in: int = 0) -> torch.Tensor:
+    _req(x, f32, "linear_f32.x"), _req(w, bf16, "linear_f32.w")
+    if bias is not None:
+        _req(bias, bf16, "linear_f32.bias")
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=f32, device=x.device)
+    st = _l.load().fx_linear_f32(_p(x), x.stride(0), _p(w), w.stride(0), _p(bias), _p(out), out.stride(0), M, N, K,
+                                 act_in, _stream())
+    _l.check(st, "fx_linear_f32")
+    return out
+
+
+def nchw_to_nhwc(src: torch.Tensor, dst: torch.Tensor, c0: int) -> torch.Tensor:
+    """src: bf16 [C, P] contiguous view; dst: bf16 [P, ld] receives columns [c0, c0+C)."""
+    _req(src, bf16, "nchw_to_nhwc.src"), _req(dst, bf16, "nchw_to_nhwc.dst")
+    Cc, P = src.shape
+    _l.check(_l.load().fx_nchw_to_nhwc(_p(src), _p(dst), dst.stride(0), c0, Cc, P, _stream()), "fx_nchw_to_nhwc")
+    return dst
+
+
+def im2col3x3(x: torch.Tensor, F: int, H: int, W: int, rows: torch.Tensor) -> torch.Tensor:
+    _req(x, bf16, "im2col3x3.x"), _req(rows, bf16, "im2col3x3.rows")
+    Cc = x.shape[-1]
+    _l.check(_l.load().fx_im2col3x3(_p(x), _p(rows), F, H, W, Cc, _stream()), "fx_im2col3x3")
+    return rows
+
+
+def groupnorm_silu(x: torch.Tensor, groups: int, eps: float, gamma: torch.Tensor, beta: torch.Tensor,
+                   resid: Optional[torch.Tensor], y_f32: Optional[torch.Tensor], y_bf16: Optional[torch.Tensor],
+                   stats: torch.Tensor) -> None:
+    _req(x, bf16, "groupnorm_silu.x")
+    P, Cc = x.shape
+    st = _l.load().fx_groupnorm_silu(_p(x), P, Cc, groups, eps, _p(gamma), _p(beta), _p(resid), _p(y_f32), _p(y_bf16),
+                                     _p(stats), _stream())
+    _l.check(st, "fx_groupnorm_silu")
+
+
+def cfg_euler_step(vu: torch.Tensor, vc: torch.Tensor, guidance: float, dsigma: float, lat: torch.Tensor,
+                   mask: Optional[torch.Tensor], pinned: Optional[torch.Tensor]) -> torch.Tensor:
+    _req(vu, bf16, "cfg_euler_step.vu"), _req(vc, bf16, "cfg_euler_step.vc"), _req(lat, f32, "cfg_euler_step.lat")
+    st = _l.load().fx_cfg_euler_step(_p(vu), _p(vc), guidance, dsigma, _p(lat), _p(mask), _p(pinned), lat.numel(),
+                                     _stream())
+    _l.check(st, "fx_cfg_euler_step")
+    return lat

@@ -1,0 +1,154 @@
+/*
+ * flexam_b200 — C ABI of the B200-native (sm_100a) FlexAM denoising-step operators.
+ *
+ * One shared library (flexam_b200/csrc/libflexam_b200.so) exports exactly these entry points. They are
+ * what a binding of the reference's hot path (FlexAM/models/wan_transformer3d_FlexAM.py, cited per
+ * function as file:line relative to the reference root) calls instead of torch/cuBLAS/cuDNN/flash-attn.
+ *
+ * Conventions
+ *   - plain pointers to DEVICE memory + sizes; no torch types, no allocation, no synchronisation and no
+ *     ownership transfer inside the library. The caller owns every buffer and passes the CUDA stream
+ *     (a cudaStream_t cast to void*; NULL = legacy default stream).
+ *   - "bf16" buffers are uint16 storage of bfloat16; "f32" are float.
+ *   - every function returns FX_OK (0) or a negative FX_ERR_* code; fx_last_error() gives the text.
+ *     Launch errors are reported; asynchronous execution errors surface at the caller's next sync.
+ *   - row-major everywhere; `ld*` arguments are leading dimensions in ELEMENTS.
+ */
+#ifndef FLEXAM_B200_H_
+#define FLEXAM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FX_OK 0
+#define FX_ERR_ARG (-1)   /* bad pointer / size / alignment / unsupported shape */
+#define FX_ERR_CUDA (-2)  /* CUDA runtime or driver error at launch time */
+#define FX_ERR_ARCH (-3)  /* device is not sm_100 */
+
+#define FX_ABI_VERSION 1
+
+int fx_abi_version(void);
+const char* fx_last_error(void);
+/* FX_OK when `device` is a compute-capability 10.x part this library was built for. */
+int fx_check_device(int device);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Dense projection on tcgen05/TMEM (replaces every nn.Linear on the path: self_attn.{q,k,v,o} :242-261,
+ * cross_attn.{q,k,v,o} :363-370, ffn :414-416,467, head.head :506, text_embedding :959-964, and the
+ * patch/ref/CNN convolutions once their input is gathered into rows :885,896,874-880).
+ *
+ *   acc[m,n] = sum_k A[m,k] * W[n,k]          A: bf16 [M,K] (lda), W: bf16 [N,K] (ldw) = nn.Linear.weight
+ *   y        = bf16_round(acc + bias[n])      bias: bf16 [N] or NULL  (one rounding, like the autocast Linear)
+ *
+ * epilogue:
+ *   FX_EPI_BF16        out bf16 [M,N] (ldo)  = y
+ *   FX_EPI_GELU_BF16   out bf16              = bf16(gelu_tanh(y))                     (ffn.1 :415)
+ *   FX_EPI_F32         out f32               = float(y)                               (patch embed -> fp32 stream)
+ *   FX_EPI_RESID_F32   out f32 (in/out)     += y * gate[m,n]                          (x + y*e[2], x + y*e[5] :456,468;
+ *                      gate[m,n] = gate_mod[n] + gate_e[row_idx[m]*gate_e_stride + n]   x + cross_attn :461 with no gate)
+ *                      gate_mod/gate_e NULL -> that term is 0; both NULL -> gate = 1; row_idx NULL -> row 0.
+ * Requirements: K % 8 == 0, N % 8 == 0, lda/ldw % 8 == 0, 16-byte aligned bases.
+ */
+#define FX_EPI_BF16 0
+#define FX_EPI_GELU_BF16 1
+#define FX_EPI_F32 2
+#define FX_EPI_RESID_F32 3
+int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* out, int64_t ldo,
+                 int M, int N, int K, int epilogue, const float* gate_mod, const float* gate_e,
+                 int64_t gate_e_stride, const int32_t* row_idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * LayerNorm (no affine, eps) + adaLN modulation + density shift, fp32 in -> bf16 out
+ * (WanAttentionBlock :444-453, :464-465; Head :493-507):
+ *   out[m,:] = LN(x[m,:]) * (1 + scale_mod[:] + scale_e[u,:]) + shift_mod[:] + shift_e[u,:] + dens[b,:]
+ *   u = row_idx[m] (NULL -> 0), b = m / rows_per_batch.  scale_e/shift_e rows are e_stride floats apart,
+ *   dens rows dens_stride floats apart (dens may be NULL).
+ * fx_ln_affine: out = LN(x) * gamma + beta  (norm3 :405-407,461), gamma/beta bf16 [D].
+ * D % 256 == 0, D <= 8192.
+ */
+int fx_ln_modulate(const float* x, void* out, int M, int D, float eps, const float* shift_mod,
+                   const float* scale_mod, const float* shift_e, const float* scale_e, int64_t e_stride,
+                   const int32_t* row_idx, const float* dens, int64_t dens_stride, int rows_per_batch,
+                   void* stream);
+int fx_ln_affine(const float* x, void* out, int M, int D, float eps, const void* gamma, const void* beta,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Full-width RMSNorm (+ optional 3-axis RoPE), in place on bf16 rows (WanRMSNorm :173-189 applied to the
+ * whole D-wide row :242-243,363-364; rope_apply :135-164).
+ *   r      = bf16(rsqrt(mean_D(x^2) + eps));  x = bf16(bf16(x * r) * w[:])
+ *   rope (freqs != NULL): per head of 128, adjacent pairs (2j,2j+1) rotated by freqs[pos(j)][j] where
+ *   pos = frame for j<22, row for 22<=j<43, col for j>=43 of token t = tok_offset + (m % rows_per_batch);
+ *   frame/row/col from t over the grid (gf,gh,gw); tokens >= gf*gh*gw are left unrotated.
+ *   freqs: f32 [1024][64][2] (cos,sin).  x: bf16 [M, D] with row stride ldx.  D % 256 == 0, head_dim 128.
+ */
+int fx_rmsnorm_rope(void* x, int64_t ldx, int M, int D, float eps, const void* weight, const float* freqs,
+                    int gf, int gh, int gw, int tok_offset, int rows_per_batch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Non-causal attention forward on tcgen05/TMEM, head_dim 128 (attention()/flash_attention,
+ * FlexAM/models/attention_utils.py:174-233; call sites :251-256 and :367):
+ *   o[b,i,h,:] = softmax_j(q[b,i,h,:].k[b,j,h,:] * scale) v[b,j,h,:],  j < Lk
+ * q/k/v/o: bf16, element (b,i,h,d) at base + b*stride_b + i*stride_l + h*128 + d  (strides in elements,
+ * multiples of 8). This matches [B,L,H,128] views of the packed projection outputs.
+ */
+int fx_fmha_fwd(const void* q, int64_t q_stride_b, int64_t q_stride_l, const void* k, int64_t k_stride_b,
+                int64_t k_stride_l, const void* v, int64_t v_stride_b, int64_t v_stride_l, void* o,
+                int64_t o_stride_b, int64_t o_stride_l, int B, int H, int Lq, int Lk, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Front end (patch_embedding Conv3d k=s=(1,2,2) :624-625,885; ref_conv Conv2d k=s=2 :675-678,896):
+ * gathers 2x2 patches into GEMM rows, K order (c, q, r) = weight.flatten(1).
+ *   src k: bf16, channel-major [C_k, F, H, W] (chan_last_k = 0) or channel-last [F, H, W, C_k] (1), k < nsrc <= 4;
+ *   rows[(f*H/2 + h)*W/2 + w][(c*2 + q)*2 + r] = cat_k(src_k)[c][f][2h+q][2w+r];  rows: bf16 [F*H/2*W/2, ldr]
+ */
+int fx_patchify(const void* const* src, const int* channels, const int* chan_last, int nsrc, int F, int H, int W,
+                void* rows, int64_t ldr, void* stream);
+/* unpatchify :1126-1149 (+ ref strip :1106-1109): out[c][f][2h+q][2w+r] = head[tok(f,h,w)][(q*2+r)*C + c];
+ * head: bf16 [F*H/2*W/2, ldh] (already offset past the ref tokens), out: bf16 [C, F, H, W]. */
+int fx_unpatchify(const void* head, int64_t ldh, void* out, int C, int F, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * fp32 embedding MLPs (sinusoidal_embedding_1d :31-41; time_embedding/time_projection :630-632,928-944;
+ * density_embedding/projection :634-636,951-955). Computed on the de-duplicated timesteps only.
+ *   fx_sinusoid: out f32 [n, dim] = [cos(t*f_j) | sin(t*f_j)], f_j = 10000^(-j/(dim/2)), evaluated in fp64.
+ *   fx_linear_f32: out f32 [M,N] = act_in(in f32 [M,K]) @ W[N,K]^T (bf16 weights up-cast) + bias; fp32 accumulate.
+ *                  act_in: 0 none, 1 SiLU.  K % 8 == 0.
+ */
+int fx_sinusoid(const float* t, float* out, int n, int dim, void* stream);
+int fx_linear_f32(const float* in, int64_t ldi, const void* w, int64_t ldw, const void* bias, float* out,
+                  int64_t ldo, int M, int N, int K, int act_in, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * CNN control fuser pieces (cnn_conv1..5 :680-711,868-881). Activations are channel-last [P, C] with
+ * P = F*H*W pixels of one sample; convs run as fx_gemm_bf16 over fx_im2col3x3 rows.
+ *   fx_nchw_to_nhwc: dst bf16 [P, ldd] columns [c0, c0+C) = src bf16 [C, P]
+ *   fx_im2col3x3   : rows bf16 [P, 9*C], column (c*3+kh)*3+kw = in[f, y+kh-1, x+kw-1, c] (zero padded per frame)
+ *   fx_groupnorm_silu: y = SiLU(GroupNorm_G(x; gamma, beta, eps)) (+ resid), stats over all pixels of the sample;
+ *                    x bf16 [P, C] (conv output), y_f32 [P, C] and y_bf16 [P, C] (either may be NULL),
+ *                    resid f32 [P, C] or NULL; stats: f32 workspace [2*G].
+ */
+int fx_nchw_to_nhwc(const void* src, void* dst, int64_t ldd, int c0, int C, int64_t P, void* stream);
+int fx_im2col3x3(const void* in, void* rows, int F, int H, int W, int C, void* stream);
+int fx_groupnorm_silu(const void* x, int64_t P, int C, int G, float eps, const void* gamma, const void* beta,
+                      const float* resid, float* y_f32, void* y_bf16, float* stats, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Sampler glue (pipeline_wan2_2_fun_control_FlexAM.py:926-934): CFG combine + Euler flow step + first-frame
+ * re-pin in one pass:  v = vu + s*(vc - vu);  lat = lat + dsigma*v;  lat = (1-mask)*pinned + mask*lat.
+ *   vu, vc, pinned: bf16 [n]; lat: f32 [n] in/out; mask: f32 [n] or NULL.
+ */
+int fx_cfg_euler_step(const void* vu, const void* vc, float guidance, float dsigma, float* lat, const float* mask,
+                      const void* pinned, int64_t n, void* stream);
+
+/* Small utility kernels used by the host glue. */
+int fx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+int fx_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLEXAM_B200_H_ */
