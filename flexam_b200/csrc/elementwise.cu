@@ -28,6 +28,7 @@ struct LnParams {
   const float* scale_e;
   long long e_stride;
   const int* row_idx;
+  const float* dens_mod;
   const float* dens;
   long long dens_stride;
   int rows_per_batch;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(256) ln_kernel(const LnParams p) {
     const float4* dn =
         p.dens ? reinterpret_cast<const float4*>(p.dens + static_cast<long long>(row / p.rows_per_batch) * p.dens_stride)
                : nullptr;
+    const float4* dm = reinterpret_cast<const float4*>(p.dens_mod);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = i * 32 + lane;
@@ -80,7 +82,11 @@ __global__ void __launch_bounds__(256) ln_kernel(const LnParams p) {
       y.z = (v[i].z - mean) * rstd * sc.z + sh.z;
       y.w = (v[i].w - mean) * rstd * sc.w + sh.w;
       if (dn != nullptr) {
-        const float4 d = __ldg(dn + c);
+        float4 d = __ldg(dn + c);
+        if (dm != nullptr) {
+          const float4 m = __ldg(dm + c);
+          d.x += m.x; d.y += m.y; d.z += m.z; d.w += m.w;
+        }
         y.x += d.x; y.y += d.y; y.z += d.z; y.w += d.w;
       }
       uint2 o;
@@ -246,8 +252,8 @@ static int ew_grid(long long n) {
 
 extern "C" int fx_ln_modulate(const float* x, void* out, int M, int D, float eps, const float* shift_mod,
                               const float* scale_mod, const float* shift_e, const float* scale_e, int64_t e_stride,
-                              const int32_t* row_idx, const float* dens, int64_t dens_stride, int rows_per_batch,
-                              void* stream) {
+                              const int32_t* row_idx, const float* dens_mod, const float* dens, int64_t dens_stride,
+                              int rows_per_batch, void* stream) {
   using namespace fx;
   FX_CHECK_ARG(x && out && shift_mod && scale_mod && shift_e && scale_e, "fx_ln_modulate: null pointer");
   FX_CHECK_ARG(M > 0 && D > 0 && D % 128 == 0, "fx_ln_modulate: bad shape M=%d D=%d", M, D);
@@ -255,7 +261,7 @@ extern "C" int fx_ln_modulate(const float* x, void* out, int M, int D, float eps
   LnParams p{};
   p.x = x; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.M = M; p.D = D; p.eps = eps;
   p.shift_mod = shift_mod; p.scale_mod = scale_mod; p.shift_e = shift_e; p.scale_e = scale_e;
-  p.e_stride = e_stride; p.row_idx = row_idx; p.dens = dens; p.dens_stride = dens_stride;
+  p.e_stride = e_stride; p.row_idx = row_idx; p.dens_mod = dens_mod; p.dens = dens; p.dens_stride = dens_stride;
   p.rows_per_batch = rows_per_batch;
   return launch_ln<0>(p, reinterpret_cast<cudaStream_t>(stream), "fx_ln_modulate");
 }

@@ -21,7 +21,7 @@ SIGNATURES = {
     "fx_abi_version": [],
     "fx_check_device": [_i],
     "fx_gemm_bf16": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _i64, _vp, _vp],
-    "fx_ln_modulate": [_vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i, _vp],
+    "fx_ln_modulate": [_vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp],
     "fx_ln_affine": [_vp, _vp, _i, _i, _f, _vp, _vp, _vp],
     "fx_rmsnorm_rope": [_vp, _i64, _i, _i, _f, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fx_fmha_fwd": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _f, _vp],

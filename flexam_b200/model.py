@@ -1,0 +1,505 @@
+"""Host-side mirror of the reference transformer interface, backed only by the C-ABI kernels.
+
+``Wan2_2Transformer3DModel_FlexAM`` here has the reference's constructor kwargs, parameter tree (state_dict keys
+and shapes), ``forward(x, t, context, seq_len, clip_fea, y, y_camera, full_ref, subject_ref,
+cond_flag, additional_control, density)`` signature and feature toggles
+(FlexAM/models/wan_transformer3d_FlexAM.py:526-1123, :1335-1438), but its forward is ``NativeEngine.forward``: a
+fixed sequence of ``fx_*`` launches on the caller's stream. ``install(module)`` rebinds the forward of an existing
+reference module instance the same way the reference's own ``enable_multi_gpus_inference`` does (:801-815).
+
+There is no torch/cuDNN/flash-attn compute on this path and no CPU fallback: torch provides device buffers,
+views and streams. Parameter packing (q|k|v concatenation, conv-weight flattening, fp32 copies of the modulation
+rows) happens once per weight version and is re-done if a parameter is edited in place (LoRA merge).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .lib import FX_EPI_BF16, FX_EPI_F32, FX_EPI_GELU_BF16, FX_EPI_RESID_F32, FlexamNativeError
+
+bf16, f32, i32 = torch.bfloat16, torch.float32, torch.int32
+
+
+# ----------------------------------------------------------------------------------------------------------
+# parameter tree (names / shapes of the reference state_dict)
+# ----------------------------------------------------------------------------------------------------------
+def param_shapes(cfg: dict) -> Dict[str, tuple]:
+    D, Fd = cfg["dim"], cfg["ffn_dim"]
+    pt, ph, pw = cfg["patch_size"]
+    out: Dict[str, tuple] = {}
+
+    def lin(p, o, i):
+        out[p + ".weight"] = (o, i)
+        out[p + ".bias"] = (o,)
+
+    out["patch_embedding.weight"] = (D, cfg["in_dim"], pt, ph, pw)
+    out["patch_embedding.bias"] = (D,)
+    lin("text_embedding.0", D, cfg["text_dim"]), lin("text_embedding.2", D, D)
+    lin("time_embedding.0", D, cfg["freq_dim"]), lin("time_embedding.2", D, D)
+    lin("time_projection.1", 6 * D, D)
+    lin("density_embedding.0", D, cfg["freq_dim"]), lin("density_embedding.2", D, D)
+    lin("density_projection.1", 2 * D, D)
+    for i in range(cfg["num_layers"]):
+        b = f"blocks.{i}."
+        out[b + "modulation"] = (1, 6, D)
+        out[b + "modulation_density"] = (1, 2, D)
+        for att in ("self_attn", "cross_attn"):
+            for nm in "qkvo":
+                lin(b + f"{att}.{nm}", D, D)
+            out[b + f"{att}.norm_q.weight"] = (D,)
+            out[b + f"{att}.norm_k.weight"] = (D,)
+        out[b + "norm3.weight"] = (D,)
+        out[b + "norm3.bias"] = (D,)
+        lin(b + "ffn.0", Fd, D), lin(b + "ffn.2", D, Fd)
+    lin("head.head", cfg["out_dim"] * pt * ph * pw, D)
+    out["head.modulation"] = (1, 2, D)
+    out["head.modulation_density"] = (1, 1, D)
+    out["ref_conv.weight"] = (D, cfg["in_dim_ref_conv"], ph, pw)
+    out["ref_conv.bias"] = (D,)
+    for j, (ci, co) in enumerate([(cfg["in_dim_cnn_block"], 192), (192, 192), (192, 96), (96, 96)], start=1):
+        out[f"cnn_conv{j}.0.weight"] = (co, ci, 1, 3, 3)
+        out[f"cnn_conv{j}.0.bias"] = (co,)
+        out[f"cnn_conv{j}.1.weight"] = (co,)
+        out[f"cnn_conv{j}.1.bias"] = (co,)
+    out["cnn_conv5.weight"] = (cfg["out_dim_cnn_block"], 96, 1, 1, 1)
+    out["cnn_conv5.bias"] = (cfg["out_dim_cnn_block"],)
+    return out
+
+
+def rope_table(head_dim: int, theta: float = 10000.0, max_len: int = 1024, riflex: Optional[dict] = None) -> torch.Tensor:
+    """fp32 [max_len, head_dim/2, 2] (cos, sin), from the float64 construction of rope_params (:44-52, :655-665);
+    RIFLEx (:56-113, :774-788) changes one temporal frequency."""
+    d = head_dim
+    cols = []
+    for axis, dim in enumerate((d - 4 * (d // 6), 2 * (d // 6), 2 * (d // 6))):
+        inv = 1.0 / torch.pow(theta, torch.arange(0, dim, 2, dtype=torch.float64) / dim)
+        if axis == 0 and riflex is not None:
+            k = riflex["k"]
+            inv[k - 1] = 0.9 * 2 * math.pi / riflex["L_test"]
+            if riflex.get("L_test_scale") is not None:
+                inv[k - 1] = inv[k - 1] / riflex["L_test_scale"]
+        cols.append(torch.outer(torch.arange(max_len, dtype=torch.float64), inv))
+    ang = torch.cat(cols, dim=1)
+    return torch.stack([ang.cos(), ang.sin()], dim=-1).to(f32).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# the engine: packed weights + workspaces + the launch sequence
+# ----------------------------------------------------------------------------------------------------------
+class NativeEngine:
+    """Runs the denoising step for a parameter mapping with the reference's state_dict keys (bf16, on one GPU)."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], cfg: dict, device: torch.device):
+        self.cfg = dict(cfg)
+        self.device = torch.device(device)
+        self.params = params
+        self.D = cfg["dim"]
+        self.H = cfg["num_heads"]
+        if self.D // self.H != 128:
+            raise FlexamNativeError(f"native path supports head_dim 128 only (dim {self.D}, heads {self.H})")
+        self.eps = float(cfg["eps"])
+        self.freqs = rope_table(128).to(self.device)
+        self.sp_group = None           # set by flexam_b200.dist for Ulysses sequence parallelism
+        self.cache_static = True       # hoist step-invariant work (context, cross K/V, CNN fuser) across calls
+        self._static_key = None
+        self._static = {}
+        self._ws = {}
+        self._versions = None
+        self.launches = 0              # kernels launched by the last forward (bench.py reports it)
+        self._pack()
+
+    # -- weights -------------------------------------------------------------------------------------------
+    def _pvers(self):
+        return tuple(p._version for p in self.params.values())
+
+    def _pack(self):
+        P, D, dev = self.params, self.D, self.device
+        for k, v in P.items():
+            if v.device != dev or v.dtype != bf16:
+                raise FlexamNativeError(f"parameter {k}: expected bf16 on {dev}, got {v.dtype} on {v.device}")
+        L = self.cfg["num_layers"]
+        self.blk = []
+        for i in range(L):
+            b = f"blocks.{i}."
+            sa, ca = b + "self_attn.", b + "cross_attn."
+            w = {
+                "wqkv": torch.cat([P[sa + "q.weight"], P[sa + "k.weight"], P[sa + "v.weight"]], 0).contiguous(),
+                "bqkv": torch.cat([P[sa + "q.bias"], P[sa + "k.bias"], P[sa + "v.bias"]], 0).contiguous(),
+                "wo": P[sa + "o.weight"], "bo": P[sa + "o.bias"],
+                "nq": P[sa + "norm_q.weight"], "nk": P[sa + "norm_k.weight"],
+                "n3w": P[b + "norm3.weight"], "n3b": P[b + "norm3.bias"],
+                "cwq": P[ca + "q.weight"], "cbq": P[ca + "q.bias"],
+                "cwkv": torch.cat([P[ca + "k.weight"], P[ca + "v.weight"]], 0).contiguous(),
+                "cbkv": torch.cat([P[ca + "k.bias"], P[ca + "v.bias"]], 0).contiguous(),
+                "cwo": P[ca + "o.weight"], "cbo": P[ca + "o.bias"],
+                "cnq": P[ca + "norm_q.weight"], "cnk": P[ca + "norm_k.weight"],
+                "w1": P[b + "ffn.0.weight"], "b1": P[b + "ffn.0.bias"],
+                "w2": P[b + "ffn.2.weight"], "b2": P[b + "ffn.2.bias"],
+                "mod": P[b + "modulation"][0].to(f32).contiguous(),            # [6, D]
+                "dmod": P[b + "modulation_density"][0].to(f32).contiguous(),   # [2, D]
+            }
+            self.blk.append(w)
+        self.w_patch = P["patch_embedding.weight"].flatten(1).contiguous()     # [D, in_dim*4], K order (c,q,r)
+        self.w_ref = P["ref_conv.weight"].flatten(1).contiguous()
+        self.w_cnn = [P[f"cnn_conv{j}.0.weight"].flatten(1).contiguous() for j in range(1, 5)]  # [Co, Ci*9] (c,kh,kw)
+        self.w_cnn5 = P["cnn_conv5.weight"].flatten(1).contiguous()
+        self.head_mod = P["head.modulation"][0].to(f32).contiguous()           # [2, D]
+        self.head_dmod = P["head.modulation_density"][0, 0].to(f32).contiguous()
+        self._versions = self._pvers()
+        self._static_key = None
+
+    def refresh_if_modified(self):
+        if self._pvers() != self._versions:
+            self._pack()
+
+    # -- buffers -------------------------------------------------------------------------------------------
+    def _buf(self, name: str, shape: Sequence[int], dtype) -> torch.Tensor:
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None:
+            for k in [k for k in self._ws if k[0] == name]:
+                del self._ws[k]
+            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            self._ws[key] = t
+        return t
+
+    def _gemm(self, *a, **k):
+        self.launches += 1
+        return ops.gemm(*a, **k)
+
+    # -- stages --------------------------------------------------------------------------------------------
+    def _embed_mlp(self, pe: str, pp: str, values: torch.Tensor):
+        """fp32 sinusoid -> Linear -> SiLU -> Linear (= e) -> SiLU -> Linear (= e0) on `values` [n]. (:928-955)"""
+        P = self.params
+        emb = ops.sinusoid(values, self.cfg["freq_dim"])
+        h = ops.linear_f32(emb, P[pe + ".0.weight"], P[pe + ".0.bias"], 0)
+        e = ops.linear_f32(h, P[pe + ".2.weight"], P[pe + ".2.bias"], 1)
+        e0 = ops.linear_f32(e, P[pp + ".1.weight"], P[pp + ".1.bias"], 1)
+        self.launches += 4
+        return e, e0
+
+    def _cnn_fuser(self, y_ctrl0: torch.Tensor, add: torch.Tensor) -> torch.Tensor:
+        """cnn_conv1..5 (:868-880) for one sample; inputs [48,F,H,W] and [240,F,H,W] bf16 -> channel-last [P, 48]."""
+        P = self.params
+        C0, F, H, W = y_ctrl0.shape
+        C1 = add.shape[0]
+        npix = F * H * W
+        act = self._buf("cnn_in", (npix, C0 + C1), bf16)
+        ops.nchw_to_nhwc(y_ctrl0.reshape(C0, npix), act, 0)
+        ops.nchw_to_nhwc(add.reshape(C1, npix), act, C0)
+        self.launches += 2
+        stats = self._buf("cnn_stats", (64,), f32)
+        resid = None
+        for j, (groups, keep) in enumerate([(24, True), (24, False), (12, True), (12, False)]):
+            cin = act.shape[1]
+            wj = self.w_cnn[j]
+            cout = wj.shape[0]
+            rows = self._buf("cnn_rows", (npix, 9 * cin), bf16)
+            ops.im2col3x3(act, F, H, W, rows)
+            conv = self._buf(f"cnn_conv{j}", (npix, cout), bf16)
+            self._gemm(rows, wj, P[f"cnn_conv{j + 1}.0.bias"], conv, FX_EPI_BF16)
+            nxt = self._buf(f"cnn_act{j}", (npix, cout), bf16)
+            keep_f32 = self._buf(f"cnn_f32_{j}", (npix, cout), f32) if keep else None
+            # x2 = S(GN(conv2(x1))) + x1 and x4 = S(GN(conv4(x3))) + x3 take the previous stage's fp32 output
+            ops.groupnorm_silu(conv, groups, 1e-5, P[f"cnn_conv{j + 1}.1.weight"], P[f"cnn_conv{j + 1}.1.bias"],
+                               None if keep else resid, keep_f32, nxt, stats)
+            self.launches += 3
+            resid = keep_f32
+            act = nxt
+        out = torch.empty((npix, self.w_cnn5.shape[0]), dtype=bf16, device=self.device)
+        self._gemm(act, self.w_cnn5, P["cnn_conv5.bias"], out, FX_EPI_BF16)
+        return out
+
+    def _context(self, context: List[torch.Tensor]) -> torch.Tensor:
+        """zero-pad to text_len, text_embedding MLP (:958-964) -> [B*text_len, D] bf16."""
+        P, T = self.params, self.cfg["text_len"]
+        B = len(context)
+        padded = torch.zeros((B * T, self.cfg["text_dim"]), dtype=bf16, device=self.device)
+        for b, u in enumerate(context):
+            if u.shape[0] > T:
+                raise FlexamNativeError(f"context {b} longer than text_len {T}")
+            padded[b * T: b * T + u.shape[0]].copy_(u)
+        h = torch.empty((B * T, self.D), dtype=bf16, device=self.device)
+        self._gemm(padded, P["text_embedding.0.weight"], P["text_embedding.0.bias"], h, FX_EPI_GELU_BF16)
+        ctx = torch.empty((B * T, self.D), dtype=bf16, device=self.device)
+        self._gemm(h, P["text_embedding.2.weight"], P["text_embedding.2.bias"], ctx, FX_EPI_BF16)
+        return ctx
+
+    def _cross_kv(self, ctx: torch.Tensor) -> List[torch.Tensor]:
+        """Per-layer cross-attention K (RMS-normed) | V of the context (:364-365): step-invariant."""
+        out = []
+        for w in self.blk:
+            kv = torch.empty((ctx.shape[0], 2 * self.D), dtype=bf16, device=self.device)
+            self._gemm(ctx, w["cwkv"], w["cbkv"], kv, FX_EPI_BF16)
+            ops.rmsnorm_rope(kv[:, : self.D], w["cnk"], self.eps)
+            self.launches += 1
+            out.append(kv)
+        return out
+
+    @staticmethod
+    def _ident(ts) -> tuple:
+        return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
+
+    # -- the denoising step ----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, t, context, seq_len, y, full_ref, additional_control, density,
+                block_hook=None) -> torch.Tensor:
+        """Returns the stacked prediction [B, out_dim, F, H, W] in bf16 (forward :817-1123)."""
+        cfg, D, dev = self.cfg, self.D, self.device
+        self.refresh_if_modified()
+        self.launches = 0
+        if y is None or full_ref is None or additional_control is None or density is None:
+            raise FlexamNativeError("the FlexAM path needs y, full_ref, additional_control and density")
+        C = cfg["out_dim"]
+        x = x.to(dev, bf16).contiguous()
+        y = y.to(dev, bf16).contiguous()
+        add = additional_control.to(dev, bf16).contiguous()
+        full_ref = full_ref.to(dev, bf16).contiguous()
+        context = [u.to(dev, bf16) for u in context]
+        B, _, F, Hh, Ww = x.shape
+        Hp, Wp = Hh // 2, Ww // 2
+        L0 = F * Hp * Wp
+        R = Hp * Wp
+        L = L0 + R
+        if seq_len != L0:
+            raise FlexamNativeError(f"seq_len {seq_len} != tokens on the grid {L0} (padding is handled by the SP layer)")
+        grid = (F + 1, Hp, Wp)
+        M = B * L
+
+        # ---- step-invariant work: control fuser, context embedding, cross-attention K/V ----------------------
+        skey = (self._ident([y, add]), self._ident(context))
+        if not (self.cache_static and self._static_key == skey):
+            st = {}
+            st["cnn"] = [self._cnn_fuser(y[b, :C], add[b]) for b in range(B)]
+            st["ctx"] = self._context(context)
+            st["kv"] = self._cross_kv(st["ctx"])
+            self._static, self._static_key = st, skey
+        st = self._static
+
+        # ---- patch + ref embedding straight into the fp32 residual stream (:885-899) --------------------------
+        xs = self._buf("x", (M, D), f32)
+        rows = self._buf("patch_rows", (L0, self.w_patch.shape[1]), bf16)
+        rrows = self._buf("ref_rows", (R, self.w_ref.shape[1]), bf16)
+        for b in range(B):
+            ops.patchify([x[b], st["cnn"][b].view(F, Hh, Ww, -1), y[b, C:]], [False, True, False], F, Hh, Ww, rows)
+            self._gemm(rows, self.w_patch, self.params["patch_embedding.bias"], xs[b * L + R: (b + 1) * L], FX_EPI_F32)
+            ops.patchify([full_ref[b].unsqueeze(1)], [False], 1, Hh, Ww, rrows)
+            self._gemm(rrows, self.w_ref, self.params["ref_conv.bias"], xs[b * L: b * L + R], FX_EPI_F32)
+            self.launches += 2
+
+        # ---- timestep / density embeddings on the distinct timesteps (:900-955) ------------------------------
+        t = t.to(dev, f32)
+        if t.dim() == 2:
+            if t.shape[1] < L:   # ref tokens are PREPENDED and take the last token's timestep (:900-904)
+                t = torch.cat([t[:, -1:].expand(B, L - t.shape[1]), t], dim=1)
+            uniq, inv = torch.unique(t.reshape(-1), return_inverse=True)
+            row_idx = inv.to(i32).contiguous()
+        else:
+            uniq = t.contiguous()
+            row_idx = torch.arange(B, device=dev, dtype=i32).repeat_interleave(L).contiguous()
+        e, e0 = self._embed_mlp("time_embedding", "time_projection", uniq.contiguous())          # [U,D], [U,6D]
+        de, de0 = self._embed_mlp("density_embedding", "density_projection", density.to(dev, f32).contiguous())
+
+        # ---- 30 x WanAttentionBlock (:422-472) ---------------------------------------------------------------
+        h = self._buf("h", (M, D), bf16)
+        qkv = self._buf("qkv", (M, 3 * D), bf16)
+        attn = self._buf("attn", (M, D), bf16)
+        cq = self._buf("cq", (M, D), bf16)
+        ffn = self._buf("ffn", (M, cfg["ffn_dim"]), bf16)
+        T = cfg["text_len"]
+        scale = 1.0 / math.sqrt(128.0)
+        qkv5 = qkv.view(B, L, 3, self.H, 128)
+        attn4 = attn.view(B, L, self.H, 128)
+        cq4 = cq.view(B, L, self.H, 128)
+        e0v = e0.view(-1, 6, D)
+        de0v = de0.view(B, 2, D)
+        for i, w in enumerate(self.blk):
+            mod, dmod = w["mod"], w["dmod"]
+            # self-attention
+            ops.ln_modulate(xs, h, self.eps, mod[0], mod[1], e0v[:, 0], e0v[:, 1], 6 * D, row_idx, dmod[0],
+                            de0v[:, 0], 2 * D, L)
+            self._gemm(h, w["wqkv"], w["bqkv"], qkv, FX_EPI_BF16)
+            ops.rmsnorm_rope(qkv[:, :D], w["nq"], self.eps, self.freqs, grid, 0, L)
+            ops.rmsnorm_rope(qkv[:, D:2 * D], w["nk"], self.eps, self.freqs, grid, 0, L)
+            if self.sp_group is None:
+                ops.fmha(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], attn4, scale)
+            else:
+                self.sp_group.attention(qkv5, attn4, scale)
+            self._gemm(attn, w["wo"], w["bo"], xs, FX_EPI_RESID_F32, gate_mod=mod[2], gate_e=e0v[:, 2], row_idx=row_idx)
+            # cross-attention (no gate, no RoPE, all text_len slots attended)
+            ops.ln_affine(xs, h, self.eps, w["n3w"], w["n3b"])
+            self._gemm(h, w["cwq"], w["cbq"], cq, FX_EPI_BF16)
+            ops.rmsnorm_rope(cq, w["cnq"], self.eps)
+            kv5 = st["kv"][i].view(B, T, 2, self.H, 128)
+            ops.fmha(cq4, kv5[:, :, 0], kv5[:, :, 1], attn4, scale)
+            self._gemm(attn, w["cwo"], w["cbo"], xs, FX_EPI_RESID_F32)
+            # ffn
+            ops.ln_modulate(xs, h, self.eps, mod[3], mod[4], e0v[:, 3], e0v[:, 4], 6 * D, row_idx, dmod[1],
+                            de0v[:, 1], 2 * D, L)
+            self._gemm(h, w["w1"], w["b1"], ffn, FX_EPI_GELU_BF16)
+            self._gemm(ffn, w["w2"], w["b2"], xs, FX_EPI_RESID_F32, gate_mod=mod[5], gate_e=e0v[:, 5], row_idx=row_idx)
+            self.launches += 8
+            if block_hook is not None:
+                block_hook(i, xs)
+
+        # ---- head (:493-507, uses e not e0) + unpatchify (:1106-1149) -----------------------------------------
+        ops.ln_modulate(xs, h, self.eps, self.head_mod[0], self.head_mod[1], e, e, D, row_idx, self.head_dmod, de, D, L)
+        ho = self._buf("head", (M, self.params["head.head.weight"].shape[0]), bf16)
+        self._gemm(h, self.params["head.head.weight"], self.params["head.head.bias"], ho, FX_EPI_BF16)
+        out = torch.empty((B, C, F, Hh, Ww), dtype=bf16, device=dev)
+        for b in range(B):
+            ops.unpatchify(ho[b * L + R: (b + 1) * L], out[b])
+        self.launches += 1 + B
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# nn.Module with the reference's surface
+# ----------------------------------------------------------------------------------------------------------
+def _set_param(root: nn.Module, dotted: str, p: nn.Parameter):
+    parts = dotted.split(".")
+    m = root
+    for i, name in enumerate(parts[:-1]):
+        if not hasattr(m, name):
+            nxt_is_index = parts[i + 1].isdigit() if i + 1 < len(parts) - 1 else False
+            m.add_module(name, nn.ModuleList() if nxt_is_index else nn.Module())
+        child = getattr(m, name)
+        if isinstance(m, nn.ModuleList):
+            child = m[int(name)]
+        m = child
+    m.register_parameter(parts[-1], p)
+
+
+class _Config(dict):
+    __getattr__ = dict.get
+
+
+class Wan2_2Transformer3DModel_FlexAM(nn.Module):
+    """Drop-in for FlexAM.models.Wan2_2Transformer3DModel_FlexAM (:1335-1438) with a native forward."""
+
+    def __init__(self, model_type="t2v", patch_size=(1, 2, 2), text_len=512, in_dim=16, dim=2048, ffn_dim=8192,
+                 freq_dim=256, text_dim=4096, out_dim=16, num_heads=16, num_layers=32, window_size=(-1, -1),
+                 qk_norm=True, cross_attn_norm=True, eps=1e-6, in_channels=16, hidden_size=2048,
+                 add_control_adapter=False, in_dim_control_adapter=24, downscale_factor_control_adapter=8,
+                 add_ref_conv=False, in_dim_ref_conv=16, add_cnn_block=False, in_dim_cnn_block=96,
+                 out_dim_cnn_block=16, dtype=torch.bfloat16, device=None):
+        super().__init__()
+        if not (add_ref_conv and add_cnn_block and qk_norm and cross_attn_norm) or add_control_adapter:
+            raise FlexamNativeError("native FlexAM path: add_ref_conv, add_cnn_block, qk_norm, cross_attn_norm must be "
+                                    "on and add_control_adapter off (config/wan2.2/wan_civitai_5b_FlexAM.yaml)")
+        if tuple(window_size) != (-1, -1) or tuple(patch_size) != (1, 2, 2):
+            raise FlexamNativeError("native FlexAM path: global attention and patch (1,2,2) only")
+        self.config = _Config(
+            model_type=model_type, patch_size=tuple(patch_size), text_len=text_len, in_dim=in_dim, dim=dim,
+            ffn_dim=ffn_dim, freq_dim=freq_dim, text_dim=text_dim, out_dim=out_dim, num_heads=num_heads,
+            num_layers=num_layers, window_size=tuple(window_size), qk_norm=qk_norm, cross_attn_norm=cross_attn_norm,
+            eps=eps, in_channels=in_channels, hidden_size=hidden_size, add_control_adapter=add_control_adapter,
+            add_ref_conv=add_ref_conv, in_dim_ref_conv=in_dim_ref_conv, add_cnn_block=add_cnn_block,
+            in_dim_cnn_block=in_dim_cnn_block, out_dim_cnn_block=out_dim_cnn_block)
+        for k in ("model_type", "patch_size", "text_len", "in_dim", "dim", "ffn_dim", "freq_dim", "text_dim", "out_dim",
+                  "num_heads", "num_layers", "eps"):
+            setattr(self, k, self.config[k])
+        self.blocks = nn.ModuleList([nn.Module() for _ in range(num_layers)])
+        for name, shape in param_shapes(self.config).items():
+            _set_param(self, name, nn.Parameter(torch.empty(shape, dtype=dtype, device=device), requires_grad=False))
+        self.d = dim // num_heads
+        self.teacache = None
+        self.cfg_skip_ratio = None
+        self.current_steps = 0
+        self.num_inference_steps = None
+        self.gradient_checkpointing = False
+        self.sp_world_size = 1
+        self.sp_world_rank = 0
+        self._riflex = None
+        self._engine: Optional[NativeEngine] = None
+
+    # -- feature toggles with the reference's names (:730-815) -----------------------------------------------
+    def enable_cfg_skip(self, cfg_skip_ratio, num_steps):
+        self.cfg_skip_ratio = cfg_skip_ratio if cfg_skip_ratio != 0 else None
+        self.current_steps = 0
+        self.num_inference_steps = num_steps if cfg_skip_ratio != 0 else None
+
+    def share_cfg_skip(self, transformer=None):
+        self.cfg_skip_ratio = transformer.cfg_skip_ratio
+        self.current_steps = transformer.current_steps
+        self.num_inference_steps = transformer.num_inference_steps
+
+    def disable_cfg_skip(self):
+        self.cfg_skip_ratio, self.current_steps, self.num_inference_steps = None, 0, None
+
+    def enable_riflex(self, k=6, L_test=66, L_test_scale=4.886):
+        self._riflex = dict(k=k, L_test=L_test, L_test_scale=L_test_scale)
+        if self._engine is not None:
+            self._engine.freqs = rope_table(128, riflex=self._riflex).to(self._engine.device)
+
+    def disable_riflex(self):
+        self._riflex = None
+        if self._engine is not None:
+            self._engine.freqs = rope_table(128).to(self._engine.device)
+
+    def enable_teacache(self, coefficients, num_steps, rel_l1_thresh, num_skip_start_steps=0, offload=True):
+        from .teacache import TeaCache
+        self.teacache = TeaCache(coefficients, num_steps, rel_l1_thresh, num_skip_start_steps, offload)
+
+    def share_teacache(self, transformer=None):
+        self.teacache = transformer.teacache
+
+    def disable_teacache(self):
+        self.teacache = None
+
+    def enable_multi_gpus_inference(self):
+        from . import dist
+        dist.attach(self)
+
+    # -- forward -----------------------------------------------------------------------------------------------
+    def engine(self) -> NativeEngine:
+        if self._engine is None:
+            params = {k: v.data for k, v in self.named_parameters()}
+            dev = next(iter(params.values())).device
+            self._engine = NativeEngine(params, self.config, dev)
+            if self._riflex is not None:
+                self._engine.freqs = rope_table(128, riflex=self._riflex).to(dev)
+        return self._engine
+
+    def forward(self, x, t, context, seq_len, clip_fea=None, y=None, y_camera=None, full_ref=None, subject_ref=None,
+                cond_flag=True, additional_control=None, density=None):
+        return native_forward(self, x, t, context, seq_len, clip_fea, y, y_camera, full_ref, subject_ref, cond_flag,
+                              additional_control, density)
+
+
+def native_forward(self, x, t, context, seq_len, clip_fea=None, y=None, y_camera=None, full_ref=None,
+                   subject_ref=None, cond_flag=True, additional_control=None, density=None):
+    """forward() of the reference (:817-1123) incl. the @cfg_skip wrapper (FlexAM/utils/cfg_optimization.py:5-38)."""
+    if clip_fea is not None or y_camera is not None or subject_ref is not None:
+        raise FlexamNativeError("clip_fea / y_camera / subject_ref are not part of the FlexAM path")
+    bs = len(x)
+    skip = (bs >= 2 and self.cfg_skip_ratio is not None and
+            self.current_steps >= self.num_inference_steps * (1 - self.cfg_skip_ratio))
+    if skip:  # run the cond half only and duplicate it, as the wrapper does
+        h = bs // 2
+        x, t, context, y, full_ref, additional_control, density = (
+            x[h:], t[h:], context[h:], y[h:], full_ref[h:], additional_control[h:], density[h:])
+    eng = self.engine() if hasattr(self, "engine") else self._flexam_engine
+    out = eng.forward(x, t, context, seq_len, y, full_ref, additional_control, density)
+    if skip:
+        out = torch.cat([out, out], dim=0)
+    return out
+
+
+def install(module: nn.Module) -> nn.Module:
+    """Rebind ``module.forward`` (a reference ``Wan2_2Transformer3DModel_FlexAM`` instance, bf16, on a B200) to the
+    native path — the same method-rebinding plug-in pattern the reference uses for USP (:807-815)."""
+    import types
+    params = {k: v.data for k, v in module.named_parameters()}
+    cfg = dict(module.config)
+    cfg.setdefault("in_dim_ref_conv", params["ref_conv.weight"].shape[1])
+    cfg.setdefault("in_dim_cnn_block", params["cnn_conv1.0.weight"].shape[1])
+    cfg.setdefault("out_dim_cnn_block", params["cnn_conv5.weight"].shape[0])
+    module._flexam_engine = NativeEngine(params, cfg, next(iter(params.values())).device)
+    module.forward = types.MethodType(native_forward, module)
+    return module

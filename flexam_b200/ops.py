@@ -62,13 +62,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
 
 def ln_modulate(x: torch.Tensor, out: torch.Tensor, eps: float, shift_mod: torch.Tensor, scale_mod: torch.Tensor,
                 shift_e: torch.Tensor, scale_e: torch.Tensor, e_stride: int, row_idx: Optional[torch.Tensor],
-                dens: Optional[torch.Tensor], dens_stride: int, rows_per_batch: int) -> torch.Tensor:
+                dens_mod: Optional[torch.Tensor], dens: Optional[torch.Tensor], dens_stride: int,
+                rows_per_batch: int) -> torch.Tensor:
     _req(x, f32, "ln_modulate.x"), _req(out, bf16, "ln_modulate.out")
     for n, t in (("shift_mod", shift_mod), ("scale_mod", scale_mod), ("shift_e", shift_e), ("scale_e", scale_e)):
         _req(t, f32, "ln_modulate." + n)
     M, D = x.shape
     st = _l.load().fx_ln_modulate(_p(x), _p(out), M, D, eps, _p(shift_mod), _p(scale_mod), _p(shift_e), _p(scale_e),
-                                  e_stride, _p(row_idx), _p(dens), dens_stride, rows_per_batch, _stream())
+                                  e_stride, _p(row_idx), _p(dens_mod), _p(dens), dens_stride, rows_per_batch,
+                                  _stream())
     _l.check(st, "fx_ln_modulate")
     return out
 

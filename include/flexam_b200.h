@@ -63,16 +63,16 @@ int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const v
 /* ---------------------------------------------------------------------------------------------------------
  * LayerNorm (no affine, eps) + adaLN modulation + density shift, fp32 in -> bf16 out
  * (WanAttentionBlock :444-453, :464-465; Head :493-507):
- *   out[m,:] = LN(x[m,:]) * (1 + scale_mod[:] + scale_e[u,:]) + shift_mod[:] + shift_e[u,:] + dens[b,:]
+ *   out[m,:] = LN(x[m,:]) * (1 + scale_mod[:] + scale_e[u,:]) + shift_mod[:] + shift_e[u,:] + (dens_mod[:] + dens[b,:])
  *   u = row_idx[m] (NULL -> 0), b = m / rows_per_batch.  scale_e/shift_e rows are e_stride floats apart,
- *   dens rows dens_stride floats apart (dens may be NULL).
+ *   dens rows dens_stride floats apart (dens NULL -> no density term; dens_mod may be NULL).
  * fx_ln_affine: out = LN(x) * gamma + beta  (norm3 :405-407,461), gamma/beta bf16 [D].
  * D % 256 == 0, D <= 8192.
  */
 int fx_ln_modulate(const float* x, void* out, int M, int D, float eps, const float* shift_mod,
                    const float* scale_mod, const float* shift_e, const float* scale_e, int64_t e_stride,
-                   const int32_t* row_idx, const float* dens, int64_t dens_stride, int rows_per_batch,
-                   void* stream);
+                   const int32_t* row_idx, const float* dens_mod, const float* dens, int64_t dens_stride,
+                   int rows_per_batch, void* stream);
 int fx_ln_affine(const float* x, void* out, int M, int D, float eps, const void* gamma, const void* beta,
                  void* stream);
 

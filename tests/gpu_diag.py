@@ -89,7 +89,7 @@ def chk_ln():
     dens = torch.randn(B, 2, D, device="cuda", generator=g) * 0.1
     idx = torch.randint(0, U, (M,), device="cuda", generator=g, dtype=torch.int32)
     out = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
-    ops.ln_modulate(x, out, 1e-6, mod[0], mod[1], e[:, 0], e[:, 1], 6 * D, idx, dens[:, 0], 2 * D, M // B)
+    ops.ln_modulate(x, out, 1e-6, mod[0], mod[1], e[:, 0], e[:, 1], 6 * D, idx, None, dens[:, 0], 2 * D, M // B)
     ln = torch.nn.functional.layer_norm(x, (D,), eps=1e-6)
     b = torch.arange(M, device="cuda") // (M // B)
     want = ln * (1 + mod[1] + e[idx.long(), 1]) + mod[0] + e[idx.long(), 0] + dens[b, 0]

@@ -1,0 +1,87 @@
+"""CPU checks that pin the oracle: against the committed golden outputs of the REAL reference module, and against
+the live reference when /root/reference is present (build container only)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flexam_oracle as O
+from oracle import ref_import, synth
+
+
+def _run_oracle(cfg_name, grid, per_tok, policy="fp32", taps=None):
+    cfg = synth.CONFIGS[cfg_name]
+    sd = O.to_torch_sd(synth.state_dict(cfg))
+    inp = synth.inputs(cfg, *grid, per_token_t=per_tok)
+    ctx = [torch.from_numpy(c) for c in inp["context"]]
+    tt = {k: torch.from_numpy(inp[k]) for k in ("x", "y", "additional_control", "full_ref", "t", "density")}
+    with torch.no_grad():
+        return O.forward(sd, cfg, tt["x"], tt["t"], ctx, inp["seq_len"], tt["y"], tt["full_ref"],
+                         tt["additional_control"], tt["density"], policy=policy, taps=taps)
+
+
+def _rel(a, b):
+    return (torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(b)).item()
+
+
+@pytest.mark.parametrize("name", ["tiny_tok", "tiny_sample"])
+def test_oracle_matches_reference_golden(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    F, H, W, per_tok = (int(v) for v in g["meta"])
+    taps = {}
+    out = _run_oracle(str(g["config"]), (F, H, W), bool(per_tok), taps=taps)
+    assert _rel(out, torch.from_numpy(g["out"])) < 2e-5
+    rows = slice(0, None, max(1, taps["x0"].shape[1] // 16))
+    assert _rel(taps["x_final"][rows], torch.from_numpy(g["x_final_rows"])) < 2e-5
+
+
+@pytest.mark.slow
+def test_oracle_matches_reference_golden_real_width(golden_dir):
+    g = np.load(os.path.join(golden_dir, "real2_tok.npz"))
+    F, H, W, per_tok = (int(v) for v in g["meta"])
+    out = _run_oracle("real2", (F, H, W), bool(per_tok))
+    assert _rel(out, torch.from_numpy(g["out"])) < 2e-5
+
+
+def test_bf16_policy_stays_within_the_bf16_gate():
+    """The emulated autocast flow must sit inside the north-star tolerance (rel-L2 <= 1e-2 vs fp32)."""
+    ref = _run_oracle("tiny", (3, 8, 12), True)
+    emu = _run_oracle("tiny", (3, 8, 12), True, policy="bf16")
+    assert 1e-5 < _rel(emu, ref) < 1e-2
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="reference tree not mounted")
+def test_oracle_matches_live_reference():
+    cfg = synth.CONFIGS["tiny"]
+    model = ref_import.build_reference_model(cfg).eval()
+    sd = O.to_torch_sd(synth.state_dict(cfg))
+    model.load_state_dict(sd, strict=True)
+    inp = synth.inputs(cfg, 2, 4, 8, per_token_t=True, tag="live")
+    ctx = [torch.from_numpy(c) for c in inp["context"]]
+    tt = {k: torch.from_numpy(inp[k]) for k in ("x", "y", "additional_control", "full_ref", "t", "density")}
+    with torch.no_grad():
+        ref = model(x=tt["x"], t=tt["t"], context=ctx, seq_len=inp["seq_len"], y=tt["y"], full_ref=tt["full_ref"],
+                    additional_control=tt["additional_control"], density=tt["density"])
+        mine = O.forward(sd, cfg, tt["x"], tt["t"], ctx, inp["seq_len"], tt["y"], tt["full_ref"],
+                         tt["additional_control"], tt["density"])
+    assert _rel(mine, ref) < 2e-5
+
+
+def test_rope_table_matches_reference_construction():
+    a = O.rope_angles(128)
+    assert a.shape == (1024, 64) and a.dtype == torch.float64
+    # frame axis uses 44-wide frequencies, row/col 42-wide (d - 4*(d//6), 2*(d//6))
+    assert torch.allclose(a[1, :22], 1.0 / torch.pow(10000.0, torch.arange(0, 44, 2, dtype=torch.float64) / 44))
+    assert torch.allclose(a[1, 22:43], 1.0 / torch.pow(10000.0, torch.arange(0, 42, 2, dtype=torch.float64) / 42))
+    from flexam_b200.model import rope_table
+    assert torch.equal(rope_table(128), O.rope_table_f32(128))
+
+
+def test_param_tree_matches_between_product_and_oracle():
+    from flexam_b200.model import param_shapes
+    cfg = dict(synth.CONFIGS["tiny"])
+    prod = param_shapes(dict(cfg, in_dim_ref_conv=cfg["out_dim"], in_dim_cnn_block=cfg["in_dim_cnn"],
+                             out_dim_cnn_block=cfg["out_dim_cnn"]))
+    orc = {n: tuple(s) for n, s, _, _ in synth.param_specs(cfg)}
+    assert prod == orc
