@@ -88,9 +88,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   // Register re-partitioning: the data-movement warpgroup (warps 8-11) gives its registers to the two softmax
-  // warpgroups (per SM sub-partition: 2 x 32 x 208 + 32 x 96 <= 16384).
+  // warpgroups (the pool is what the launch allocated, 3 warps x 168 per sub-partition: 2 x 208 + 88 <= 504).
   if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {

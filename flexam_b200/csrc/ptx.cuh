@@ -44,9 +44,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Spin on the phase parity. A pipeline bug would otherwise hang the GPU until an external timeout; the watchdog
+// turns ~2 s without progress into a trap (reported as a launch failure at the caller's next synchronisation).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifndef FX_NO_WATCHDOG
+  uint32_t polls = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++polls & 0xFFFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
+  }
+#else
   while (!mbar_try_wait(bar, parity)) {
   }
+#endif
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -111,6 +111,7 @@ class NativeEngine:
         self._ws = {}
         self._versions = None
         self.launches = 0              # kernels launched by the last forward (bench.py reports it)
+        self.timing = None             # list -> per-launch CUDA events for the GEMM / attention families
         self._pack()
 
     # -- weights -------------------------------------------------------------------------------------------
@@ -168,9 +169,25 @@ class NativeEngine:
             self._ws[key] = t
         return t
 
-    def _gemm(self, *a, **k):
+    def _timed(self, kind: str, flops: float, fn, *a, **k):
+        """Launch through `fn`; when `self.timing` is a list, bracket the launch with CUDA events on the launching
+        stream so bench.py can attribute device time per kernel family inside the timed region."""
         self.launches += 1
-        return ops.gemm(*a, **k)
+        if self.timing is None:
+            return fn(*a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a, **k)
+        e1.record()
+        self.timing.append((kind, flops, e0, e1))
+        return r
+
+    def _gemm(self, a, w, bias, out, epi, **k):
+        return self._timed("gemm", 2.0 * a.shape[0] * w.shape[0] * a.shape[1], ops.gemm, a, w, bias, out, epi, **k)
+
+    def _fmha(self, q, k, v, out, scale):
+        B, Lq, H, hd = q.shape
+        return self._timed("fmha", 4.0 * B * H * Lq * k.shape[1] * hd, ops.fmha, q, k, v, out, scale)
 
     # -- stages --------------------------------------------------------------------------------------------
     def _embed_mlp(self, pe: str, pp: str, values: torch.Tensor):
@@ -327,7 +344,7 @@ class NativeEngine:
             ops.rmsnorm_rope(qkv[:, :D], w["nq"], self.eps, self.freqs, grid, 0, L)
             ops.rmsnorm_rope(qkv[:, D:2 * D], w["nk"], self.eps, self.freqs, grid, 0, L)
             if self.sp_group is None:
-                ops.fmha(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], attn4, scale)
+                self._fmha(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], attn4, scale)
             else:
                 self.sp_group.attention(qkv5, attn4, scale)
             self._gemm(attn, w["wo"], w["bo"], xs, FX_EPI_RESID_F32, gate_mod=mod[2], gate_e=e0v[:, 2], row_idx=row_idx)
@@ -336,14 +353,14 @@ class NativeEngine:
             self._gemm(h, w["cwq"], w["cbq"], cq, FX_EPI_BF16)
             ops.rmsnorm_rope(cq, w["cnq"], self.eps)
             kv5 = st["kv"][i].view(B, T, 2, self.H, 128)
-            ops.fmha(cq4, kv5[:, :, 0], kv5[:, :, 1], attn4, scale)
+            self._fmha(cq4, kv5[:, :, 0], kv5[:, :, 1], attn4, scale)
             self._gemm(attn, w["cwo"], w["cbo"], xs, FX_EPI_RESID_F32)
             # ffn
             ops.ln_modulate(xs, h, self.eps, mod[3], mod[4], e0v[:, 3], e0v[:, 4], 6 * D, row_idx, dmod[1],
                             de0v[:, 1], 2 * D, L)
             self._gemm(h, w["w1"], w["b1"], ffn, FX_EPI_GELU_BF16)
             self._gemm(ffn, w["w2"], w["b2"], xs, FX_EPI_RESID_F32, gate_mod=mod[5], gate_e=e0v[:, 5], row_idx=row_idx)
-            self.launches += 8
+            self.launches += 6
             if block_hook is not None:
                 block_hook(i, xs)
 

@@ -160,7 +160,7 @@ if __name__ == "__main__":
     results = []
     for n in names:
         try:
-            r = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=180)
+            r = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=60)
             line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")]
             if line:
                 res = json.loads(line[-1][7:])

@@ -1,0 +1,231 @@
+"""GPU parity tests: the native sm_100a path (through the C ABI) against the oracle and the reference's golden
+outputs. Tolerances come from BASELINE.json's north star: bf16 path vs the reference, relative L2 <= 1e-2."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16_GATE = 1e-2  # north_star: relative L2 <= 1e-2 in bf16
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return (torch.linalg.vector_norm(a - b) / (torch.linalg.vector_norm(b) + 1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from flexam_b200 import lib
+    lib.check(lib.load().fx_check_device(0), "fx_check_device")
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------------------------------------------
+# operators
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 512), (1344, 3072, 592), (672, 192, 3072),
+                                   (512, 14336, 3072), (4096, 3072, 14336), (300, 48, 96), (1024, 9216, 3072)])
+def test_gemm_bias_bf16(dev, M, N, K):
+    from flexam_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    a = (torch.randn(M, K, device=dev, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    b = torch.randn(N, device=dev, generator=g).bfloat16()
+    out = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, b, out, ops.FX_EPI_BF16)
+    want = (a.float() @ w.float().t() + b.float()).bfloat16()
+    assert _rel(out, want) < 3e-3
+
+
+def test_gemm_epilogues(dev):
+    from flexam_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(7)
+    M, N, K, U = 1344, 3072, 512, 3
+    a = (torch.randn(M, K, device=dev, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    b = torch.randn(N, device=dev, generator=g).bfloat16()
+    y = (a.float() @ w.float().t() + b.float()).bfloat16().float()
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, b, out, ops.FX_EPI_GELU_BF16)
+    assert _rel(out, torch.nn.functional.gelu(y, approximate="tanh")) < 3e-3
+    of = torch.empty(M, N, device=dev)
+    ops.gemm(a, w, b, of, ops.FX_EPI_F32)
+    assert _rel(of, y) < 3e-3
+    x0 = torch.randn(M, N, device=dev, generator=g)
+    gm = torch.randn(N, device=dev, generator=g)
+    ge = torch.randn(U, 6, N, device=dev, generator=g)
+    idx = torch.randint(0, U, (M,), device=dev, generator=g, dtype=torch.int32)
+    xr = x0.clone()
+    ops.gemm(a, w, b, xr, ops.FX_EPI_RESID_F32, gate_mod=gm, gate_e=ge[:, 2], row_idx=idx)
+    assert _rel(xr, x0 + y * (gm + ge[idx.long(), 2])) < 3e-3
+    xr = x0.clone()
+    ops.gemm(a, w, b, xr, ops.FX_EPI_RESID_F32)
+    assert _rel(xr, x0 + y) < 3e-3
+
+
+def test_gemm_is_linear_in_a(dev):
+    """Size-independent property at full width: gemm(a1 + a2) == gemm(a1) + gemm(a2) for exactly representable sums."""
+    from flexam_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(11)
+    M, N, K = 2048, 3072, 3072
+    a1 = torch.randint(-4, 5, (M, K), device=dev, generator=g).bfloat16()
+    a2 = torch.randint(-4, 5, (M, K), device=dev, generator=g).bfloat16()
+    w = torch.randint(-2, 3, (N, K), device=dev, generator=g).bfloat16()
+    o = [torch.empty(M, N, device=dev) for _ in range(3)]
+    for t, a in zip(o, (a1, a2, a1 + a2)):
+        ops.gemm(a, w, None, t, ops.FX_EPI_F32)
+    # small integers: every partial sum is exact in fp32 and bf16-representable only if |y| < 256; compare in fp32
+    want = (a1.float() + a2.float()) @ w.float().t()
+    assert torch.equal(o[2], want.bfloat16().float())
+    assert _rel(o[0] + o[1], want) < 4e-3
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk", [(1, 1, 256, 128), (1, 2, 200, 672), (2, 3, 672, 672), (2, 24, 1344, 512),
+                                       (1, 2, 1024, 11648), (1, 1, 300, 11200)])
+def test_fmha_matches_softmax_attention(dev, B, H, Lq, Lk):
+    from flexam_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(Lq + Lk)
+    q = torch.randn(B, Lq, H, 128, device=dev, generator=g).bfloat16()
+    k = torch.randn(B, Lk, H, 128, device=dev, generator=g).bfloat16()
+    v = torch.randn(B, Lk, H, 128, device=dev, generator=g).bfloat16()
+    out = torch.full((B, Lq, H, 128), float("nan"), device=dev, dtype=torch.bfloat16)
+    ops.fmha(q, k, v, out, 128 ** -0.5)
+    s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * 128 ** -0.5
+    want = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), v.float())
+    assert not torch.isnan(out.float()).any()
+    assert _rel(out, want) < 6e-3
+
+
+def test_fmha_rows_are_convex_combinations_of_v(dev):
+    """Property that holds at any size: with v == const the output is that constant (softmax weights sum to 1)."""
+    from flexam_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(5)
+    B, H, L = 1, 4, 11648
+    qkv = torch.randn(B * L, 3 * H * 128, device=dev, generator=g).bfloat16()
+    v5 = qkv.view(B, L, 3, H, 128)
+    v5[:, :, 2] = 0.75
+    out = torch.empty(B, L, H, 128, device=dev, dtype=torch.bfloat16)
+    ops.fmha(v5[:, :, 0], v5[:, :, 1], v5[:, :, 2], out, 128 ** -0.5)
+    assert (out.float() - 0.75).abs().max().item() < 1e-2
+
+
+def test_ln_and_rmsnorm_rope(dev):
+    from flexam_b200 import ops
+    from oracle import flexam_oracle as O
+    g = torch.Generator(device=dev).manual_seed(3)
+    M, D, U, B = 1344, 3072, 3, 2
+    x = torch.randn(M, D, device=dev, generator=g) * 2 + 0.3
+    mod = torch.randn(6, D, device=dev, generator=g) * 0.1
+    e = torch.randn(U, 6, D, device=dev, generator=g) * 0.1
+    dmod = torch.randn(2, D, device=dev, generator=g) * 0.1
+    dens = torch.randn(B, 2, D, device=dev, generator=g) * 0.1
+    idx = torch.randint(0, U, (M,), device=dev, generator=g, dtype=torch.int32)
+    out = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    ops.ln_modulate(x, out, 1e-6, mod[0], mod[1], e[:, 0], e[:, 1], 6 * D, idx, dmod[0], dens[:, 0], 2 * D, M // B)
+    ln = torch.nn.functional.layer_norm(x, (D,), eps=1e-6)
+    b = torch.arange(M, device=dev) // (M // B)
+    want = ln * (1 + mod[1] + e[idx.long(), 1]) + mod[0] + e[idx.long(), 0] + dmod[0] + dens[b, 0]
+    assert _rel(out, want) < 3e-3
+    gam = torch.randn(D, device=dev, generator=g).bfloat16()
+    bet = torch.randn(D, device=dev, generator=g).bfloat16()
+    ops.ln_affine(x, out, 1e-6, gam, bet)
+    assert _rel(out, ln * gam.float() + bet.float()) < 3e-3
+
+    # RMSNorm over the full row + RoPE against the oracle's float64 rotation (ref frame => grid f+1)
+    Bq, L, grid = 2, 96, (4, 4, 6)
+    buf = torch.randn(Bq * L, 3 * D, device=dev, generator=g).bfloat16()
+    keep = buf.clone()
+    w = (1 + 0.1 * torch.randn(D, device=dev, generator=g)).bfloat16()
+    ops.rmsnorm_rope(buf[:, :D], w, 1e-6, O.rope_table_f32(128).to(dev), grid, 0, L)
+    xn = O._rmsnorm(keep[:, :D].float(), w.float(), 1e-6, "bf16")
+    ang = O.rope_angles(128)
+    want = torch.stack([O.rope_apply(xn[i * L:(i + 1) * L].view(L, 24, 128).cpu(), grid, ang) for i in range(Bq)])
+    assert _rel(buf[:, :D].cpu().view(Bq, L, 24, 128), want) < 3e-3
+    assert torch.equal(buf[:, D:], keep[:, D:])  # neighbours in the packed buffer untouched
+
+
+# ------------------------------------------------------------------------------------------------------
+# whole denoising step
+# ------------------------------------------------------------------------------------------------------
+def _native_model(cfg_name, dev):
+    from flexam_b200.model import Wan2_2Transformer3DModel_FlexAM
+    from oracle import synth
+    cfg = synth.CONFIGS[cfg_name]
+    m = Wan2_2Transformer3DModel_FlexAM(
+        model_type="ti2v", patch_size=cfg["patch_size"], text_len=cfg["text_len"], in_dim=cfg["in_dim"], dim=cfg["dim"],
+        ffn_dim=cfg["ffn_dim"], freq_dim=cfg["freq_dim"], text_dim=cfg["text_dim"], out_dim=cfg["out_dim"],
+        num_heads=cfg["num_heads"], num_layers=cfg["num_layers"], eps=cfg["eps"], add_ref_conv=True,
+        in_dim_ref_conv=cfg["out_dim"], add_cnn_block=True, in_dim_cnn_block=cfg["in_dim_cnn"],
+        out_dim_cnn_block=cfg["out_dim_cnn"], device=dev)
+    sd = {k: torch.from_numpy(v).to(dev, torch.bfloat16) for k, v in synth.state_dict(cfg).items()}
+    m.load_state_dict(sd, strict=True)
+    return m, cfg
+
+
+def _inputs(cfg, grid, per_tok, dev):
+    from oracle import synth
+    inp = synth.inputs(cfg, *grid, per_token_t=per_tok)
+    tt = {k: torch.from_numpy(inp[k]).to(dev) for k in ("x", "y", "additional_control", "full_ref", "t", "density")}
+    ctx = [torch.from_numpy(c).to(dev) for c in inp["context"]]
+    return tt, ctx, inp["seq_len"]
+
+
+@pytest.mark.parametrize("name", ["tiny_tok", "tiny_sample", "real2_tok"])
+def test_forward_matches_reference_golden(dev, golden_dir, name):
+    """Native bf16 step vs the REAL reference's fp32 CPU output (tests/golden, made by oracle/make_golden.py)."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    F, H, W, per_tok = (int(v) for v in g["meta"])
+    model, cfg = _native_model(str(g["config"]), dev)
+    tt, ctx, seq_len = _inputs(cfg, (F, H, W), bool(per_tok), dev)
+    taps = {}
+    out = model(x=tt["x"].bfloat16(), t=tt["t"], context=[c.bfloat16() for c in ctx], seq_len=seq_len,
+                y=tt["y"].bfloat16(), full_ref=tt["full_ref"].bfloat16(),
+                additional_control=tt["additional_control"].bfloat16(), density=tt["density"])
+    torch.cuda.synchronize()
+    assert out.shape == (2, cfg["out_dim"], F, H, W) and out.dtype == torch.bfloat16
+    rel = _rel(out.cpu(), torch.from_numpy(g["out"]))
+    print(f"{name}: native vs reference golden rel-L2 {rel:.3e}")
+    assert rel < BF16_GATE
+
+
+def test_forward_matches_bf16_policy_oracle(dev):
+    """Closer check: against the oracle emulating the reference's CUDA bf16-autocast rounding points."""
+    from oracle import flexam_oracle as O
+    from oracle import synth
+    model, cfg = _native_model("tiny", dev)
+    tt, ctx, seq_len = _inputs(cfg, (3, 8, 12), True, dev)
+    out = model(x=tt["x"].bfloat16(), t=tt["t"], context=[c.bfloat16() for c in ctx], seq_len=seq_len,
+                y=tt["y"].bfloat16(), full_ref=tt["full_ref"].bfloat16(),
+                additional_control=tt["additional_control"].bfloat16(), density=tt["density"])
+    sd = O.to_torch_sd(synth.state_dict(cfg), dev)
+    want = O.forward(sd, cfg, tt["x"], tt["t"], ctx, seq_len, tt["y"], tt["full_ref"], tt["additional_control"],
+                     tt["density"], policy="bf16")
+    rel = _rel(out, want)
+    print(f"native vs bf16-policy oracle rel-L2 {rel:.3e}")
+    assert rel < 5e-3
+
+
+def test_forward_is_deterministic_and_cache_consistent(dev):
+    model, cfg = _native_model("tiny", dev)
+    tt, ctx, seq_len = _inputs(cfg, (3, 8, 12), True, dev)
+    kw = dict(x=tt["x"].bfloat16(), t=tt["t"], context=[c.bfloat16() for c in ctx], seq_len=seq_len,
+              y=tt["y"].bfloat16(), full_ref=tt["full_ref"].bfloat16(),
+              additional_control=tt["additional_control"].bfloat16(), density=tt["density"])
+    a = model(**kw).clone()          # cold: computes the step-invariant caches
+    b = model(**kw).clone()          # warm: reuses them
+    model.engine().cache_static = False
+    c = model(**kw).clone()
+    assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_missing_extension_fails_loudly(monkeypatch):
+    from flexam_b200 import lib
+    monkeypatch.setattr(lib, "_lib", None)
+    monkeypatch.setattr(lib, "LIB_PATH", "/nonexistent/libflexam_b200.so")
+    with pytest.raises(lib.FlexamNativeError):
+        lib.load()
