@@ -342,3 +342,67 @@ extern "C" int fx_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void*
   FX_CHECK_LAUNCH("fx_cast_bf16_to_f32");
   return FX_OK;
 }
+
+// -------------------------------------------------------------------------------------------------
+// Ulysses exchange layout + TeaCache residual helpers
+// -------------------------------------------------------------------------------------------------
+namespace fx {
+__global__ void swap01_kernel(const uint4* in, long long ld_a_vec, uint4* out, int A, int B, int inner_vec) {
+  const long long total = static_cast<long long>(A) * B * inner_vec;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total; i += stride) {
+    const int c = static_cast<int>(i % inner_vec);
+    const long long ab = i / inner_vec;
+    const int b = static_cast<int>(ab % B);
+    const int a = static_cast<int>(ab / B);
+    out[(static_cast<long long>(b) * A + a) * inner_vec + c] = in[a * ld_a_vec + static_cast<long long>(b) * inner_vec + c];
+  }
+}
+__global__ void add_f32_kernel(float4* dst, const float4* src, long long n4) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 d = dst[i];
+    const float4 s = src[i];
+    d.x += s.x; d.y += s.y; d.z += s.z; d.w += s.w;
+    dst[i] = d;
+  }
+}
+__global__ void sub_f32_kernel(float4* out, const float4* a, const float4* b, long long n4) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 x = a[i], y = b[i];
+    out[i] = make_float4(x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w);
+  }
+}
+}  // namespace fx
+
+extern "C" int fx_swap01_bf16(const void* in, int64_t ld_a, void* out, int A, int B, int inner, void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(in && out && A > 0 && B > 0 && inner > 0, "fx_swap01_bf16: bad arguments");
+  FX_CHECK_ARG(inner % 8 == 0 && ld_a % 8 == 0 && ld_a >= static_cast<int64_t>(B) * inner,
+               "fx_swap01_bf16: inner and ld_a must be multiples of 8 and ld_a >= B*inner");
+  const long long total = static_cast<long long>(A) * B * (inner / 8);
+  swap01_kernel<<<ew_grid(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(in), ld_a / 8, reinterpret_cast<uint4*>(out), A, B, inner / 8);
+  FX_CHECK_LAUNCH("fx_swap01_bf16");
+  return FX_OK;
+}
+extern "C" int fx_add_f32(float* dst, const float* src, int64_t n, void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(dst && src && n > 0 && n % 4 == 0, "fx_add_f32: bad arguments (n must be a multiple of 4)");
+  add_f32_kernel<<<ew_grid(n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(src), n / 4);
+  FX_CHECK_LAUNCH("fx_add_f32");
+  return FX_OK;
+}
+extern "C" int fx_sub_f32(float* out, const float* a, const float* b, int64_t n, void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(out && a && b && n > 0 && n % 4 == 0, "fx_sub_f32: bad arguments (n must be a multiple of 4)");
+  sub_f32_kernel<<<ew_grid(n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<float4*>(out), reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), n / 4);
+  FX_CHECK_LAUNCH("fx_sub_f32");
+  return FX_OK;
+}

@@ -33,6 +33,9 @@ SIGNATURES = {
     "fx_im2col3x3": [_vp, _vp, _i, _i, _i, _i, _vp],
     "fx_groupnorm_silu": [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "fx_cfg_euler_step": [_vp, _vp, _f, _f, _vp, _vp, _vp, _i64, _vp],
+    "fx_swap01_bf16": [_vp, _i64, _vp, _i, _i, _i, _vp],
+    "fx_add_f32": [_vp, _vp, _i64, _vp],
+    "fx_sub_f32": [_vp, _vp, _vp, _i64, _vp],
     "fx_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "fx_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
 }

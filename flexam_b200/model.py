@@ -381,13 +381,11 @@ class NativeEngine:
 def _set_param(root: nn.Module, dotted: str, p: nn.Parameter):
     parts = dotted.split(".")
     m = root
-    for i, name in enumerate(parts[:-1]):
-        if not hasattr(m, name):
-            nxt_is_index = parts[i + 1].isdigit() if i + 1 < len(parts) - 1 else False
-            m.add_module(name, nn.ModuleList() if nxt_is_index else nn.Module())
-        child = getattr(m, name)
-        if isinstance(m, nn.ModuleList):
-            child = m[int(name)]
+    for name in parts[:-1]:
+        child = m._modules.get(name)
+        if child is None:
+            child = nn.Module()
+            m.add_module(name, child)   # digit names ("0", "2") mirror the reference's nn.Sequential children
         m = child
     m.register_parameter(parts[-1], p)
 
@@ -476,7 +474,7 @@ class Wan2_2Transformer3DModel_FlexAM(nn.Module):
     # -- forward -----------------------------------------------------------------------------------------------
     def engine(self) -> NativeEngine:
         if self._engine is None:
-            params = {k: v.data for k, v in self.named_parameters()}
+            params = {k: v.detach() for k, v in self.named_parameters()}   # detach() shares the version counter
             dev = next(iter(params.values())).device
             self._engine = NativeEngine(params, self.config, dev)
             if self._riflex is not None:
@@ -512,7 +510,7 @@ def install(module: nn.Module) -> nn.Module:
     """Rebind ``module.forward`` (a reference ``Wan2_2Transformer3DModel_FlexAM`` instance, bf16, on a B200) to the
     native path — the same method-rebinding plug-in pattern the reference uses for USP (:807-815)."""
     import types
-    params = {k: v.data for k, v in module.named_parameters()}
+    params = {k: v.detach() for k, v in module.named_parameters()}
     cfg = dict(module.config)
     cfg.setdefault("in_dim_ref_conv", params["ref_conv.weight"].shape[1])
     cfg.setdefault("in_dim_cnn_block", params["cnn_conv1.0.weight"].shape[1])

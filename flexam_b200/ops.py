@@ -189,3 +189,30 @@ def cfg_euler_step(vu: torch.Tensor, vc: torch.Tensor, guidance: float, dsigma: 
                                      _stream())
     _l.check(st, "fx_cfg_euler_step")
     return lat
+
+
+def swap01(src: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[b, a, :] = src[a, b, :]; src: bf16 [A, B, inner] (row stride of A free), out: contiguous [B, A, inner]."""
+    _req(src, bf16, "swap01.src"), _req(out, bf16, "swap01.out")
+    A, B, inner = src.shape
+    if src.stride(1) != inner or not out.is_contiguous() or out.shape != (B, A, inner):
+        raise _l.FlexamNativeError(f"swap01: bad layout src{tuple(src.shape)}/{src.stride()} out{tuple(out.shape)}")
+    _l.check(_l.load().fx_swap01_bf16(_p(src), src.stride(0), _p(out), A, B, inner, _stream()), "fx_swap01_bf16")
+    return out
+
+
+def add_(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    _req(dst, f32, "add_.dst"), _req(src, f32, "add_.src")
+    if not (dst.is_contiguous() and src.is_contiguous() and dst.numel() == src.numel()):
+        raise _l.FlexamNativeError("add_: contiguous tensors of equal size required")
+    _l.check(_l.load().fx_add_f32(_p(dst), _p(src), dst.numel(), _stream()), "fx_add_f32")
+    return dst
+
+
+def sub(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    for n, t in (("a", a), ("b", b), ("out", out)):
+        _req(t, f32, "sub." + n)
+        if not t.is_contiguous() or t.numel() != a.numel():
+            raise _l.FlexamNativeError("sub: contiguous tensors of equal size required")
+    _l.check(_l.load().fx_sub_f32(_p(out), _p(a), _p(b), a.numel(), _stream()), "fx_sub_f32")
+    return out

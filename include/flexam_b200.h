@@ -144,6 +144,19 @@ int fx_groupnorm_silu(const void* x, int64_t P, int C, int G, float eps, const v
 int fx_cfg_euler_step(const void* vu, const void* vc, float guidance, float dsigma, float* lat, const float* mask,
                       const void* pinned, int64_t n, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Ulysses sequence-parallel exchange layout (the head-scatter all-to-all around self-attention that the
+ * reference delegates to the absent FlexAM/dist usp_attn_forward, :801-815): out[b][a][:] = in[a][b][:] for
+ * bf16 blocks of `inner` contiguous elements (inner % 8 == 0); `in` rows may be strided (ld_a elements between
+ * consecutive a). Packs [tokens][3*P head groups][Hl*128] into per-destination send buffers and unpacks
+ * [P][tokens][Hl*128] back into [tokens][H*128].
+ */
+int fx_swap01_bf16(const void* in, int64_t ld_a, void* out, int A, int B, int inner, void* stream);
+
+/* TeaCache residual bookkeeping on the fp32 token stream (:1003-1051): dst += src, out = a - b. */
+int fx_add_f32(float* dst, const float* src, int64_t n, void* stream);
+int fx_sub_f32(float* out, const float* a, const float* b, int64_t n, void* stream);
+
 /* Small utility kernels used by the host glue. */
 int fx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int fx_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);

@@ -1,0 +1,167 @@
+"""TEST INFRASTRUCTURE — torch emulation of the ``flexam_b200.ops`` entry points (same signatures, same in-place /
+view semantics), so the HOST logic of ``NativeEngine`` (buffer views, strides, token/ref ordering, index tables,
+launch order, sharding) can be exercised on CPU without a GPU. It is monkey-patched over ``flexam_b200.ops`` by
+tests only; the product never imports it. Each function is also the executable specification of its kernel."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _rb(t):
+    return t.to(bf16).to(f32)
+
+
+def gemm(a, w, bias, out, epilogue, gate_mod=None, gate_e=None, row_idx=None):
+    y = a.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias.float()
+    y = _rb(y)
+    if epilogue == 0:
+        out.copy_(y.to(bf16))
+    elif epilogue == 1:
+        out.copy_(F.gelu(y, approximate="tanh").to(bf16))
+    elif epilogue == 2:
+        out.copy_(y)
+    else:
+        if gate_mod is None and gate_e is None:
+            gate = 1.0
+        else:
+            gate = 0.0
+            if gate_mod is not None:
+                gate = gate + gate_mod.float()[None]
+            if gate_e is not None:
+                idx = row_idx.long() if row_idx is not None else torch.zeros(a.shape[0], dtype=torch.long)
+                gate = gate + gate_e[idx]
+        out.add_(y * gate)
+    return out
+
+
+def ln_modulate(x, out, eps, shift_mod, scale_mod, shift_e, scale_e, e_stride, row_idx, dens_mod, dens, dens_stride,
+                rows_per_batch):
+    M, D = x.shape
+    idx = row_idx.long() if row_idx is not None else torch.zeros(M, dtype=torch.long)
+    ln = F.layer_norm(x, (D,), eps=eps)
+    y = ln * (1 + (scale_mod + scale_e[idx])) + (shift_mod + shift_e[idx])
+    if dens is not None:
+        b = torch.arange(M, device=x.device) // rows_per_batch
+        d = dens[b]
+        if dens_mod is not None:
+            d = d + dens_mod
+        y = y + d
+    out.copy_(y.to(bf16))
+    return out
+
+
+def ln_affine(x, out, eps, gamma, beta):
+    out.copy_((F.layer_norm(x, (x.shape[1],), eps=eps) * gamma.float() + beta.float()).to(bf16))
+    return out
+
+
+def rmsnorm_rope(x, weight, eps, freqs=None, grid=(0, 0, 0), tok_offset=0, rows_per_batch=0):
+    M, D = x.shape
+    xf = x.float()
+    r = _rb(torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps))
+    y = _rb(_rb(xf * r) * weight.float())
+    if freqs is not None:
+        gf, gh, gw = grid
+        rpb = rows_per_batch if rows_per_batch > 0 else M
+        t = tok_offset + torch.arange(M) % rpb
+        valid = t < gf * gh * gw
+        tt = t.clamp(max=gf * gh * gw - 1)
+        f, h, w = tt // (gh * gw), (tt // gw) % gh, tt % gw
+        cs = torch.cat([freqs[f, :22], freqs[h, 22:43], freqs[w, 43:]], dim=1)     # [M, 64, 2]
+        yv = y.view(M, D // 128, 64, 2)
+        c, s = cs[:, None, :, 0], cs[:, None, :, 1]
+        re = yv[..., 0] * c - yv[..., 1] * s
+        im = yv[..., 0] * s + yv[..., 1] * c
+        rot = torch.stack([re, im], -1).reshape(M, D)
+        y = torch.where(valid[:, None], rot, y)
+    x.copy_(y.to(bf16))
+    return x
+
+
+def fmha(q, k, v, out, scale):
+    s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * scale
+    o = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), v.float())
+    out.copy_(o.to(bf16))
+    return out
+
+
+def patchify(srcs, chan_last, Fr, H, W, rows):
+    planes = []
+    for s, last in zip(srcs, chan_last):
+        planes.append(s.permute(3, 0, 1, 2) if last else s)
+    u = torch.cat(planes, 0)                                            # [C, F, H, W]
+    C = u.shape[0]
+    u = u.view(C, Fr, H // 2, 2, W // 2, 2).permute(1, 2, 4, 0, 3, 5)    # f h w c q r
+    rows[:, : C * 4].copy_(u.reshape(Fr * (H // 2) * (W // 2), C * 4))
+    return rows
+
+
+def unpatchify(head, out):
+    C, Fr, H, W = out.shape
+    u = head[:, : 4 * C].reshape(Fr, H // 2, W // 2, 2, 2, C).permute(5, 0, 1, 3, 2, 4)
+    out.copy_(u.reshape(C, Fr, H, W))
+    return out
+
+
+def sinusoid(t, dim):
+    half = dim // 2
+    fr = torch.pow(10000.0, -torch.arange(half, dtype=torch.float64) / half)
+    s = torch.outer(t.double(), fr)
+    return torch.cat([s.cos(), s.sin()], 1).float()
+
+
+def linear_f32(x, w, bias, act_in=0):
+    if act_in == 1:
+        x = F.silu(x)
+    return F.linear(x, w.float(), None if bias is None else bias.float())
+
+
+def nchw_to_nhwc(src, dst, c0):
+    dst[:, c0:c0 + src.shape[0]].copy_(src.t())
+    return dst
+
+
+def im2col3x3(x, Fr, H, W, rows):
+    C = x.shape[-1]
+    u = x.view(Fr, H, W, C).permute(0, 3, 1, 2).float()                  # [F, C, H, W]
+    cols = F.unfold(u, kernel_size=3, padding=1)                         # [F, C*9, H*W], (c, kh, kw) order
+    rows.copy_(cols.transpose(1, 2).reshape(Fr * H * W, C * 9).to(bf16))
+    return rows
+
+
+def groupnorm_silu(x, groups, eps, gamma, beta, resid, y_f32, y_bf16, stats):
+    P, C = x.shape
+    u = x.float().t().reshape(1, C, P)
+    g = F.group_norm(u, groups, gamma.float(), beta.float(), eps=eps)
+    y = F.silu(g)[0].t()
+    if resid is not None:
+        y = y + resid
+    if y_f32 is not None:
+        y_f32.copy_(y)
+    if y_bf16 is not None:
+        y_bf16.copy_(y.to(bf16))
+
+
+def swap01(src, out):
+    out.copy_(src.transpose(0, 1))
+    return out
+
+
+def add_(dst, src):
+    return dst.add_(src)
+
+
+def sub(a, b, out):
+    return out.copy_(a - b)
+
+
+def install(monkeypatch):
+    from flexam_b200 import ops
+    for name in ("gemm", "ln_modulate", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
+                 "linear_f32", "nchw_to_nhwc", "im2col3x3", "groupnorm_silu", "swap01", "add_", "sub"):
+        monkeypatch.setattr(ops, name, globals()[name])

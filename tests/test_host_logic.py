@@ -1,0 +1,80 @@
+"""CPU tests of the host side of the native path: NativeEngine's launch sequence, buffer views and index tables are
+run with the kernels replaced by their torch specifications (tests/cpu_ops_emul.py) and compared with the oracle.
+The kernels themselves are checked on the GPU (tests/test_native_gpu.py)."""
+import numpy as np
+import pytest
+import torch
+
+import cpu_ops_emul
+from flexam_b200.model import Wan2_2Transformer3DModel_FlexAM
+from oracle import flexam_oracle as O
+from oracle import synth
+
+
+def build(cfg, device="cpu"):
+    m = Wan2_2Transformer3DModel_FlexAM(
+        model_type="ti2v", patch_size=cfg["patch_size"], text_len=cfg["text_len"], in_dim=cfg["in_dim"], dim=cfg["dim"],
+        ffn_dim=cfg["ffn_dim"], freq_dim=cfg["freq_dim"], text_dim=cfg["text_dim"], out_dim=cfg["out_dim"],
+        num_heads=cfg["num_heads"], num_layers=cfg["num_layers"], eps=cfg["eps"], add_ref_conv=True,
+        in_dim_ref_conv=cfg["out_dim"], add_cnn_block=True, in_dim_cnn_block=cfg["in_dim_cnn"],
+        out_dim_cnn_block=cfg["out_dim_cnn"], device=device)
+    np_sd = synth.state_dict(cfg)
+    m.load_state_dict({k: torch.from_numpy(v).to(torch.bfloat16) for k, v in np_sd.items()}, strict=True)
+    return m, np_sd
+
+
+def call(m, inp):
+    tt = {k: torch.from_numpy(inp[k]) for k in ("x", "y", "additional_control", "full_ref", "t", "density")}
+    ctx = [torch.from_numpy(c) for c in inp["context"]]
+    out = m(x=tt["x"].bfloat16(), t=tt["t"], context=[c.bfloat16() for c in ctx], seq_len=inp["seq_len"],
+            y=tt["y"].bfloat16(), full_ref=tt["full_ref"].bfloat16(),
+            additional_control=tt["additional_control"].bfloat16(), density=tt["density"])
+    return out, tt, ctx
+
+
+def rel(a, b):
+    return (torch.linalg.vector_norm(a.float() - b.float()) / torch.linalg.vector_norm(b.float())).item()
+
+
+@pytest.mark.parametrize("per_tok", [True, False])
+def test_engine_host_logic_matches_oracle(monkeypatch, per_tok):
+    cpu_ops_emul.install(monkeypatch)
+    cfg = synth.CONFIGS["tiny"]
+    m, np_sd = build(cfg)
+    inp = synth.inputs(cfg, 3, 8, 12, per_token_t=per_tok)
+    out, tt, ctx = call(m, inp)
+    assert out.shape == (2, 48, 3, 8, 12) and out.dtype == torch.bfloat16
+    want = O.forward(O.to_torch_sd(np_sd), cfg, tt["x"], tt["t"], ctx, inp["seq_len"], tt["y"], tt["full_ref"],
+                     tt["additional_control"], tt["density"], policy="bf16")
+    assert rel(out, want) < 4e-3
+    assert m.engine().launches > 0
+
+
+def test_cfg_skip_wrapper_halves_and_duplicates(monkeypatch):
+    cpu_ops_emul.install(monkeypatch)
+    cfg = synth.CONFIGS["tiny"]
+    m, _ = build(cfg)
+    inp = synth.inputs(cfg, 2, 4, 8, per_token_t=True)
+    full, _, _ = call(m, inp)
+    m.enable_cfg_skip(0.5, 10)
+    m.current_steps = 9                     # inside the last 50 % of the steps -> cond half only
+    skipped, _, _ = call(m, inp)
+    assert skipped.shape == full.shape
+    assert torch.equal(skipped[0], skipped[1])
+    assert rel(skipped[1], full[1]) < 3e-3   # CPU matmul blocking differs with the batch size
+    m.current_steps = 0
+    again, _, _ = call(m, inp)
+    assert torch.equal(again, full)
+
+
+def test_static_cache_tracks_in_place_edits(monkeypatch):
+    cpu_ops_emul.install(monkeypatch)
+    cfg = synth.CONFIGS["tiny"]
+    m, _ = build(cfg)
+    inp = synth.inputs(cfg, 2, 4, 8, per_token_t=True)
+    a, _, _ = call(m, inp)
+    # LoRA-style in-place weight edit must invalidate the packed q|k|v copy
+    with torch.no_grad():
+        m.blocks[0].self_attn.q.weight.mul_(0.5)
+    b, _, _ = call(m, inp)
+    assert rel(b, a) > 1e-4
