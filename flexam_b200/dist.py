@@ -1,0 +1,182 @@
+"""Multi-GPU partitioning of the denoising step on one NVLink/NVSwitch box: CFG-branch parallelism x Ulysses
+sequence parallelism. This is the replacement for the reference's absent ``FlexAM/dist`` package (SURVEY.md F1;
+hook sites wan_transformer3d_FlexAM.py:801-815, :919-920, :971-975, :1103-1104).
+
+One process per GPU (torchrun). Every rank runs the unchanged sampler with the same inputs, so ``forward`` still
+receives the batch-of-2 ``[uncond, cond]`` tensors (pipeline :850). Inside ``forward`` a rank keeps
+
+  * CFG:      row ``cfg_rank`` of the batch (the two branches are independent until the combine, pipeline :926-928);
+  * Ulysses:  token slice ``sp_rank`` of length Lp = ceil(L / P) — everything except self-attention is token-local.
+              Around self-attention the q/k/v shards ``[Lp, H, 128]`` are exchanged head-scattered to
+              ``[P*Lp, H/P, 128]`` (one all-to-all per tensor), attention runs on H/P heads over the whole sequence
+              (padding tokens masked as keys through ``Lk = L``), and the output goes back through one all-to-all.
+
+and before returning all-gathers the head output over the SP group (dim 1, as :1103-1104) and the prediction over
+the CFG group (dim 0), so the caller sees the same ``[2, C, F, H, W]`` tensor as on one GPU.
+
+Layouts: 2 GPUs = CFG2 x SP1, 4 = CFG2 x SP2, 8 = CFG2 x SP4 (24 heads -> 6 per rank). Collectives are NCCL
+(all_to_all_single / all_gather_into_tensor) on the compute stream; packing to per-destination buffers is the native
+``fx_swap01_bf16`` kernel. The exchange functions take the permute/attention kernels as arguments so the CPU tests
+(world_size 2, gloo) can drive the same partitioning logic with torch stand-ins.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class Layout:
+    world: int
+    rank: int
+    cfg_size: int
+    sp_size: int
+
+    @property
+    def cfg_rank(self) -> int:
+        return self.rank // self.sp_size
+
+    @property
+    def sp_rank(self) -> int:
+        return self.rank % self.sp_size
+
+    def sp_ranks(self, cfg_rank: int) -> List[int]:
+        return [cfg_rank * self.sp_size + i for i in range(self.sp_size)]
+
+    def cfg_ranks(self, sp_rank: int) -> List[int]:
+        return [c * self.sp_size + sp_rank for c in range(self.cfg_size)]
+
+    def describe(self) -> str:
+        return f"cfg{self.cfg_size}xsp{self.sp_size}"
+
+
+def make_layout(world: int, rank: int, cfg_size: Optional[int] = None, num_heads: int = 24) -> Layout:
+    """CFG-parallel first (no per-layer traffic), then Ulysses over what is left."""
+    if cfg_size is None:
+        cfg_size = 2 if world % 2 == 0 else 1
+    if world % cfg_size != 0:
+        raise ValueError(f"world size {world} not divisible by cfg_size {cfg_size}")
+    sp = world // cfg_size
+    if num_heads % sp != 0:
+        raise ValueError(f"{num_heads} heads do not divide over {sp} sequence-parallel ranks")
+    return Layout(world, rank, cfg_size, sp)
+
+
+def shard_bounds(L: int, P: int, r: int):
+    """Token slice of rank r: (start, stop, Lp, L_pad); the last rank(s) may hold padding rows (:919-920)."""
+    Lp = -(-L // P)
+    return r * Lp, min((r + 1) * Lp, L), Lp, Lp * P
+
+
+def _all_to_all(out: torch.Tensor, inp: torch.Tensor, group) -> None:
+    """all_to_all_single over dim 0; gloo (CPU tests) has no all-to-all, so it is composed from all_gather there."""
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(out, inp, group=group)
+        return
+    P = dist.get_world_size(group)
+    me = dist.get_rank(group)
+    gathered = [torch.empty_like(inp) for _ in range(P)]
+    dist.all_gather(gathered, inp.contiguous(), group=group)
+    chunk = inp.shape[0] // P
+    for src in range(P):
+        out[src * chunk:(src + 1) * chunk].copy_(gathered[src][me * chunk:(me + 1) * chunk])
+
+
+class Parallel:
+    """Process groups + the exchange steps used by NativeEngine.forward."""
+
+    def __init__(self, layout: Layout, swap01: Callable, fmha: Callable):
+        self.layout = layout
+        self.swap01 = swap01
+        self.fmha = fmha
+        self.sp_group = None
+        self.cfg_group = None
+        # every rank must create every group, in the same order
+        for c in range(layout.cfg_size):
+            g = dist.new_group(layout.sp_ranks(c))
+            if c == layout.cfg_rank:
+                self.sp_group = g
+        for s in range(layout.sp_size):
+            g = dist.new_group(layout.cfg_ranks(s))
+            if s == layout.sp_rank:
+                self.cfg_group = g
+        self._bufs = {}
+
+    def _buf(self, name, shape, like):
+        key = (name, tuple(shape), like.dtype)
+        b = self._bufs.get(key)
+        if b is None:
+            b = torch.empty(tuple(shape), dtype=like.dtype, device=like.device)
+            self._bufs[key] = b
+        return b
+
+    # -- Ulysses attention for ONE sample --------------------------------------------------------------------
+    def attention(self, qkv: torch.Tensor, out: torch.Tensor, L: int, scale: float) -> None:
+        """qkv: [Lp, 3, H, 128] local shard (q,k already normed + rotated); out: [Lp, H, 128]."""
+        P = self.layout.sp_size
+        Lp, _, H, hd = qkv.shape
+        Hl = H // P
+        inner = Hl * hd
+        # [Lp][3*P][inner] -> [3*P][Lp][inner]: per (tensor, destination) send blocks
+        send = self._buf("send", (3 * P, Lp, inner), qkv)
+        self.swap01(qkv.view(Lp, 3 * P, inner), send)
+        recv = self._buf("recv", (3, P * Lp, inner), qkv)
+        for w in range(3):
+            _all_to_all(recv[w], send[w * P:(w + 1) * P].view(P * Lp, inner), self.sp_group)
+        full = recv.view(3, 1, P * Lp, Hl, hd)
+        o_full = self._buf("o_full", (1, P * Lp, Hl, hd), qkv)
+        # keys beyond the real sequence (SP padding) are masked by Lk = L; padded query rows are discarded below
+        self.fmha(full[0], full[1][:, :L], full[2][:, :L], o_full, scale)
+        o_recv = self._buf("o_recv", (P, Lp, inner), qkv)
+        _all_to_all(o_recv.view(P * Lp, inner), o_full.view(P * Lp, inner), self.sp_group)
+        # [P (head group)][Lp][inner] -> [Lp][P][inner] = [Lp, H, 128]
+        self.swap01(o_recv, out.view(Lp, P, inner))
+
+    def gather_tokens(self, local: torch.Tensor) -> torch.Tensor:
+        """[Lp, C] -> [P*Lp, C] over the SP group (:1103-1104)."""
+        P = self.layout.sp_size
+        if P == 1:
+            return local
+        out = torch.empty((P * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        if dist.get_backend(self.sp_group) == "nccl":
+            dist.all_gather_into_tensor(out, local.contiguous(), group=self.sp_group)
+        else:
+            parts = [torch.empty_like(local) for _ in range(P)]
+            dist.all_gather(parts, local.contiguous(), group=self.sp_group)
+            out.copy_(torch.cat(parts, 0))
+        return out
+
+    def gather_cfg(self, local: torch.Tensor) -> torch.Tensor:
+        """[b, ...] -> [cfg_size*b, ...] ordered by cfg_rank (uncond first, as the sampler built the batch)."""
+        Cg = self.layout.cfg_size
+        if Cg == 1:
+            return local
+        out = torch.empty((Cg * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        if dist.get_backend(self.cfg_group) == "nccl":
+            dist.all_gather_into_tensor(out, local.contiguous(), group=self.cfg_group)
+        else:
+            parts = [torch.empty_like(local) for _ in range(Cg)]
+            dist.all_gather(parts, local.contiguous(), group=self.cfg_group)
+            out.copy_(torch.cat(parts, 0))
+        return out
+
+
+def setup(model, world: int, rank: int, cfg_size: Optional[int] = None) -> str:
+    """Attach the partitioning to a native model (torch.distributed must be initialised). Returns e.g. 'cfg2xsp4'."""
+    from . import ops
+    eng = model.engine() if hasattr(model, "engine") else model._flexam_engine
+    layout = make_layout(world, rank, cfg_size, eng.H)
+    eng.par = Parallel(layout, ops.swap01, ops.fmha)
+    model.sp_world_size = layout.sp_size
+    model.sp_world_rank = layout.sp_rank
+    return layout.describe()
+
+
+def attach(model) -> None:
+    """``enable_multi_gpus_inference`` (:801-815): take the layout from the initialised default process group."""
+    if not dist.is_initialized():
+        raise RuntimeError("enable_multi_gpus_inference: torch.distributed is not initialised")
+    setup(model, dist.get_world_size(), dist.get_rank())
