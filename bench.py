@@ -212,6 +212,12 @@ def run_native(args):
         f = fam.setdefault(kind, [0.0, 0.0, 0])
         f[0] += flops; f[1] += a.elapsed_time(b); f[2] += 1
 
+    if args.quick:   # profiling runs (ncu) only need the resident region
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms_value, "gpu_launches": launches}))
+        if clocks:
+            clocks.stop()
+        return
     # ---------------- hoisted region (informational): step-invariant control/context work cached, as in the sampler --
     eng.cache_static = True
     call(resident)
@@ -358,6 +364,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="resident region only (for ncu runs)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

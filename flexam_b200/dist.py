@@ -166,10 +166,9 @@ class Parallel:
 
 def setup(model, world: int, rank: int, cfg_size: Optional[int] = None) -> str:
     """Attach the partitioning to a native model (torch.distributed must be initialised). Returns e.g. 'cfg2xsp4'."""
-    from . import ops
     eng = model.engine() if hasattr(model, "engine") else model._flexam_engine
     layout = make_layout(world, rank, cfg_size, eng.H)
-    eng.par = Parallel(layout, ops.swap01, ops.fmha)
+    eng.par = Parallel(layout, eng._swap01, eng._fmha)
     model.sp_world_size = layout.sp_size
     model.sp_world_rank = layout.sp_rank
     return layout.describe()

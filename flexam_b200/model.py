@@ -104,7 +104,7 @@ class NativeEngine:
             raise FlexamNativeError(f"native path supports head_dim 128 only (dim {self.D}, heads {self.H})")
         self.eps = float(cfg["eps"])
         self.freqs = rope_table(128).to(self.device)
-        self.sp_group = None           # set by flexam_b200.dist for Ulysses sequence parallelism
+        self.par = None                # flexam_b200.dist.Parallel: CFG-branch x Ulysses sequence parallelism
         self.cache_static = True       # hoist step-invariant work (context, cross K/V, CNN fuser) across calls
         self._static_key = None
         self._static = {}
@@ -265,7 +265,7 @@ class NativeEngine:
     # -- the denoising step ----------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, x, t, context, seq_len, y, full_ref, additional_control, density,
-                block_hook=None) -> torch.Tensor:
+                block_hook=None, teacache=None, cond_flag=True) -> torch.Tensor:
         """Returns the stacked prediction [B, out_dim, F, H, W] in bf16 (forward :817-1123)."""
         cfg, D, dev = self.cfg, self.D, self.device
         self.refresh_if_modified()
@@ -278,6 +278,20 @@ class NativeEngine:
         add = additional_control.to(dev, bf16).contiguous()
         full_ref = full_ref.to(dev, bf16).contiguous()
         context = [u.to(dev, bf16) for u in context]
+        t = t.to(dev, f32)
+        density = density.to(dev, f32)
+
+        # ---- partitioning (flexam_b200/dist.py): CFG rows, then a token slice per sequence-parallel rank ------
+        par = self.par
+        cfg_split = par is not None and par.layout.cfg_size > 1 and x.shape[0] % par.layout.cfg_size == 0
+        if cfg_split:
+            nb = x.shape[0] // par.layout.cfg_size
+            lo = par.layout.cfg_rank * nb
+            x, y, add, full_ref, t, density = (u[lo:lo + nb] for u in (x, y, add, full_ref, t, density))
+            context = context[lo:lo + nb]
+        P = par.layout.sp_size if par is not None else 1
+        sp_rank = par.layout.sp_rank if par is not None else 0
+
         B, _, F, Hh, Ww = x.shape
         Hp, Wp = Hh // 2, Ww // 2
         L0 = F * Hp * Wp
@@ -286,7 +300,10 @@ class NativeEngine:
         if seq_len != L0:
             raise FlexamNativeError(f"seq_len {seq_len} != tokens on the grid {L0} (padding is handled by the SP layer)")
         grid = (F + 1, Hp, Wp)
-        M = B * L
+        Lp = -(-L // P)            # tokens per SP rank; the tail of the last rank may be padding (:919-920)
+        L_pad = Lp * P
+        tok0 = sp_rank * Lp
+        M = B * Lp
 
         # ---- step-invariant work: control fuser, context embedding, cross-attention K/V ----------------------
         skey = (self._ident([y, add]), self._ident(context))
@@ -300,27 +317,36 @@ class NativeEngine:
 
         # ---- patch + ref embedding straight into the fp32 residual stream (:885-899) --------------------------
         xs = self._buf("x", (M, D), f32)
+        x_full = xs if P == 1 else self._buf("x_full", (B * L_pad, D), f32)   # the embed is cheap: done for all tokens
+        if L_pad != L:
+            x_full.view(B, L_pad, D)[:, L:].zero_()
         rows = self._buf("patch_rows", (L0, self.w_patch.shape[1]), bf16)
         rrows = self._buf("ref_rows", (R, self.w_ref.shape[1]), bf16)
         for b in range(B):
+            o = b * L_pad
             ops.patchify([x[b], st["cnn"][b].view(F, Hh, Ww, -1), y[b, C:]], [False, True, False], F, Hh, Ww, rows)
-            self._gemm(rows, self.w_patch, self.params["patch_embedding.bias"], xs[b * L + R: (b + 1) * L], FX_EPI_F32)
+            self._gemm(rows, self.w_patch, self.params["patch_embedding.bias"], x_full[o + R: o + L], FX_EPI_F32)
             ops.patchify([full_ref[b].unsqueeze(1)], [False], 1, Hh, Ww, rrows)
-            self._gemm(rrows, self.w_ref, self.params["ref_conv.bias"], xs[b * L: b * L + R], FX_EPI_F32)
+            self._gemm(rrows, self.w_ref, self.params["ref_conv.bias"], x_full[o: o + R], FX_EPI_F32)
             self.launches += 2
+        if P > 1:   # keep this rank's token slice (torch.chunk(x, P, dim=1)[rank], :971-975)
+            xs.view(B, Lp, D).copy_(x_full.view(B, L_pad, D)[:, tok0:tok0 + Lp])
 
         # ---- timestep / density embeddings on the distinct timesteps (:900-955) ------------------------------
-        t = t.to(dev, f32)
         if t.dim() == 2:
             if t.shape[1] < L:   # ref tokens are PREPENDED and take the last token's timestep (:900-904)
                 t = torch.cat([t[:, -1:].expand(B, L - t.shape[1]), t], dim=1)
             uniq, inv = torch.unique(t.reshape(-1), return_inverse=True)
-            row_idx = inv.to(i32).contiguous()
+            idx_full = inv.to(i32).view(B, L)
         else:
             uniq = t.contiguous()
-            row_idx = torch.arange(B, device=dev, dtype=i32).repeat_interleave(L).contiguous()
+            idx_full = torch.arange(B, device=dev, dtype=i32).view(B, 1).expand(B, L)
+        last_idx = idx_full[:, -1].long()
+        if L_pad != L:           # padding rows reuse the last token's timestep (:931-935)
+            idx_full = torch.cat([idx_full, idx_full[:, -1:].expand(B, L_pad - L)], dim=1)
+        row_idx = idx_full[:, tok0:tok0 + Lp].contiguous().view(-1)
         e, e0 = self._embed_mlp("time_embedding", "time_projection", uniq.contiguous())          # [U,D], [U,6D]
-        de, de0 = self._embed_mlp("density_embedding", "density_projection", density.to(dev, f32).contiguous())
+        de, de0 = self._embed_mlp("density_embedding", "density_projection", density.contiguous())
 
         # ---- 30 x WanAttentionBlock (:422-472) ---------------------------------------------------------------
         h = self._buf("h", (M, D), bf16)
@@ -330,23 +356,37 @@ class NativeEngine:
         ffn = self._buf("ffn", (M, cfg["ffn_dim"]), bf16)
         T = cfg["text_len"]
         scale = 1.0 / math.sqrt(128.0)
-        qkv5 = qkv.view(B, L, 3, self.H, 128)
-        attn4 = attn.view(B, L, self.H, 128)
-        cq4 = cq.view(B, L, self.H, 128)
+        qkv5 = qkv.view(B, Lp, 3, self.H, 128)
+        attn4 = attn.view(B, Lp, self.H, 128)
+        cq4 = cq.view(B, Lp, self.H, 128)
         e0v = e0.view(-1, 6, D)
         de0v = de0.view(B, 2, D)
-        for i, w in enumerate(self.blk):
+
+        # ---- TeaCache (:977-1051): skip the block stack and re-apply the previous residual when the modulated
+        #      timestep embedding moved little. The decision uses the GLOBAL last token so all SP ranks agree.
+        run_blocks = True
+        ori = None
+        if teacache is not None:
+            run_blocks = teacache.decide(e0v[last_idx], cond_flag)
+            if not run_blocks:
+                prev = teacache.previous_residual_cond if cond_flag else teacache.previous_residual_uncond
+                ops.add_(xs, prev[-M:].contiguous())
+                self.launches += 1
+            else:
+                ori = xs.clone()
+        for i, w in enumerate(self.blk if run_blocks else ()):
             mod, dmod = w["mod"], w["dmod"]
             # self-attention
             ops.ln_modulate(xs, h, self.eps, mod[0], mod[1], e0v[:, 0], e0v[:, 1], 6 * D, row_idx, dmod[0],
-                            de0v[:, 0], 2 * D, L)
+                            de0v[:, 0], 2 * D, Lp)
             self._gemm(h, w["wqkv"], w["bqkv"], qkv, FX_EPI_BF16)
-            ops.rmsnorm_rope(qkv[:, :D], w["nq"], self.eps, self.freqs, grid, 0, L)
-            ops.rmsnorm_rope(qkv[:, D:2 * D], w["nk"], self.eps, self.freqs, grid, 0, L)
-            if self.sp_group is None:
+            ops.rmsnorm_rope(qkv[:, :D], w["nq"], self.eps, self.freqs, grid, tok0, Lp)
+            ops.rmsnorm_rope(qkv[:, D:2 * D], w["nk"], self.eps, self.freqs, grid, tok0, Lp)
+            if P == 1:
                 self._fmha(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], attn4, scale)
-            else:
-                self.sp_group.attention(qkv5, attn4, scale)
+            else:           # Ulysses: head-scatter all-to-all around attention, one sample at a time
+                for b in range(B):
+                    par.attention(qkv5[b], attn4[b], L, scale)
             self._gemm(attn, w["wo"], w["bo"], xs, FX_EPI_RESID_F32, gate_mod=mod[2], gate_e=e0v[:, 2], row_idx=row_idx)
             # cross-attention (no gate, no RoPE, all text_len slots attended)
             ops.ln_affine(xs, h, self.eps, w["n3w"], w["n3b"])
@@ -357,22 +397,39 @@ class NativeEngine:
             self._gemm(attn, w["cwo"], w["cbo"], xs, FX_EPI_RESID_F32)
             # ffn
             ops.ln_modulate(xs, h, self.eps, mod[3], mod[4], e0v[:, 3], e0v[:, 4], 6 * D, row_idx, dmod[1],
-                            de0v[:, 1], 2 * D, L)
+                            de0v[:, 1], 2 * D, Lp)
             self._gemm(h, w["w1"], w["b1"], ffn, FX_EPI_GELU_BF16)
             self._gemm(ffn, w["w2"], w["b2"], xs, FX_EPI_RESID_F32, gate_mod=mod[5], gate_e=e0v[:, 5], row_idx=row_idx)
             self.launches += 6
             if block_hook is not None:
                 block_hook(i, xs)
+        if teacache is not None and run_blocks:
+            res = torch.empty_like(xs)
+            ops.sub(xs, ori, res)
+            self.launches += 1
+            if cond_flag:
+                teacache.previous_residual_cond = res
+            else:
+                teacache.previous_residual_uncond = res
 
         # ---- head (:493-507, uses e not e0) + unpatchify (:1106-1149) -----------------------------------------
-        ops.ln_modulate(xs, h, self.eps, self.head_mod[0], self.head_mod[1], e, e, D, row_idx, self.head_dmod, de, D, L)
+        ops.ln_modulate(xs, h, self.eps, self.head_mod[0], self.head_mod[1], e, e, D, row_idx, self.head_dmod, de, D, Lp)
         ho = self._buf("head", (M, self.params["head.head.weight"].shape[0]), bf16)
         self._gemm(h, self.params["head.head.weight"], self.params["head.head.bias"], ho, FX_EPI_BF16)
         out = torch.empty((B, C, F, Hh, Ww), dtype=bf16, device=dev)
         for b in range(B):
-            ops.unpatchify(ho[b * L + R: (b + 1) * L], out[b])
+            tokens = ho[b * Lp: (b + 1) * Lp] if P == 1 else par.gather_tokens(ho[b * Lp: (b + 1) * Lp])  # :1103-1104
+            ops.unpatchify(tokens[R:L], out[b])     # the ref tokens are dropped from the FRONT (:1106-1109)
         self.launches += 1 + B
+        if cfg_split:
+            out = par.gather_cfg(out)
+        if teacache is not None:
+            teacache.step_done(cond_flag)
         return out
+
+    def _swap01(self, src, out):
+        self.launches += 1
+        return ops.swap01(src, out)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -500,7 +557,8 @@ def native_forward(self, x, t, context, seq_len, clip_fea=None, y=None, y_camera
         x, t, context, y, full_ref, additional_control, density = (
             x[h:], t[h:], context[h:], y[h:], full_ref[h:], additional_control[h:], density[h:])
     eng = self.engine() if hasattr(self, "engine") else self._flexam_engine
-    out = eng.forward(x, t, context, seq_len, y, full_ref, additional_control, density)
+    out = eng.forward(x, t, context, seq_len, y, full_ref, additional_control, density,
+                      teacache=getattr(self, "teacache", None), cond_flag=cond_flag)
     if skip:
         out = torch.cat([out, out], dim=0)
     return out

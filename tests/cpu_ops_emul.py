@@ -15,10 +15,10 @@ def _rb(t):
 
 
 def gemm(a, w, bias, out, epilogue, gate_mod=None, gate_e=None, row_idx=None):
-    y = a.float() @ w.float().t()
+    y = a.double() @ w.double().t()
     if bias is not None:
-        y = y + bias.float()
-    y = _rb(y)
+        y = y + bias.double()
+    y = _rb(y.float())
     if epilogue == 0:
         out.copy_(y.to(bf16))
     elif epilogue == 1:
@@ -84,8 +84,8 @@ def rmsnorm_rope(x, weight, eps, freqs=None, grid=(0, 0, 0), tok_offset=0, rows_
 
 
 def fmha(q, k, v, out, scale):
-    s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * scale
-    o = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), v.float())
+    s = torch.einsum("bqhd,bkhd->bhqk", q.double(), k.double()) * scale
+    o = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), v.double()).float()
     out.copy_(o.to(bf16))
     return out
 

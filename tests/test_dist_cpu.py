@@ -1,0 +1,115 @@
+"""world_size-2 tests (gloo, CPU) of the multi-GPU partitioning in flexam_b200/dist.py: CFG-branch parallelism and
+Ulysses sequence parallelism must reproduce the single-process output. The kernels are replaced by their torch
+specifications (tests/cpu_ops_emul.py); the partitioning, exchange layouts, padding and gathers are the product code."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _patch_ops():
+    import cpu_ops_emul
+    from flexam_b200 import ops
+    for name in ("gemm", "ln_modulate", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
+                 "linear_f32", "nchw_to_nhwc", "im2col3x3", "groupnorm_silu", "swap01", "add_", "sub"):
+        setattr(ops, name, getattr(cpu_ops_emul, name))
+
+
+def _build_and_run(grid, cfg_size, world, rank):
+    from flexam_b200 import dist as fdist
+    from test_host_logic import build, call
+    from oracle import synth
+    cfg = synth.CONFIGS["tiny"]
+    m, _ = build(cfg)
+    if world > 1:
+        fdist.setup(m, world, rank, cfg_size=cfg_size)
+    inp = synth.inputs(cfg, *grid, per_token_t=True)
+    out, _, _ = call(m, inp)
+    return out
+
+
+def _worker(rank, world, port, grid, cfg_size, ref_path, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    torch.set_num_threads(2)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _patch_ops()
+        out = _build_and_run(grid, cfg_size, world, rank)
+        ref = torch.load(ref_path)
+        err = (torch.linalg.vector_norm(out.float() - ref.float()) / torch.linalg.vector_norm(ref.float())).item()
+        q.put((rank, tuple(out.shape), err))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_case(tmp_path, grid, cfg_size):
+    sys.path.insert(0, HERE)
+    import cpu_ops_emul  # noqa: F401
+    from flexam_b200 import ops
+    saved = {n: getattr(ops, n) for n in dir(ops) if callable(getattr(ops, n)) and not n.startswith("_")}
+    try:
+        _patch_ops()
+        ref = _build_and_run(grid, None, 1, 0)
+    finally:
+        for n, f in saved.items():
+            setattr(ops, n, f)
+    ref_path = str(tmp_path / "ref.pt")
+    torch.save(ref, ref_path)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, grid, cfg_size, ref_path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=10) for _ in range(2))
+    for rank, shape, err in res:
+        assert shape == tuple(ref.shape)
+        # same arithmetic, different blocking of the emulated matmuls -> tiny bf16 flips only
+        assert err < 3e-3, f"rank {rank}: sharded output differs from single-process output ({err:.2e})"
+
+
+def test_layouts():
+    from flexam_b200.dist import make_layout, shard_bounds
+    l8 = [make_layout(8, r) for r in range(8)]
+    assert l8[0].describe() == "cfg2xsp4"
+    assert [x.cfg_rank for x in l8] == [0, 0, 0, 0, 1, 1, 1, 1] and [x.sp_rank for x in l8] == [0, 1, 2, 3] * 2
+    assert l8[5].sp_ranks(1) == [4, 5, 6, 7] and l8[5].cfg_ranks(1) == [1, 5]
+    assert make_layout(2, 1).describe() == "cfg2xsp1" and make_layout(4, 3).describe() == "cfg2xsp2"
+    assert shard_bounds(11648, 4, 3) == (8736, 11648, 2912, 11648)
+    assert shard_bounds(45, 2, 1) == (23, 45, 23, 46)          # ragged: one padding row on the last rank
+    with pytest.raises(ValueError):
+        make_layout(10, 0, cfg_size=1)                         # 24 heads do not divide over 10 ranks
+
+
+def test_cfg_parallel_matches_single_process(tmp_path):
+    _run_case(tmp_path, (2, 4, 8), cfg_size=2)
+
+
+def test_ulysses_sequence_parallel_matches_single_process(tmp_path):
+    _run_case(tmp_path, (3, 8, 12), cfg_size=1)
+
+
+def test_ulysses_with_ragged_token_count(tmp_path):
+    # (F+1)*Hp*Wp = 3*3*5 = 45 tokens over 2 ranks -> 23 + 22 (+1 padding row that must be masked as a key)
+    _run_case(tmp_path, (2, 6, 10), cfg_size=1)
