@@ -48,10 +48,16 @@ static EncodeTiledFn encode_fn() {
 
 bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap(out, false, base, rank, dims, strides_bytes, box);
+}
+
+bool make_tmap(CUtensorMap* out, bool is_f32, const void* base, int rank, const uint64_t* dims,
+               const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return false;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+  CUresult r = fn(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                  static_cast<cuuint32_t>(rank), const_cast<void*>(base),
                   reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
                   reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

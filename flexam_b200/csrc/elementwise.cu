@@ -37,38 +37,57 @@ struct LnParams {
   const __nv_bfloat16* beta;
 };
 
-template <int NV, int MODE>  // NV = float4 vectors per lane = D / 128
+// A row is owned by WPR warps (4 for wide rows: 6 float4 per lane at D = 3072 keeps the kernel at ~60 registers and
+// full occupancy; 1 for narrow rows). Row statistics are reduced with shuffles, then across the row's warps via smem.
+template <int WPR>
+__device__ __forceinline__ float row_reduce(float v, float* red, int row_in_block, int warp_in_row, int lane) {
+  v = warp_sum(v);
+  if constexpr (WPR == 1) return v;
+  if (lane == 0) red[row_in_block * WPR + warp_in_row] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < WPR; ++i) t += red[row_in_block * WPR + i];
+  __syncthreads();
+  return t;
+}
+
+template <int NV, int WPR, int MODE>  // NV = float4 vectors per lane = D / (128 * WPR)
 __global__ void __launch_bounds__(256) ln_kernel(const LnParams p) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= p.M) return;
-  const int lane = threadIdx.x & 31;
-  const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<long long>(row) * p.D);
+  __shared__ float red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_in_block = warp / WPR, warp_in_row = warp % WPR;
+  const int row = blockIdx.x * (8 / WPR) + row_in_block;
+  const bool valid = row < p.M;
+  const int c0 = warp_in_row * NV * 32;  // first float4 column of this warp
+  const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<long long>(valid ? row : 0) * p.D) + c0;
   float4 v[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = xr[i * 32 + lane];
+  for (int i = 0; i < NV; ++i) v[i] = valid ? xr[i * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  const float mean = warp_sum(s) / static_cast<float>(p.D);
+  const float mean = row_reduce<WPR>(s, red, row_in_block, warp_in_row, lane) / static_cast<float>(p.D);
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
     q += (a * a + b * b) + (c * c + d * d);
   }
-  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(p.D) + p.eps);
+  const float rstd = rsqrtf(row_reduce<WPR>(q, red, row_in_block, warp_in_row, lane) / static_cast<float>(p.D) + p.eps);
+  if (!valid) return;
 
-  uint2* orow = reinterpret_cast<uint2*>(p.out + static_cast<long long>(row) * p.D);
+  uint2* orow = reinterpret_cast<uint2*>(p.out + static_cast<long long>(row) * p.D) + c0;
   if constexpr (MODE == 0) {
     const long long u = p.row_idx ? p.row_idx[row] : 0;
-    const float4* sh_e = reinterpret_cast<const float4*>(p.shift_e + u * p.e_stride);
-    const float4* sc_e = reinterpret_cast<const float4*>(p.scale_e + u * p.e_stride);
-    const float4* sh_m = reinterpret_cast<const float4*>(p.shift_mod);
-    const float4* sc_m = reinterpret_cast<const float4*>(p.scale_mod);
+    const float4* sh_e = reinterpret_cast<const float4*>(p.shift_e + u * p.e_stride) + c0;
+    const float4* sc_e = reinterpret_cast<const float4*>(p.scale_e + u * p.e_stride) + c0;
+    const float4* sh_m = reinterpret_cast<const float4*>(p.shift_mod) + c0;
+    const float4* sc_m = reinterpret_cast<const float4*>(p.scale_mod) + c0;
     const float4* dn =
-        p.dens ? reinterpret_cast<const float4*>(p.dens + static_cast<long long>(row / p.rows_per_batch) * p.dens_stride)
+        p.dens ? reinterpret_cast<const float4*>(p.dens + static_cast<long long>(row / p.rows_per_batch) * p.dens_stride) + c0
                : nullptr;
-    const float4* dm = reinterpret_cast<const float4*>(p.dens_mod);
+    const float4* dm = p.dens_mod ? reinterpret_cast<const float4*>(p.dens_mod) + c0 : nullptr;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = i * 32 + lane;
@@ -95,8 +114,8 @@ __global__ void __launch_bounds__(256) ln_kernel(const LnParams p) {
       orow[c] = o;
     }
   } else {
-    const uint2* gm = reinterpret_cast<const uint2*>(p.gamma);
-    const uint2* bt = reinterpret_cast<const uint2*>(p.beta);
+    const uint2* gm = reinterpret_cast<const uint2*>(p.gamma) + c0;
+    const uint2* bt = reinterpret_cast<const uint2*>(p.beta) + c0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = i * 32 + lane;
@@ -116,48 +135,55 @@ __global__ void __launch_bounds__(256) ln_kernel(const LnParams p) {
 
 template <int MODE>
 static int launch_ln(const LnParams& p, cudaStream_t s, const char* name) {
-  const int nv = p.D / 128;
-  const int rows_per_block = 8;
+  // wide rows: 4 warps per row (D % 512 == 0); narrow rows: one warp per row
+  const bool wide = (p.D % 512 == 0) && p.D >= 2048;
+  const int wpr = wide ? 4 : 1;
+  const int nv = p.D / (128 * wpr);
+  const int rows_per_block = 8 / wpr;
   const int grid = (p.M + rows_per_block - 1) / rows_per_block;
-#define FX_LN_CASE(NVV)                                   \
-  case NVV:                                               \
-    ln_kernel<NVV, MODE><<<grid, 256, 0, s>>>(p);         \
-    break;
-  switch (nv) {
-    FX_LN_CASE(1) FX_LN_CASE(2) FX_LN_CASE(4) FX_LN_CASE(8) FX_LN_CASE(12) FX_LN_CASE(16) FX_LN_CASE(24)
-    FX_LN_CASE(32) FX_LN_CASE(40)
-    default:
-      set_error("%s: unsupported D=%d (D/128 must be one of 1,2,4,8,12,16,24,32,40)", name, p.D);
-      return FX_ERR_ARG;
+#define FX_LN_CASE(NVV, WPRV)                                   \
+  if (nv == NVV && wpr == WPRV) {                               \
+    ln_kernel<NVV, WPRV, MODE><<<grid, 256, 0, s>>>(p);         \
+    FX_CHECK_LAUNCH(name);                                      \
+    return FX_OK;                                               \
   }
+  FX_LN_CASE(1, 1) FX_LN_CASE(2, 1) FX_LN_CASE(4, 1) FX_LN_CASE(8, 1) FX_LN_CASE(12, 1)
+  FX_LN_CASE(4, 4) FX_LN_CASE(5, 4) FX_LN_CASE(6, 4) FX_LN_CASE(8, 4) FX_LN_CASE(10, 4) FX_LN_CASE(12, 4) FX_LN_CASE(16, 4)
 #undef FX_LN_CASE
-  FX_CHECK_LAUNCH(name);
-  return FX_OK;
+  set_error("%s: unsupported D=%d (supported: 128,256,512,1024,1536 and 2048,2560,3072,4096,5120,6144,8192)", name, p.D);
+  return FX_ERR_ARG;
 }
 
 // -------------------------------------------------------------------------------------------------
 // Full-width RMSNorm (+ RoPE), in place on bf16 rows.  WanRMSNorm :173-189 at :242-243/:363-364;
 // rope_apply :135-164 with the [22,21,21] frame/row/col split of the 64 complex pairs per head.
+// One launch covers q and k (two D-wide column blocks of the packed projection output) when w2 is given.
 // -------------------------------------------------------------------------------------------------
 struct RmsParams {
   __nv_bfloat16* x;
   long long ldx;
-  int M, D;
+  int M, D, ntensors;
   float eps;
   const __nv_bfloat16* w;
+  const __nv_bfloat16* w2;
   const float2* freqs;  // [1024][64] (cos, sin) or nullptr
   int gf, gh, gw, tok_offset, rows_per_batch;
 };
 
-template <int NV>  // NV = 16-byte vectors (8 bf16) per lane = D / 256
+template <int NV, int WPR>  // NV = 16-byte vectors (8 bf16) per lane = D / (256 * WPR)
 __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const RmsParams p) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= p.M) return;
-  const int lane = threadIdx.x & 31;
-  uint4* xr = reinterpret_cast<uint4*>(p.x + static_cast<long long>(row) * p.ldx);
+  __shared__ float red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_in_block = warp / WPR, warp_in_row = warp % WPR;
+  const int vrow = blockIdx.x * (8 / WPR) + row_in_block;  // virtual row = (token row, tensor)
+  const bool valid = vrow < p.M * p.ntensors;
+  const int row = valid ? vrow / p.ntensors : 0;
+  const int which = valid ? vrow - row * p.ntensors : 0;
+  const int c0 = warp_in_row * NV * 32;  // first 16-byte vector of this warp inside the row
+  uint4* xr = reinterpret_cast<uint4*>(p.x + static_cast<long long>(row) * p.ldx + static_cast<long long>(which) * p.D) + c0;
   uint4 v[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = xr[i * 32 + lane];
+  for (int i = 0; i < NV; ++i) v[i] = valid ? xr[i * 32 + lane] : make_uint4(0, 0, 0, 0);
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -169,37 +195,39 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const RmsParams p) {
     }
   }
   // r is rounded to bf16 before the multiply, as `.to(x.dtype)` does at :189
-  const float r = bf16_round(rsqrtf(warp_sum(ss) / static_cast<float>(p.D) + p.eps));
+  const float r = bf16_round(
+      rsqrtf(row_reduce<WPR>(ss, red, row_in_block, warp_in_row, lane) / static_cast<float>(p.D) + p.eps));
+  if (!valid) return;
 
-  int pos[3] = {0, 0, 0};
+  int pf = 0, ph = 0, pw = 0;
   bool rotate = false;
   if (p.freqs != nullptr) {
     const int t = p.tok_offset + row % p.rows_per_batch;
     if (t < p.gf * p.gh * p.gw) {
       rotate = true;
-      pos[0] = t / (p.gh * p.gw);
-      const int rem = t - pos[0] * (p.gh * p.gw);
-      pos[1] = rem / p.gw;
-      pos[2] = rem - pos[1] * p.gw;
+      pf = t / (p.gh * p.gw);
+      const int rem = t - pf * (p.gh * p.gw);
+      ph = rem / p.gw;
+      pw = rem - ph * p.gw;
     }
   }
-  const uint4* wr = reinterpret_cast<const uint4*>(p.w);
+  const uint4* wr = reinterpret_cast<const uint4*>(which == 0 ? p.w : p.w2) + c0;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int c = i * 32 + lane;  // vector index; elements [8c, 8c+8)
+    const int c = i * 32 + lane;  // vector index inside this warp's span
     const uint4 wv = __ldg(wr + c);
     const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
     const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
     uint32_t o[4];
-    const int pair0 = (c & 15) * 4;  // first complex pair of this vector inside its 128-wide head
+    const int pair0 = ((c0 + c) & 15) * 4;  // first complex pair of this vector inside its 128-wide head
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float a = bf16_round(bf16_round(bf16_lo(u[j]) * r) * bf16_lo(ww[j]));
       float b = bf16_round(bf16_round(bf16_hi(u[j]) * r) * bf16_hi(ww[j]));
       if (rotate) {
         const int pj = pair0 + j;
-        const int axis = pj < 22 ? 0 : (pj < 43 ? 1 : 2);
-        const float2 cs = __ldg(p.freqs + pos[axis] * 64 + pj);
+        const int pos = pj < 22 ? pf : (pj < 43 ? ph : pw);
+        const float2 cs = __ldg(p.freqs + pos * 64 + pj);
         const float re = a * cs.x - b * cs.y;
         const float im = a * cs.y + b * cs.x;
         a = re;
@@ -278,12 +306,14 @@ extern "C" int fx_ln_affine(const float* x, void* out, int M, int D, float eps, 
   return launch_ln<1>(p, reinterpret_cast<cudaStream_t>(stream), "fx_ln_affine");
 }
 
-extern "C" int fx_rmsnorm_rope(void* x, int64_t ldx, int M, int D, float eps, const void* weight, const float* freqs,
-                               int gf, int gh, int gw, int tok_offset, int rows_per_batch, void* stream) {
+extern "C" int fx_rmsnorm_rope(void* x, int64_t ldx, int M, int D, float eps, const void* weight,
+                               const void* weight2, const float* freqs, int gf, int gh, int gw, int tok_offset,
+                               int rows_per_batch, void* stream) {
   using namespace fx;
   FX_CHECK_ARG(x && weight, "fx_rmsnorm_rope: null pointer");
-  FX_CHECK_ARG(M > 0 && D > 0 && D % 256 == 0 && ldx % 8 == 0 && ldx >= D, "fx_rmsnorm_rope: bad shape M=%d D=%d", M,
-               D);
+  const int nt = weight2 ? 2 : 1;
+  FX_CHECK_ARG(M > 0 && D > 0 && D % 256 == 0 && ldx % 8 == 0 && ldx >= static_cast<int64_t>(nt) * D,
+               "fx_rmsnorm_rope: bad shape M=%d D=%d ldx=%lld", M, D, (long long)ldx);
   if (freqs != nullptr) {
     FX_CHECK_ARG(gf > 0 && gh > 0 && gw > 0 && gf <= 1024 && gh <= 1024 && gw <= 1024 && rows_per_batch > 0,
                  "fx_rmsnorm_rope: grid (%d,%d,%d) outside the 1024-entry RoPE table", gf, gh, gw);
@@ -291,27 +321,28 @@ extern "C" int fx_rmsnorm_rope(void* x, int64_t ldx, int M, int D, float eps, co
     rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1;
   }
   RmsParams p;
-  p.x = reinterpret_cast<__nv_bfloat16*>(x); p.ldx = ldx; p.M = M; p.D = D; p.eps = eps;
+  p.x = reinterpret_cast<__nv_bfloat16*>(x); p.ldx = ldx; p.M = M; p.D = D; p.ntensors = nt; p.eps = eps;
   p.w = reinterpret_cast<const __nv_bfloat16*>(weight);
+  p.w2 = reinterpret_cast<const __nv_bfloat16*>(weight2);
   p.freqs = reinterpret_cast<const float2*>(freqs);
   p.gf = gf; p.gh = gh; p.gw = gw; p.tok_offset = tok_offset; p.rows_per_batch = rows_per_batch;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int grid = (M + 7) / 8;
-  switch (D / 256) {
-    case 1: rmsnorm_rope_kernel<1><<<grid, 256, 0, s>>>(p); break;
-    case 2: rmsnorm_rope_kernel<2><<<grid, 256, 0, s>>>(p); break;
-    case 4: rmsnorm_rope_kernel<4><<<grid, 256, 0, s>>>(p); break;
-    case 6: rmsnorm_rope_kernel<6><<<grid, 256, 0, s>>>(p); break;
-    case 8: rmsnorm_rope_kernel<8><<<grid, 256, 0, s>>>(p); break;
-    case 12: rmsnorm_rope_kernel<12><<<grid, 256, 0, s>>>(p); break;
-    case 16: rmsnorm_rope_kernel<16><<<grid, 256, 0, s>>>(p); break;
-    case 20: rmsnorm_rope_kernel<20><<<grid, 256, 0, s>>>(p); break;
-    default:
-      set_error("fx_rmsnorm_rope: unsupported D=%d (D/256 must be one of 1,2,4,6,8,12,16,20)", D);
-      return FX_ERR_ARG;
+  const bool wide = (D % 1024 == 0) && D >= 2048;
+  const int wpr = wide ? 4 : 1;
+  const int nv = D / (256 * wpr);
+  const long long vrows = static_cast<long long>(M) * nt;
+  const int grid = static_cast<int>((vrows + (8 / wpr) - 1) / (8 / wpr));
+#define FX_RMS_CASE(NVV, WPRV)                                   \
+  if (nv == NVV && wpr == WPRV) {                                \
+    rmsnorm_rope_kernel<NVV, WPRV><<<grid, 256, 0, s>>>(p);      \
+    FX_CHECK_LAUNCH("fx_rmsnorm_rope");                          \
+    return FX_OK;                                                \
   }
-  FX_CHECK_LAUNCH("fx_rmsnorm_rope");
-  return FX_OK;
+  FX_RMS_CASE(1, 1) FX_RMS_CASE(2, 1) FX_RMS_CASE(4, 1) FX_RMS_CASE(6, 1) FX_RMS_CASE(10, 1)
+  FX_RMS_CASE(2, 4) FX_RMS_CASE(3, 4) FX_RMS_CASE(4, 4) FX_RMS_CASE(5, 4) FX_RMS_CASE(6, 4) FX_RMS_CASE(8, 4)
+#undef FX_RMS_CASE
+  set_error("fx_rmsnorm_rope: unsupported D=%d (supported: 256,512,1024,1536,2560 and 2048,3072,4096,5120,6144,8192)", D);
+  return FX_ERR_ARG;
 }
 
 extern "C" int fx_cfg_euler_step(const void* vu, const void* vc, float guidance, float dsigma, float* lat,

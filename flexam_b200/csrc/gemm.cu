@@ -2,8 +2,13 @@
 // accumulators double-buffered in TMEM) -> fused epilogues. One CTA per SM, static round-robin tile schedule
 // with M-grouped rasterisation so the concurrently resident tiles share weight and activation panels in L2.
 //
+// Epilogues (include/flexam_b200.h): bf16 store, GELU-tanh + bf16 store, fp32 store, and the gated fp32 residual
+// `x += bf16(acc + bias) * gate`. The residual variant never reads x: each epilogue warp stages its 32 x 32 fp32
+// slab in swizzled shared memory and issues a TMA reduction (`cp.reduce.async.bulk.tensor ... add.f32`), so the
+// read-modify-write happens in L2 with fully coalesced traffic while the next slab is being computed.
+//
 // Replaces the nn.Linear / conv-as-GEMM call sites of FlexAM/models/wan_transformer3d_FlexAM.py
-// (:242-261, :363-370, :414-416, :506, :624-625, :675-678, :959-964); see include/flexam_b200.h.
+// (:242-261, :363-370, :414-416, :456, :461, :468, :506, :624-625, :675-678, :959-964).
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -15,15 +20,18 @@ constexpr int kUmmaK = 16;    // K per tcgen05.mma for 16-bit inputs
 constexpr int kGemmThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
 constexpr int kEpiThreads = 128;
 constexpr int kAccStride = 256;    // TMEM columns between the two accumulator buffers
+constexpr int kSlabBytes = 32 * 32 * 4;  // one warp's 32 rows x 32 fp32 columns (128-byte rows, SWIZZLE_128B)
 
-template <int BN>
+template <int BN, int EPI>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kStagingBytes = (EPI == FX_EPI_RESID_F32) ? 4 * 2 * kSlabBytes : 0;  // 4 warps x 2 slabs
+  static constexpr int kBudget = 226 * 1024 - 2048 - kStagingBytes;
+  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;  // +1024: alignment
 };
 
 struct GemmParams {
@@ -48,7 +56,23 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& 
   n_tile = r / gsize;
 }
 
-// One 32-column slab of one output row: v[j] = accumulator (fp32 bits) for column col0 + j.
+// y[j] = accumulator + bias for 8 consecutive columns starting at `col` (col < N guaranteed by the caller)
+__device__ __forceinline__ void add_bias8(const GemmParams& p, int col, const uint32_t* v, float (&y)[8]) {
+  if (p.bias != nullptr) {
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      y[2 * j] = __uint_as_float(v[2 * j]) + bf16_lo(bw[j]);
+      y[2 * j + 1] = __uint_as_float(v[2 * j + 1]) + bf16_hi(bw[j]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(v[j]);
+  }
+}
+
+// Direct-store epilogues: one 32-column slab of one output row, v[j] = accumulator bits for column col0 + j.
 template <int EPI>
 __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int col0, uint32_t (&v)[32]) {
   // 8-column groups; N % 8 == 0 so a group is either fully valid or fully out of range.
@@ -57,18 +81,7 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int
     const int col = col0 + g * 8;
     if (col >= p.N) break;
     float y[8];
-    if (p.bias != nullptr) {
-      const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
-      const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        y[2 * j] = __uint_as_float(v[g * 8 + 2 * j]) + bf16_lo(bw[j]);
-        y[2 * j + 1] = __uint_as_float(v[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(v[g * 8 + j]);
-    }
+    add_bias8(p, col, &v[g * 8], y);
     if constexpr (EPI == FX_EPI_BF16 || EPI == FX_EPI_GELU_BF16) {
       if constexpr (EPI == FX_EPI_GELU_BF16) {
 #pragma unroll
@@ -81,15 +94,29 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int
       o.w = pack_bf16x2(y[6], y[7]);
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col;
       *reinterpret_cast<uint4*>(dst) = o;
-    } else if constexpr (EPI == FX_EPI_F32) {
+    } else {  // FX_EPI_F32
       float* dst = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
       float4 o0 = make_float4(bf16_round(y[0]), bf16_round(y[1]), bf16_round(y[2]), bf16_round(y[3]));
       float4 o1 = make_float4(bf16_round(y[4]), bf16_round(y[5]), bf16_round(y[6]), bf16_round(y[7]));
       *reinterpret_cast<float4*>(dst) = o0;
       *reinterpret_cast<float4*>(dst + 4) = o1;
-    } else {  // FX_EPI_RESID_F32
+    }
+  }
+}
+
+// Residual epilogue, staging half: writes bf16(acc + bias) * gate for this lane's row into the warp's swizzled slab
+// (row r at r*128 B, 16-byte chunk c at position c ^ (r & 7) — the SWIZZLE_128B pattern the output tensor map expects).
+__device__ __forceinline__ void resid_stage_row32(const GemmParams& p, bool row_valid, long long u, int col0,
+                                                  const uint32_t (&v)[32], uint8_t* slab, int lane) {
+  const bool has_gate = (p.gate_mod != nullptr) || (p.gate_e != nullptr);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = col0 + g * 8;
+    float o[8];
+    if (row_valid && col < p.N) {
+      float y[8];
+      add_bias8(p, col, &v[g * 8], y);
       float gate[8];
-      const bool has_gate = (p.gate_mod != nullptr) || (p.gate_e != nullptr);
 #pragma unroll
       for (int j = 0; j < 8; ++j) gate[j] = has_gate ? 0.f : 1.f;
       if (p.gate_mod != nullptr) {
@@ -99,35 +126,34 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int
         gate[4] += g1.x; gate[5] += g1.y; gate[6] += g1.z; gate[7] += g1.w;
       }
       if (p.gate_e != nullptr) {
-        const long long u = p.row_idx ? p.row_idx[row] : 0;
         const float* ge = p.gate_e + u * p.gate_e_stride + col;
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(ge));
         const float4 g1 = __ldg(reinterpret_cast<const float4*>(ge + 4));
         gate[0] += g0.x; gate[1] += g0.y; gate[2] += g0.z; gate[3] += g0.w;
         gate[4] += g1.x; gate[5] += g1.y; gate[6] += g1.z; gate[7] += g1.w;
       }
-      float* dst = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
-      float4 x0 = *reinterpret_cast<const float4*>(dst);
-      float4 x1 = *reinterpret_cast<const float4*>(dst + 4);
-      x0.x += bf16_round(y[0]) * gate[0]; x0.y += bf16_round(y[1]) * gate[1];
-      x0.z += bf16_round(y[2]) * gate[2]; x0.w += bf16_round(y[3]) * gate[3];
-      x1.x += bf16_round(y[4]) * gate[4]; x1.y += bf16_round(y[5]) * gate[5];
-      x1.z += bf16_round(y[6]) * gate[6]; x1.w += bf16_round(y[7]) * gate[7];
-      *reinterpret_cast<float4*>(dst) = x0;
-      *reinterpret_cast<float4*>(dst + 4) = x1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = bf16_round(y[j]) * gate[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;  // clipped by the TMA store anyway
     }
+    uint8_t* rowp = slab + lane * 128;
+    *reinterpret_cast<float4*>(rowp + (((2 * g) ^ (lane & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(rowp + (((2 * g + 1) ^ (lane & 7)) << 4)) = make_float4(o[4], o[5], o[6], o[7]);
   }
 }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+                 const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+  using Cfg = GemmCfg<BN, EPI>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* staging = smem + kStages * Cfg::kStageBytes;  // 1024-aligned: stage sizes are multiples of 1024
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -141,6 +167,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if constexpr (EPI == FX_EPI_RESID_F32) tma_prefetch_desc(&tmap_out);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -220,26 +247,54 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else {
     // ===================== epilogue warps: TMEM -> registers -> global =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    uint8_t* my_slabs = staging + (warp - 2) * 2 * kSlabBytes;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t slab_sel = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int m_tile, n_tile;
       tile_coords(p, tile, m_tile, n_tile);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_tile * kBM + quad * 32 + lane;
+      const int row0 = m_tile * kBM + quad * 32;
+      const int row = row0 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride;
+      long long u = 0;
+      if constexpr (EPI == FX_EPI_RESID_F32) {
+        if (p.row_idx != nullptr && row < p.M) u = p.row_idx[row];
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
         tmem_wait_ld();
-        if (row < p.M) epilogue_row32<EPI>(p, row, n_tile * BN + c * 32, v);
+        const int col0 = n_tile * BN + c * 32;
+        if constexpr (EPI == FX_EPI_RESID_F32) {
+          if (col0 < p.N) {  // warp-uniform
+            uint8_t* slab = my_slabs + (slab_sel & 1) * kSlabBytes;
+            if (lane == 0) tma_wait_group_read<1>();  // the reduction issued from this slab two slabs ago has read it
+            __syncwarp();
+            resid_stage_row32(p, row < p.M, u, col0, v, slab, lane);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_reduce_add_2d(&tmap_out, slab, col0, row0);
+              tma_commit_group();
+            }
+            ++slab_sel;
+          }
+        } else {
+          if (row < p.M) epilogue_row32<EPI>(p, row, col0, v);
+        }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+    if constexpr (EPI == FX_EPI_RESID_F32) {
+      if (lane == 0) tma_wait_group<0>();
+      __syncwarp();
     }
   }
 
@@ -252,8 +307,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 template <int BN, int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, EPI>;
+  static_assert(Cfg::kStages >= 3, "pipeline too shallow");
+  static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
   static bool configured = false;  // per (BN, EPI) instantiation; attribute is per-function, set once per process
   auto kern = gemm_bf16_kernel<BN, EPI>;
   if (!configured) {
@@ -266,19 +324,19 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   }
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tout, p);
   FX_CHECK_LAUNCH("fx_gemm_bf16");
   return FX_OK;
 }
 
 template <int BN>
-static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                        cudaStream_t s) {
+static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
+                        const GemmParams& p, cudaStream_t s) {
   switch (epi) {
-    case FX_EPI_BF16: return launch_gemm<BN, FX_EPI_BF16>(ta, tb, p, s);
-    case FX_EPI_GELU_BF16: return launch_gemm<BN, FX_EPI_GELU_BF16>(ta, tb, p, s);
-    case FX_EPI_F32: return launch_gemm<BN, FX_EPI_F32>(ta, tb, p, s);
-    case FX_EPI_RESID_F32: return launch_gemm<BN, FX_EPI_RESID_F32>(ta, tb, p, s);
+    case FX_EPI_BF16: return launch_gemm<BN, FX_EPI_BF16>(ta, tb, tout, p, s);
+    case FX_EPI_GELU_BF16: return launch_gemm<BN, FX_EPI_GELU_BF16>(ta, tb, tout, p, s);
+    case FX_EPI_F32: return launch_gemm<BN, FX_EPI_F32>(ta, tb, tout, p, s);
+    case FX_EPI_RESID_F32: return launch_gemm<BN, FX_EPI_RESID_F32>(ta, tb, tout, p, s);
   }
   set_error("fx_gemm_bf16: unknown epilogue %d", epi);
   return FX_ERR_ARG;
@@ -321,7 +379,7 @@ extern "C" int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t l
   p.num_n_tiles = (N + bn - 1) / bn;
   p.group_m = 16;
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tout;
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
     const uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
@@ -334,11 +392,19 @@ extern "C" int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t l
     const uint32_t box[2] = {kBK, static_cast<uint32_t>(bn)};
     if (!make_tmap_bf16(&tb, w, 2, dims, strides, box)) return FX_ERR_CUDA;
   }
+  if (epilogue == FX_EPI_RESID_F32) {  // fp32 [M, N] view of the residual stream, 32 x 32 boxes for the reduction
+    const uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(ldo) * 4};
+    const uint32_t box[2] = {32, 32};
+    if (!make_tmap(&tout, true, out, 2, dims, strides, box)) return FX_ERR_CUDA;
+  } else {
+    tout = ta;  // unused by the other epilogues
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 256: return dispatch_epi<256>(epilogue, ta, tb, p, s);
-    case 192: return dispatch_epi<192>(epilogue, ta, tb, p, s);
-    case 128: return dispatch_epi<128>(epilogue, ta, tb, p, s);
-    default: return dispatch_epi<64>(epilogue, ta, tb, p, s);
+    case 256: return dispatch_epi<256>(epilogue, ta, tb, tout, p, s);
+    case 192: return dispatch_epi<192>(epilogue, ta, tb, tout, p, s);
+    case 128: return dispatch_epi<128>(epilogue, ta, tb, tout, p, s);
+    default: return dispatch_epi<64>(epilogue, ta, tb, tout, p, s);
   }
 }

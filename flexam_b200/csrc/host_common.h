@@ -17,6 +17,9 @@ int num_sms();  // SM count of the current device (cached per device)
 // dims/strides are innermost-first; strides in BYTES for dims 1..rank-1.
 bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box);
+// Same for bf16 (is_f32 = false) or fp32 (true) elements; the innermost box must span exactly 128 bytes.
+bool make_tmap(CUtensorMap* out, bool is_f32, const void* base, int rank, const uint64_t* dims,
+               const uint64_t* strides_bytes, const uint32_t* box);
 
 #define FX_CHECK_ARG(cond, ...)   \
   do {                            \

@@ -23,7 +23,7 @@ SIGNATURES = {
     "fx_gemm_bf16": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _i64, _vp, _vp],
     "fx_ln_modulate": [_vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp],
     "fx_ln_affine": [_vp, _vp, _i, _i, _f, _vp, _vp, _vp],
-    "fx_rmsnorm_rope": [_vp, _i64, _i, _i, _f, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "fx_rmsnorm_rope": [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fx_fmha_fwd": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _f, _vp],
     "fx_patchify": [C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _i, _i, _i, _vp, _i64, _vp],
     "fx_unpatchify": [_vp, _i64, _vp, _i, _i, _i, _i, _vp],

@@ -380,8 +380,7 @@ class NativeEngine:
             ops.ln_modulate(xs, h, self.eps, mod[0], mod[1], e0v[:, 0], e0v[:, 1], 6 * D, row_idx, dmod[0],
                             de0v[:, 0], 2 * D, Lp)
             self._gemm(h, w["wqkv"], w["bqkv"], qkv, FX_EPI_BF16)
-            ops.rmsnorm_rope(qkv[:, :D], w["nq"], self.eps, self.freqs, grid, tok0, Lp)
-            ops.rmsnorm_rope(qkv[:, D:2 * D], w["nk"], self.eps, self.freqs, grid, tok0, Lp)
+            ops.rmsnorm_rope(qkv[:, :2 * D], w["nq"], self.eps, self.freqs, grid, tok0, Lp, weight2=w["nk"])
             if P == 1:
                 self._fmha(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], attn4, scale)
             else:           # Ulysses: head-scatter all-to-all around attention, one sample at a time
@@ -400,7 +399,7 @@ class NativeEngine:
                             de0v[:, 1], 2 * D, Lp)
             self._gemm(h, w["w1"], w["b1"], ffn, FX_EPI_GELU_BF16)
             self._gemm(ffn, w["w2"], w["b2"], xs, FX_EPI_RESID_F32, gate_mod=mod[5], gate_e=e0v[:, 5], row_idx=row_idx)
-            self.launches += 6
+            self.launches += 5
             if block_hook is not None:
                 block_hook(i, xs)
         if teacache is not None and run_blocks:

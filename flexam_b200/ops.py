@@ -84,14 +84,20 @@ def ln_affine(x: torch.Tensor, out: torch.Tensor, eps: float, gamma: torch.Tenso
 
 
 def rmsnorm_rope(x: torch.Tensor, weight: torch.Tensor, eps: float, freqs: Optional[torch.Tensor] = None,
-                 grid: Sequence[int] = (0, 0, 0), tok_offset: int = 0, rows_per_batch: int = 0) -> torch.Tensor:
-    """In place on x: bf16 [M, D] view (row stride free)."""
+                 grid: Sequence[int] = (0, 0, 0), tok_offset: int = 0, rows_per_batch: int = 0,
+                 weight2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """In place on x: bf16 [M, D] view (row stride free). With weight2, x is an [M, 2D] view whose second D columns
+    are normed with weight2 in the same launch (q and k of the packed projection output)."""
     _req(x, bf16, "rmsnorm_rope.x"), _req(weight, bf16, "rmsnorm_rope.weight")
     if freqs is not None:
         _req(freqs, f32, "rmsnorm_rope.freqs")
     M, D = x.shape
-    st = _l.load().fx_rmsnorm_rope(_p(x), x.stride(0), M, D, eps, _p(weight), _p(freqs), int(grid[0]), int(grid[1]),
-                                   int(grid[2]), tok_offset, rows_per_batch if rows_per_batch > 0 else M, _stream())
+    if weight2 is not None:
+        _req(weight2, bf16, "rmsnorm_rope.weight2")
+        D //= 2
+    st = _l.load().fx_rmsnorm_rope(_p(x), x.stride(0), M, D, eps, _p(weight), _p(weight2), _p(freqs), int(grid[0]),
+                                   int(grid[1]), int(grid[2]), tok_offset, rows_per_batch if rows_per_batch > 0 else M,
+                                   _stream())
     _l.check(st, "fx_rmsnorm_rope")
     return x
 

@@ -84,9 +84,11 @@ int fx_ln_affine(const float* x, void* out, int M, int D, float eps, const void*
  *   pos = frame for j<22, row for 22<=j<43, col for j>=43 of token t = tok_offset + (m % rows_per_batch);
  *   frame/row/col from t over the grid (gf,gh,gw); tokens >= gf*gh*gw are left unrotated.
  *   freqs: f32 [1024][64][2] (cos,sin).  x: bf16 [M, D] with row stride ldx.  D % 256 == 0, head_dim 128.
+ *   weight2 != NULL: the same launch also norms (and rotates) the next D columns [D, 2D) of every row with
+ *   weight2 — q and k of the packed q|k|v projection output in one pass.
  */
-int fx_rmsnorm_rope(void* x, int64_t ldx, int M, int D, float eps, const void* weight, const float* freqs,
-                    int gf, int gh, int gw, int tok_offset, int rows_per_batch, void* stream);
+int fx_rmsnorm_rope(void* x, int64_t ldx, int M, int D, float eps, const void* weight, const void* weight2,
+                    const float* freqs, int gf, int gh, int gw, int tok_offset, int rows_per_batch, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Non-causal attention forward on tcgen05/TMEM, head_dim 128 (attention()/flash_attention,

@@ -60,7 +60,12 @@ def ln_affine(x, out, eps, gamma, beta):
     return out
 
 
-def rmsnorm_rope(x, weight, eps, freqs=None, grid=(0, 0, 0), tok_offset=0, rows_per_batch=0):
+def rmsnorm_rope(x, weight, eps, freqs=None, grid=(0, 0, 0), tok_offset=0, rows_per_batch=0, weight2=None):
+    if weight2 is not None:     # q | k column blocks of the packed projection output, one launch
+        D2 = x.shape[1] // 2
+        rmsnorm_rope(x[:, :D2], weight, eps, freqs, grid, tok_offset, rows_per_batch or x.shape[0])
+        rmsnorm_rope(x[:, D2:], weight2, eps, freqs, grid, tok_offset, rows_per_batch or x.shape[0])
+        return x
     M, D = x.shape
     xf = x.float()
     r = _rb(torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps))

@@ -148,6 +148,21 @@ def test_ln_and_rmsnorm_rope(dev):
     assert _rel(buf[:, :D].cpu().view(Bq, L, 24, 128), want) < 3e-3
     assert torch.equal(buf[:, D:], keep[:, D:])  # neighbours in the packed buffer untouched
 
+    # q|k in one launch must equal two separate launches, and leave v alone
+    w2 = (1 + 0.1 * torch.randn(D, device=dev, generator=g)).bfloat16()
+    one = keep.clone()
+    ops.rmsnorm_rope(one[:, :2 * D], w, 1e-6, O.rope_table_f32(128).to(dev), grid, 0, L, weight2=w2)
+    two = keep.clone()
+    ops.rmsnorm_rope(two[:, :D], w, 1e-6, O.rope_table_f32(128).to(dev), grid, 0, L)
+    ops.rmsnorm_rope(two[:, D:2 * D], w2, 1e-6, O.rope_table_f32(128).to(dev), grid, 0, L)
+    assert torch.equal(one, two) and torch.equal(one[:, 2 * D:], keep[:, 2 * D:])
+    # narrow rows (one warp per row) and a sequence-parallel token offset
+    small = torch.randn(50, 256, device=dev, generator=g).bfloat16()
+    ws = torch.ones(256, device=dev, dtype=torch.bfloat16)
+    ref_small = O._rmsnorm(small.float(), ws.float(), 1e-6, "bf16")
+    ops.rmsnorm_rope(small, ws, 1e-6)
+    assert _rel(small, ref_small) < 3e-3
+
 
 # ------------------------------------------------------------------------------------------------------
 # whole denoising step
