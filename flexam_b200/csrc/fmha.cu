@@ -13,6 +13,8 @@
 //
 // Replaces attention()/flash_attention() (FlexAM/models/attention_utils.py:174-233) at its two call sites,
 // wan_transformer3d_FlexAM.py:251-256 (self, Lk = all tokens) and :367 (cross, Lk = 512, unmasked).
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -31,12 +33,50 @@ struct FmhaParams {
   float scale_log2;
 };
 
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
+// Packed fp32x2 arithmetic (sm_100): one issue slot for two lanes of work.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)),
+        "l"(reinterpret_cast<const unsigned long long&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+  return d;
+}
+
+// 2^x for a pair, x <= ~8: n = round(x) via the 1.5*2^23 magic constant (n lands in the low mantissa bits of t),
+// f = x - n in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial, exponent patched in with an integer add.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  const float kMagic = 12582912.f;
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 t = add2(x, make_float2(kMagic, kMagic));
+  const float2 n = add2(t, make_float2(-kMagic, -kMagic));
+  const float2 f = fma2(n, make_float2(-1.f, -1.f), x);
+  float2 q = fma2(f, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111251f, 0.2426111251f));
+  q = fma2(q, f, make_float2(0.6932609677f, 0.6932609677f));
+  q = fma2(q, f, make_float2(0.9999280572f, 0.9999280572f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
+// kPolyPairs: of every 4 (x0,x1) pairs of a score row, how many take the FMA-pipe exp2 instead of MUFU.EX2
+template <int kPolyPairs>
 __global__ void __launch_bounds__(kFmhaThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const FmhaParams p) {
@@ -237,21 +277,32 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       }
 
-      float sum0 = 0.f, sum1 = 0.f;
+      // P = exp2(S * scale_log2 - m_used) on packed fp32 pairs. The MUFU (16 ex2/clk/SM) would cost as many cycles
+      // as the MMAs of the tile, so kPolyPairs of every 4 pairs are evaluated on the FMA pipe instead
+      // (round-to-nearest range reduction + degree-3 polynomial, rel. error 7.5e-5 << bf16 rounding of P).
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+      const float2 nm2 = make_float2(-m_used, -m_used);
+      float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + 2 * i]), p.scale_log2, -m_used));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + 2 * i + 1]), p.scale_log2, -m_used));
-          sum0 += e0;
-          sum1 += e1;
-          pk[i] = pack_bf16x2(e0, e1);
+          const float2 x = fma2(make_float2(__uint_as_float(s[c * 32 + 2 * i]), __uint_as_float(s[c * 32 + 2 * i + 1])),
+                                sc2, nm2);
+          float2 e;
+          if ((i & 3) < kPolyPairs) {
+            e = exp2_poly2(x);
+          } else {
+            e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          }
+          if (i & 1) sum_b = add2(sum_b, e); else sum_a = add2(sum_a, e);
+          pk[i] = pack_bf16x2(e.x, e.y);
         }
         tmem_st16(s_tmem + c * 16, pk);
       }
-      l += sum0 + sum1;
+      sum_a = add2(sum_a, sum_b);
+      l += sum_a.x + sum_a.y;
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[w]);
@@ -323,14 +374,23 @@ extern "C" int fx_fmha_fwd(const void* q, int64_t q_stride_b, int64_t q_stride_l
   if (!make_qkv_tmap(&tk, k, bs(k_stride_b, k_stride_l, Lk), k_stride_l, B, H, Lk)) return FX_ERR_CUDA;
   if (!make_qkv_tmap(&tv, v, bs(v_stride_b, v_stride_l, Lk), v_stride_l, B, H, Lk)) return FX_ERR_CUDA;
 
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fmha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmhaSmem);
+  // exp2 split between MUFU and the FMA pipe: 2 of 4 pairs by default; FX_FMHA_POLY=0..3 overrides it for tuning runs
+  static int poly = -1;
+  if (poly < 0) {
+    const char* env = getenv("FX_FMHA_POLY");
+    poly = (env && env[0] >= '0' && env[0] <= '3') ? env[0] - '0' : 2;
+  }
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const FmhaParams);
+  const Kern kerns[4] = {fmha_fwd_kernel<0>, fmha_fwd_kernel<1>, fmha_fwd_kernel<2>, fmha_fwd_kernel<3>};
+  const Kern kern = kerns[poly];
+  static bool configured[4] = {false, false, false, false};
+  if (!configured[poly]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmhaSmem);
     if (e != cudaSuccess) {
       set_error("fx_fmha_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return FX_ERR_CUDA;
     }
-    configured = true;
+    configured[poly] = true;
   }
   FmhaParams p;
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
@@ -340,7 +400,7 @@ extern "C" int fx_fmha_fwd(const void* q, int64_t q_stride_b, int64_t q_stride_l
   p.Lk = Lk;
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((Lq + 255) / 256, H, B);
-  fmha_fwd_kernel<<<grid, kFmhaThreads, kFmhaSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  kern<<<grid, kFmhaThreads, kFmhaSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
   FX_CHECK_LAUNCH("fx_fmha_fwd");
   return FX_OK;
 }

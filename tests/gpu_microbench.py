@@ -1,0 +1,111 @@
+"""Kernel-level timing at the config-2 shapes (run on the GPU box): CUDA events, warm-up, L2 flushed between
+repetitions by the working set itself or an explicit 256 MB write. Not a pytest file; prints one JSON line per case.
+
+    python tests/gpu_microbench.py [fmha] [gemm] [rows]
+"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from flexam_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, reps=10, warm=3, flush=True):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    total = 0.0
+    for _ in range(reps):
+        if flush:
+            flush_buf.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        total += a.elapsed_time(b)
+    return total / reps
+
+
+def bench_fmha():
+    B, H, L = 2, 24, 11648
+    g = torch.Generator(device=dev).manual_seed(0)
+    qkv = torch.randn(B * L, 3 * H * 128, device=dev, generator=g).bfloat16()
+    v5 = qkv.view(B, L, 3, H, 128)
+    out = torch.empty(B, L, H, 128, device=dev, dtype=torch.bfloat16)
+    ms = timeit(lambda: ops.fmha(v5[:, :, 0], v5[:, :, 1], v5[:, :, 2], out, 128 ** -0.5))
+    fl = 4.0 * B * H * L * L * 128
+    print(json.dumps({"case": "fmha_self", "poly": os.environ.get("FX_FMHA_POLY", "default"), "ms": ms,
+                      "tflops": fl / ms / 1e9}))
+    # accuracy of the exp2 split against fp32 softmax on a slice
+    q, k, v = v5[:1, :512, 0, :2].float(), v5[:1, :, 1, :2].float(), v5[:1, :, 2, :2].float()
+    s = torch.einsum("bqhd,bkhd->bhqk", q, k) * 128 ** -0.5
+    want = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), v)
+    got = out[:1, :512, :2].float()
+    print(json.dumps({"case": "fmha_self_err", "rel": ((got - want).norm() / want.norm()).item()}))
+    kv = torch.randn(B * 512, 2 * H * 128, device=dev, generator=g).bfloat16().view(B, 512, 2, H, 128)
+    ms = timeit(lambda: ops.fmha(v5[:, :, 0], kv[:, :, 0], kv[:, :, 1], out, 128 ** -0.5))
+    print(json.dumps({"case": "fmha_cross", "ms": ms, "tflops": 4.0 * B * H * L * 512 * 128 / ms / 1e9}))
+
+
+def bench_gemm():
+    M = 2 * 11648
+    g = torch.Generator(device=dev).manual_seed(0)
+    for name, N, K, epi in (("qkv", 9216, 3072, 0), ("o_resid", 3072, 3072, 3), ("cq", 3072, 3072, 0),
+                            ("ffn1_gelu", 14336, 3072, 1), ("ffn2_resid", 3072, 14336, 3)):
+        a = (torch.randn(M, K, device=dev, generator=g) * 0.5).bfloat16()
+        w = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+        b = torch.randn(N, device=dev, generator=g).bfloat16()
+        out = torch.zeros(M, N, device=dev, dtype=torch.float32 if epi == 3 else torch.bfloat16)
+        gm = torch.randn(N, device=dev, generator=g)
+        ge = torch.randn(2, 6, N, device=dev, generator=g)
+        idx = torch.randint(0, 2, (M,), device=dev, generator=g, dtype=torch.int32)
+        if epi == 3:
+            fn = lambda: ops.gemm(a, w, b, out, 3, gate_mod=gm, gate_e=ge[:, 2], row_idx=idx)  # noqa: E731
+        else:
+            fn = lambda: ops.gemm(a, w, b, out, epi)  # noqa: E731
+        ms = timeit(fn)
+        print(json.dumps({"case": "gemm_" + name, "mode": os.environ.get("FX_GEMM_MODE", "default"), "ms": ms,
+                          "tflops": 2.0 * M * N * K / ms / 1e9}))
+
+
+def bench_rows():
+    M, D = 2 * 11648, 3072
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(M, D, device=dev, generator=g)
+    out = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    mod = torch.randn(6, D, device=dev, generator=g)
+    e = torch.randn(2, 6, D, device=dev, generator=g)
+    dens = torch.randn(2, 2, D, device=dev, generator=g)
+    idx = torch.randint(0, 2, (M,), device=dev, generator=g, dtype=torch.int32)
+    ms = timeit(lambda: ops.ln_modulate(x, out, 1e-6, mod[0], mod[1], e[:, 0], e[:, 1], 6 * D, idx, mod[2], dens[:, 0],
+                                        2 * D, M // 2))
+    print(json.dumps({"case": "ln_modulate", "ms": ms, "gbs": M * D * 6 / ms / 1e6}))
+    gam = torch.ones(D, device=dev, dtype=torch.bfloat16)
+    ms = timeit(lambda: ops.ln_affine(x, out, 1e-6, gam, gam))
+    print(json.dumps({"case": "ln_affine", "ms": ms, "gbs": M * D * 6 / ms / 1e6}))
+    qkv = torch.randn(M, 3 * D, device=dev, generator=g).bfloat16()
+    from flexam_b200.model import rope_table
+    fr = rope_table(128).to(dev)
+    ms = timeit(lambda: ops.rmsnorm_rope(qkv[:, :2 * D], gam, 1e-6, fr, (26, 16, 28), 0, M // 2, weight2=gam))
+    print(json.dumps({"case": "rmsnorm_rope_qk", "ms": ms, "gbs": M * D * 8 / ms / 1e6}))
+    cq = torch.randn(M, D, device=dev, generator=g).bfloat16()
+    ms = timeit(lambda: ops.rmsnorm_rope(cq, gam, 1e-6))
+    print(json.dumps({"case": "rmsnorm_cq", "ms": ms, "gbs": M * D * 4 / ms / 1e6}))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["fmha", "gemm", "rows"]
+    if "fmha" in which:
+        bench_fmha()
+    if "gemm" in which:
+        bench_gemm()
+    if "rows" in which:
+        bench_rows()
