@@ -374,11 +374,11 @@ extern "C" int fx_fmha_fwd(const void* q, int64_t q_stride_b, int64_t q_stride_l
   if (!make_qkv_tmap(&tk, k, bs(k_stride_b, k_stride_l, Lk), k_stride_l, B, H, Lk)) return FX_ERR_CUDA;
   if (!make_qkv_tmap(&tv, v, bs(v_stride_b, v_stride_l, Lk), v_stride_l, B, H, Lk)) return FX_ERR_CUDA;
 
-  // exp2 split between MUFU and the FMA pipe: 2 of 4 pairs by default; FX_FMHA_POLY=0..3 overrides it for tuning runs
+  // exp2 split between MUFU and the FMA pipe: measured fastest with all-MUFU (0); FX_FMHA_POLY=0..3 overrides it
   static int poly = -1;
   if (poly < 0) {
     const char* env = getenv("FX_FMHA_POLY");
-    poly = (env && env[0] >= '0' && env[0] <= '3') ? env[0] - '0' : 2;
+    poly = (env && env[0] >= '0' && env[0] <= '3') ? env[0] - '0' : 0;
   }
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const FmhaParams);
   const Kern kerns[4] = {fmha_fwd_kernel<0>, fmha_fwd_kernel<1>, fmha_fwd_kernel<2>, fmha_fwd_kernel<3>};

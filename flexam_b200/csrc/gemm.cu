@@ -306,6 +306,233 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile with UMMA
+// M = 256. Each CTA stages its own 128 rows of A and its own 128-row half of the B panel (32 KB per stage
+// instead of 48 KB), so smem fill + operand-read traffic per SM drops by a third and the ring gets 6-7 stages.
+// Both CTAs run a TMA producer and the epilogue; only the leader (cluster rank 0) issues MMAs. TMA completions
+// from both CTAs are credited to the LEADER's full barrier; tcgen05.commit multicasts the "slot free" and
+// "accumulator ready" arrivals to both CTAs; the peer's epilogue releases the accumulator on the leader's barrier.
+// ---------------------------------------------------------------------------------------------------------
+template <int EPI>
+struct Gemm2Cfg {
+  static constexpr int kBN = 256;
+  static constexpr int kABytes = kBM * kBK * 2;        // this CTA's 128 rows of A
+  static constexpr int kBBytes = (kBN / 2) * kBK * 2;  // this CTA's half of the B panel
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = (EPI == FX_EPI_RESID_F32) ? 4 * 2 * kSlabBytes : 0;
+  static constexpr int kBudget = 226 * 1024 - 2048 - kStagingBytes;
+  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;
+};
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+  using Cfg = Gemm2Cfg<EPI>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int BN = Cfg::kBN;
+  extern __shared__ uint8_t smem_raw[];
+  // identical carve-up in both CTAs: barrier offsets must match for multicast commits / peer arrivals
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;  // 256 x 256 tiles
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    if constexpr (EPI == FX_EPI_RESID_F32) tma_prefetch_desc(&tmap_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);   // used in the leader only: its own expect_tx arrival + bytes from both CTAs
+      mbar_init(&empty_bar[s], 1);  // one multicast commit per use
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 8);  // leader only: 4 epilogue warps x 2 CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();  // peer barriers initialised and TMEM allocated before any cross-CTA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        int m_tile, n_tile;
+        tile_coords(p, tile, m_tile, n_tile);
+        const int a_row = m_tile * 256 + static_cast<int>(cta_rank) * kBM;
+        const int b_row = n_tile * BN + static_cast<int>(cta_rank) * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          tma_load_2d_2sm(sa, &tmap_a, leader_full, kb * kBK, a_row);
+          tma_load_2d_2sm(sb, &tmap_b, leader_full, kb * kBK, b_row);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint64_t a_desc = umma_desc_sw128(a_addr + k * kUmmaK * 2, 16, 1024);
+            const uint64_t b_desc = umma_desc_sw128(b_addr + k * kUmmaK * 2, 16, 1024);
+            umma_ss_2sm(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
+          }
+          umma_commit_2sm(&empty_bar[stage], 3);  // frees this slot in both CTAs
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tfull_bar[acc], 3);  // accumulator halves complete in both CTAs
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (both CTAs): own 128 rows of the 256-row tile =====================
+    const int quad = warp & 3;
+    uint8_t* my_slabs = staging + (warp - 2) * 2 * kSlabBytes;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t slab_sel = 0;
+    for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+      int m_tile, n_tile;
+      tile_coords(p, tile, m_tile, n_tile);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row0 = m_tile * 256 + static_cast<int>(cta_rank) * kBM + quad * 32;
+      const int row = row0 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride;
+      long long u = 0;
+      if constexpr (EPI == FX_EPI_RESID_F32) {
+        if (p.row_idx != nullptr && row < p.M) u = p.row_idx[row];
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_wait_ld();
+        const int col0 = n_tile * BN + c * 32;
+        if constexpr (EPI == FX_EPI_RESID_F32) {
+          uint8_t* slab = my_slabs + (slab_sel & 1) * kSlabBytes;
+          if (lane == 0) tma_wait_group_read<1>();
+          __syncwarp();
+          resid_stage_row32(p, row < p.M, u, col0, v, slab, lane);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tmap_out, slab, col0, row0);
+            tma_commit_group();
+          }
+          ++slab_sel;
+        } else {
+          if (row < p.M) epilogue_row32<EPI>(p, row, col0, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if constexpr (EPI == FX_EPI_RESID_F32) {
+      if (lane == 0) tma_wait_group<0>();
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still signal it or read its smem
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
+template <int EPI>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
+                        cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<EPI>;
+  static_assert(Cfg::kStages >= 4, "pipeline too shallow");
+  static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
+  static bool configured = false;
+  auto kern = gemm2_bf16_kernel<EPI>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("fx_gemm_bf16(2cta): cudaFuncSetAttribute(%d B smem): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      return FX_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int total = p.num_m_tiles * p.num_n_tiles;
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (total < pairs ? total : pairs);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tout, p);
+  FX_CHECK_LAUNCH("fx_gemm_bf16(2cta)");
+  return FX_OK;
+}
+
+static int dispatch_epi2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
+                         const GemmParams& p, cudaStream_t s) {
+  switch (epi) {
+    case FX_EPI_BF16: return launch_gemm2<FX_EPI_BF16>(ta, tb, tout, p, s);
+    case FX_EPI_GELU_BF16: return launch_gemm2<FX_EPI_GELU_BF16>(ta, tb, tout, p, s);
+    case FX_EPI_F32: return launch_gemm2<FX_EPI_F32>(ta, tb, tout, p, s);
+    case FX_EPI_RESID_F32: return launch_gemm2<FX_EPI_RESID_F32>(ta, tb, tout, p, s);
+  }
+  set_error("fx_gemm_bf16: unknown epilogue %d", epi);
+  return FX_ERR_ARG;
+}
+
 template <int BN, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
                        cudaStream_t stream) {
