@@ -25,6 +25,20 @@ constexpr int kHalfBytes = 128 * 64 * 2;       // one [128 rows][64 d] swizzled 
 constexpr int kTileBytes = 2 * kHalfBytes;     // [128 rows][128 d]
 constexpr int kFmhaSmem = 2 * kTileBytes /*Q*/ + 2 * kTileBytes /*K ring*/ + 2 * kTileBytes /*V ring*/ + 256 + 1024;
 constexpr float kRescaleThreshold = 8.0f;      // log2 units
+constexpr int kDefaultPoly8 = 3;               // 3 of 8 exponential pairs on the FMA pipe
+
+// Developer tracing (tests/native/fmha_trace.cu builds this file with -DFX_FMHA_TRACE): CTA (0,0,0) records
+// clock64() at pipeline events of its first 64 KV steps. Compiled out of the library.
+#ifdef FX_FMHA_TRACE
+__device__ long long fx_fmha_trace[16 * 64];
+#define FX_TRACE(who, j)                                                                     \
+  do {                                                                                       \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64 && lane == 0)      \
+      fx_fmha_trace[(who) * 64 + (j)] = clock64();                                           \
+  } while (0)
+#else
+#define FX_TRACE(who, j)
+#endif
 
 struct FmhaParams {
   __nv_bfloat16* o;
@@ -75,8 +89,54 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   return r;
 }
 
-// kPolyPairs: of every 4 (x0,x1) pairs of a score row, how many take the FMA-pipe exp2 instead of MUFU.EX2
-template <int kPolyPairs>
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// keys at or beyond `valid_in_chunk` (relative to this 32-column chunk) do not exist: score = -inf
+__device__ __forceinline__ void mask_chunk(uint32_t* s, int valid_in_chunk) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i >= valid_in_chunk) s[i] = 0xff800000u;
+}
+
+// running maximum over one 32-column chunk, two independent 3-input chains
+__device__ __forceinline__ void max_chunk(const uint32_t* s, float& mxa, float& mxb) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    mxa = fmax3(mxa, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+    mxb = fmax3(mxb, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+  }
+}
+
+// P = exp2(S * scale_log2 - m) for one 32-column chunk on packed fp32 pairs, written to TMEM as 16 bf16x2 columns.
+// MUFU.EX2 (16/clk/SM) alone would cost as many cycles per tile as the tile's MMAs, so kPoly8 of every 8 pairs are
+// evaluated on the FMA pipe instead (round-to-nearest range reduction + degree-3 polynomial, rel. error 7.5e-5,
+// far below the bf16 rounding of P).
+template <int kPoly8>
+__device__ __forceinline__ void exp_chunk(const uint32_t* s, float2 sc2, float2 nm2, float2& sum_a, float2& sum_b,
+                                          uint32_t tmem_dst) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 x = fma2(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sc2, nm2);
+    float2 e;
+    if ((i & 7) < kPoly8) {
+      e = exp2_poly2(x);
+    } else {
+      e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+    }
+    if (i & 1) sum_b = add2(sum_b, e); else sum_a = add2(sum_a, e);
+    pk[i] = pack_bf16x2(e.x, e.y);
+  }
+  tmem_st16(tmem_dst, pk);
+}
+
+// kPoly8: of every 8 (x0,x1) pairs of a score row, how many take the FMA-pipe exp2 instead of MUFU.EX2
+template <int kPoly8>
 __global__ void __launch_bounds__(kFmhaThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const FmhaParams p) {
@@ -93,8 +153,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* v_empty = bars + 7;     // 2
   uint64_t* s_full = bars + 9;      // 2 (per query tile)
   uint64_t* p_full = bars + 11;     // 2 (per query tile)
-  uint64_t* o_done = bars + 13;     // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* o_done = bars + 13;     // 2 (per query tile)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,8 +177,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 128);
+      mbar_init(&o_done[i], 1);
     }
-    mbar_init(o_done, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -131,30 +191,41 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   // warpgroups (the pool is what the launch allocated, 3 warps x 168 per sub-partition: 2 x 208 + 88 <= 504).
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-  if (warp == 8) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * kTileBytes);
-      for (int t = 0; t < 2; ++t)
-        for (int hf = 0; hf < 2; ++hf)
-          tma_load_4d(sQ + t * kTileBytes + hf * kHalfBytes, &tmap_q, q_full, hf * 64, head, q0 + t * 128, batch);
+    if (warp == 8) {
+      // ===================== TMA producer (whole warp polls, one elected lane issues) =====================
+      const bool leader = elect_one_sync();
+      if (leader) {
+        mbar_expect_tx(q_full, 2 * kTileBytes);
+        for (int t = 0; t < 2; ++t)
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_4d(sQ + t * kTileBytes + hf * kHalfBytes, &tmap_q, q_full, hf * 64, head, q0 + t * 128, batch);
+      }
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&k_empty[s], ph ^ 1);
-        mbar_expect_tx(&k_full[s], kTileBytes);
-        for (int hf = 0; hf < 2; ++hf)
-          tma_load_4d(sK + s * kTileBytes + hf * kHalfBytes, &tmap_k, &k_full[s], hf * 64, head, j * 128, batch);
+        if (leader) {
+          mbar_expect_tx(&k_full[s], kTileBytes);
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_4d(sK + s * kTileBytes + hf * kHalfBytes, &tmap_k, &k_full[s], hf * 64, head, j * 128, batch);
+        }
         mbar_wait(&v_empty[s], ph ^ 1);
-        mbar_expect_tx(&v_full[s], kTileBytes);
-        for (int hf = 0; hf < 2; ++hf)
-          tma_load_4d(sV + s * kTileBytes + hf * kHalfBytes, &tmap_v, &v_full[s], hf * 64, head, j * 128, batch);
+        if (leader) {
+          mbar_expect_tx(&v_full[s], kTileBytes);
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_4d(sV + s * kTileBytes + hf * kHalfBytes, &tmap_v, &v_full[s], hf * 64, head, j * 128, batch);
+        }
       }
-    }
-    __syncwarp();
-  } else if (warp == 9) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+      __syncwarp();
+    } else if (warp == 9) {
+      // ===================== MMA issuer (whole warp polls, one elected lane issues) =====================
+      // The issue path is synchronous: the thread gets about one UMMA ahead of the tensor pipe, so whatever stands
+      // between two instruction groups is pipe idle time (tests/native/umma_rate.cu: a barrier probe between groups
+      // costs 120-190 idle cycles). Hence: elect.sync (straight-line UTCHMMA, no per-instruction elect loop), a
+      // one-probe fast path in mbar_wait, and strict alternation between the two query tiles, which keeps their
+      // softmax phases staggered (two independent issuers lock into the same phase and serialise softmax
+      // against MMA).
+      const bool leader = elect_one_sync();
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, false, true);  // B = V is MN-major
       const uint32_t q_addr = smem_u32(sQ);
@@ -162,6 +233,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const uint32_t v_addr = smem_u32(sV);
 
       auto issue_qk = [&](int w, int kstage) {
+#if defined(FX_FMHA_EXPERIMENT) && FX_FMHA_EXPERIMENT == 3
+        return;
+#endif
         const uint32_t a0 = q_addr + w * kTileBytes;
         const uint32_t b0 = k_addr + kstage * kTileBytes;
 #pragma unroll
@@ -172,6 +246,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       };
       auto issue_pv = [&](int w, int vstage, bool accumulate) {
+#if defined(FX_FMHA_EXPERIMENT) && FX_FMHA_EXPERIMENT == 2
+        return;
+#endif
         const uint32_t b0 = v_addr + vstage * kTileBytes;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -184,40 +261,51 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      issue_qk(0, 0);
-      umma_commit(&s_full[0]);
-      issue_qk(1, 0);
-      umma_commit(&s_full[1]);
-      umma_commit(&k_empty[0]);
-
+      if (leader) {
+        issue_qk(0, 0);
+        umma_commit(&s_full[0]);
+        issue_qk(1, 0);
+        umma_commit(&s_full[1]);
+        umma_commit(&k_empty[0]);
+      }
       for (int j = 0; j < n_kv; ++j) {
         const int vs = j & 1;
         const int ks_next = (j + 1) & 1;
         const bool has_next = (j + 1) < n_kv;
         mbar_wait(&v_full[vs], (j >> 1) & 1);
+        FX_TRACE(0, j);
         mbar_wait(&p_full[0], j & 1);
+        FX_TRACE(1, j);
         tc_fence_after();
-        issue_pv(0, vs, j > 0);
+        if (leader) issue_pv(0, vs, j > 0);
         if (has_next) {
           mbar_wait(&k_full[ks_next], ((j + 1) >> 1) & 1);
-          tc_fence_after();
-          issue_qk(0, ks_next);
-          umma_commit(&s_full[0]);
+          if (leader) {
+            issue_qk(0, ks_next);
+            umma_commit(&s_full[0]);
+          }
         }
+        FX_TRACE(2, j);
         mbar_wait(&p_full[1], j & 1);
+        FX_TRACE(3, j);
         tc_fence_after();
-        issue_pv(1, vs, j > 0);
-        umma_commit(&v_empty[vs]);
-        if (has_next) {
-          issue_qk(1, ks_next);
-          umma_commit(&s_full[1]);
-          umma_commit(&k_empty[ks_next]);
+        if (leader) {
+          issue_pv(1, vs, j > 0);
+          umma_commit(&v_empty[vs]);
+          if (has_next) {
+            issue_qk(1, ks_next);
+            umma_commit(&s_full[1]);
+            umma_commit(&k_empty[ks_next]);
+          }
         }
+        FX_TRACE(4, j);
       }
-      umma_commit(o_done);
+      if (leader) {
+        umma_commit(&o_done[0]);
+        umma_commit(&o_done[1]);
+      }
+      __syncwarp();
     }
-    __syncwarp();
-  }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // ===================== softmax / correction / output: one thread per query row =====================
@@ -230,34 +318,57 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
     float m_used = 0.f;  // reference maximum (log2 domain) that the stored P / O / l are relative to
     float l = 0.f;
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+    uint32_t s[128];
     for (int j = 0; j < n_kv; ++j) {
+      if (quad == 0 && w == 0) FX_TRACE(6, j);
       mbar_wait(&s_full[w], j & 1);
+      if (quad == 0 && w == 0) FX_TRACE(7, j);
       tc_fence_after();
-      uint32_t s[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
-      tmem_wait_ld();
-
       const int valid = p.Lk - j * 128;  // keys of this tile that exist
-      if (valid < 128) {
-#pragma unroll
-        for (int c = 0; c < 128; ++c)
-          if (c >= valid) s[c] = 0xff800000u;  // -inf
+      float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+#ifdef FX_FMHA_EXPERIMENT
+      if (p.Lk > 0) {  // MMA-only experiments: the softmax groups just hand the tile back
+        l = 1.f;
+        tc_fence_before();
+        mbar_arrive(&p_full[w]);
+        continue;
       }
-      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
-      float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
-#pragma unroll
-      for (int c = 4; c < 128; c += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(s[c]));
-        mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+#endif
 
       if (j == 0) {
-        m_used = mx;
+        // first tile: the reference maximum has to exist before any exponential
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+        tmem_wait_ld();
+        float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (valid < 128) mask_chunk(&s[c * 32], valid - c * 32);
+          max_chunk(&s[c * 32], mxa, mxb);
+        }
+        m_used = fmaxf(mxa, mxb) * p.scale_log2;
+        const float2 nm2 = make_float2(-m_used, -m_used);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) exp_chunk<kPoly8>(&s[c * 32], sc2, nm2, sum_a, sum_b, s_tmem + c * 16);
       } else {
+        // Speculative pass: exponentials relative to the CURRENT reference maximum start as soon as the first 32
+        // columns are in registers (the tile maximum is tracked on the side), and the TMEM load of chunk c+1 runs
+        // behind the MUFU/FMA work of chunk c. The reference only has to move when the tile maximum exceeds it by
+        // more than 2^8 (lazy rescale) - rare after the first tiles - and then the tile is redone from registers.
+        const float2 nm2 = make_float2(-m_used, -m_used);
+        float mxa = -INFINITY, mxb = -INFINITY;
+        tmem_ld32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_wait_ld();
+          if (c < 3) tmem_ld32(s_tmem + (c + 1) * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[(c + 1) * 32]));
+          if (valid < 128) mask_chunk(&s[c * 32], valid - c * 32);
+          max_chunk(&s[c * 32], mxa, mxb);
+          exp_chunk<kPoly8>(&s[c * 32], sc2, nm2, sum_a, sum_b, s_tmem + c * 16);
+          if (quad == 0 && w == 0) FX_TRACE(10 + c, j);
+        }
+        const float mx = fmaxf(mxa, mxb) * p.scale_log2;
         const bool grow = mx > m_used + kRescaleThreshold;
         if (__any_sync(0xffffffffu, grow)) {
           const float m_new = grow ? mx : m_used;
@@ -265,51 +376,32 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           m_used = m_new;
           l *= f;
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t o[32];
-            tmem_ld32(o_tmem + c * 32, o);
+          for (int c = 0; c < 8; ++c) {
+            uint32_t o[16];
+            tmem_ld16(o_tmem + c * 16, o);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st32(o_tmem + c * 32, o);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st16(o_tmem + c * 16, o);
           }
-          tmem_wait_st();
-        }
-      }
-
-      // P = exp2(S * scale_log2 - m_used) on packed fp32 pairs. The MUFU (16 ex2/clk/SM) would cost as many cycles
-      // as the MMAs of the tile, so kPolyPairs of every 4 pairs are evaluated on the FMA pipe instead
-      // (round-to-nearest range reduction + degree-3 polynomial, rel. error 7.5e-5 << bf16 rounding of P).
-      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
-      const float2 nm2 = make_float2(-m_used, -m_used);
-      float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+          const float2 nm2b = make_float2(-m_used, -m_used);
+          sum_a = make_float2(0.f, 0.f);
+          sum_b = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 x = fma2(make_float2(__uint_as_float(s[c * 32 + 2 * i]), __uint_as_float(s[c * 32 + 2 * i + 1])),
-                                sc2, nm2);
-          float2 e;
-          if ((i & 3) < kPolyPairs) {
-            e = exp2_poly2(x);
-          } else {
-            e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
-          }
-          if (i & 1) sum_b = add2(sum_b, e); else sum_a = add2(sum_a, e);
-          pk[i] = pack_bf16x2(e.x, e.y);
+          for (int c = 0; c < 4; ++c) exp_chunk<kPoly8>(&s[c * 32], sc2, nm2b, sum_a, sum_b, s_tmem + c * 16);
         }
-        tmem_st16(s_tmem + c * 16, pk);
       }
       sum_a = add2(sum_a, sum_b);
       l += sum_a.x + sum_a.y;
+      if (quad == 0 && w == 0) FX_TRACE(8, j);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[w]);
+      if (quad == 0 && w == 0) FX_TRACE(9, j);
     }
 
     // epilogue: O / l -> bf16 -> global
-    mbar_wait(o_done, 0);
+    mbar_wait(&o_done[w], 0);
     tc_fence_after();
     const float inv_l = 1.0f / l;
     __nv_bfloat16* orow = p.o + static_cast<long long>(batch) * p.o_stride_b +
@@ -374,16 +466,17 @@ extern "C" int fx_fmha_fwd(const void* q, int64_t q_stride_b, int64_t q_stride_l
   if (!make_qkv_tmap(&tk, k, bs(k_stride_b, k_stride_l, Lk), k_stride_l, B, H, Lk)) return FX_ERR_CUDA;
   if (!make_qkv_tmap(&tv, v, bs(v_stride_b, v_stride_l, Lk), v_stride_l, B, H, Lk)) return FX_ERR_CUDA;
 
-  // exp2 split between MUFU and the FMA pipe: measured fastest with all-MUFU (0); FX_FMHA_POLY=0..3 overrides it
+  // exp2 split between MUFU and the FMA pipe, in eighths of the pairs; FX_FMHA_POLY=0|2|3|4 overrides the default
   static int poly = -1;
   if (poly < 0) {
     const char* env = getenv("FX_FMHA_POLY");
-    poly = (env && env[0] >= '0' && env[0] <= '3') ? env[0] - '0' : 0;
+    poly = kDefaultPoly8;
+    if (env && (env[0] == '0' || env[0] == '2' || env[0] == '3' || env[0] == '4')) poly = env[0] - '0';
   }
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const FmhaParams);
-  const Kern kerns[4] = {fmha_fwd_kernel<0>, fmha_fwd_kernel<1>, fmha_fwd_kernel<2>, fmha_fwd_kernel<3>};
+  const Kern kerns[5] = {fmha_fwd_kernel<0>, nullptr, fmha_fwd_kernel<2>, fmha_fwd_kernel<3>, fmha_fwd_kernel<4>};
   const Kern kern = kerns[poly];
-  static bool configured[4] = {false, false, false, false};
+  static bool configured[5] = {false, false, false, false, false};
   if (!configured[poly]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmhaSmem);
     if (e != cudaSuccess) {

@@ -9,6 +9,8 @@
 //
 // Replaces the nn.Linear / conv-as-GEMM call sites of FlexAM/models/wan_transformer3d_FlexAM.py
 // (:242-261, :363-370, :414-416, :456, :461, :468, :506, :624-625, :675-678, :959-964).
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -187,43 +189,45 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int m_tile, n_tile;
-        tile_coords(p, tile, m_tile, n_tile);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===================== TMA producer (whole warp polls, one elected lane issues) =====================
+    const bool leader = elect_one_sync();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int m_tile, n_tile;
+      tile_coords(p, tile, m_tile, n_tile);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m_tile * kBM);
           tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBK, n_tile * BN);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, false, false);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    // ===================== MMA issuer (whole warp polls, one elected lane issues) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, false, false);
+    const bool leader = elect_one_sync();
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kAccStride;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kAccStride;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+        if (leader) {
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
@@ -233,15 +237,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             umma_ss(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (leader) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
     __syncwarp();
   } else {
@@ -377,34 +381,36 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
-        int m_tile, n_tile;
-        tile_coords(p, tile, m_tile, n_tile);
-        const int a_row = m_tile * 256 + static_cast<int>(cta_rank) * kBM;
-        const int b_row = n_tile * BN + static_cast<int>(cta_rank) * (BN / 2);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    const bool elected = elect_one_sync();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+      int m_tile, n_tile;
+      tile_coords(p, tile, m_tile, n_tile);
+      const int a_row = m_tile * 256 + static_cast<int>(cta_rank) * kBM;
+      const int b_row = n_tile * BN + static_cast<int>(cta_rank) * (BN / 2);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elected) {
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
           const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
           tma_load_2d_2sm(sa, &tmap_a, leader_full, kb * kBK, a_row);
           tma_load_2d_2sm(sb, &tmap_b, leader_full, kb * kBK, b_row);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA, one thread) =====================
-    if (leader && lane == 0) {
+    // ===================== MMA issuer (leader CTA, one elected lane) =====================
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN, false, false);
+      const bool elected = elect_one_sync();
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -416,21 +422,23 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t b_addr = a_addr + Cfg::kABytes;
+          if (elected) {
+            const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k) {
-            const uint64_t a_desc = umma_desc_sw128(a_addr + k * kUmmaK * 2, 16, 1024);
-            const uint64_t b_desc = umma_desc_sw128(b_addr + k * kUmmaK * 2, 16, 1024);
-            umma_ss_2sm(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              const uint64_t a_desc = umma_desc_sw128(a_addr + k * kUmmaK * 2, 16, 1024);
+              const uint64_t b_desc = umma_desc_sw128(b_addr + k * kUmmaK * 2, 16, 1024);
+              umma_ss_2sm(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
+            }
+            umma_commit_2sm(&empty_bar[stage], 3);  // frees this slot in both CTAs
           }
-          umma_commit_2sm(&empty_bar[stage], 3);  // frees this slot in both CTAs
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&tfull_bar[acc], 3);  // accumulator halves complete in both CTAs
+        if (elected) umma_commit_2sm(&tfull_bar[acc], 3);  // accumulator halves complete in both CTAs
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -533,6 +541,16 @@ static int dispatch_epi2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, 
   return FX_ERR_ARG;
 }
 
+// CTA-pair kernel: only for full-width panels; FX_GEMM_MODE=pair|single overrides the default (pair)
+static bool use_pair_kernel(int M, int N, int bn) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* env = getenv("FX_GEMM_MODE");
+    mode = (env && env[0] == 's') ? 0 : 1;
+  }
+  return mode == 1 && bn == 256 && N % 256 == 0 && M >= 256;
+}
+
 template <int BN, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
                        cudaStream_t stream) {
@@ -619,6 +637,13 @@ extern "C" int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t l
     const uint32_t box[2] = {kBK, static_cast<uint32_t>(bn)};
     if (!make_tmap_bf16(&tb, w, 2, dims, strides, box)) return FX_ERR_CUDA;
   }
+  CUtensorMap tb128 = tb;
+  if (use_pair_kernel(M, N, bn)) {  // each CTA of a pair stages a 128-row half of the 256-wide B panel
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    const uint32_t box[2] = {kBK, 128};
+    if (!make_tmap_bf16(&tb128, w, 2, dims, strides, box)) return FX_ERR_CUDA;
+  }
   if (epilogue == FX_EPI_RESID_F32) {  // fp32 [M, N] view of the residual stream, 32 x 32 boxes for the reduction
     const uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ldo) * 4};
@@ -628,6 +653,11 @@ extern "C" int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t l
     tout = ta;  // unused by the other epilogues
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (use_pair_kernel(M, N, bn)) {
+    p.num_m_tiles = (M + 255) / 256;
+    p.group_m = 8;
+    return dispatch_epi2(epilogue, ta, tb128, tout, p, s);
+  }
   switch (bn) {
     case 256: return dispatch_epi<256>(epilogue, ta, tb, tout, p, s);
     case 192: return dispatch_epi<192>(epilogue, ta, tb, tout, p, s);

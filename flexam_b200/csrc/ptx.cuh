@@ -44,9 +44,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin on the phase parity. A pipeline bug would otherwise hang the GPU until an external timeout; the watchdog
-// turns ~2 s without progress into a trap (reported as a launch failure at the caller's next synchronisation).
+// Spin on the phase parity. The first probe is the fast path (a completed phase costs one try_wait, ~40 cycles; the
+// single-thread MMA issuers sit on this path between instruction groups). A pipeline bug would otherwise hang the GPU
+// until an external timeout; the watchdog in the slow path turns ~2 s without progress into a trap (reported as a
+// launch failure at the caller's next synchronisation).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
 #ifndef FX_NO_WATCHDOG
   uint32_t polls = 0;
   long long t0 = 0;
@@ -61,6 +64,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 #endif
+}
+
+// One lane of the (converged) warp, chosen by the hardware. Unlike `lane == 0`, ptxas knows that code predicated on
+// the result runs in exactly one thread, so tcgen05.mma / TMA issue compiles to straight-line uniform-datapath
+// instructions instead of a per-instruction elect-and-retry loop.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFF));
+  return pred != 0;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -142,6 +160,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }

@@ -1,0 +1,73 @@
+// Developer tool (GPU box): pipeline timeline of the attention kernel. Builds flexam_b200/csrc/fmha.cu with
+// -DFX_FMHA_TRACE (see tests/native/Makefile), runs one self-attention launch at the config-2 shape and prints, for
+// CTA (0,0,0), the clock64() stamps of the MMA issuer and of one softmax warp per query tile for KV steps 8..23,
+// relative to the first stamp. Not part of the library or of the test suite.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "../../include/flexam_b200.h"
+
+#ifdef FX_FMHA_TRACE
+namespace fx {
+extern __device__ long long fx_fmha_trace[16 * 64];
+}
+#endif
+
+int main(int argc, char** argv) {
+  const int B = 2, H = 24, L = argc > 1 ? atoi(argv[1]) : 11648;
+  const size_t n = static_cast<size_t>(B) * L * 3 * H * 128;
+  std::vector<__nv_bfloat16> h(n);
+  unsigned s = 12345u;
+  for (size_t i = 0; i < n; ++i) {
+    s = s * 1664525u + 1013904223u;
+    h[i] = __float2bfloat16(((s >> 8) & 0xffff) / 65536.0f * 2.f - 1.f);
+  }
+  __nv_bfloat16 *qkv, *o;
+  cudaMalloc(&qkv, n * 2);
+  cudaMalloc(&o, n / 3 * 2);
+  cudaMemcpy(qkv, h.data(), n * 2, cudaMemcpyHostToDevice);
+  const long long sl = 3LL * H * 128, sb = sl * L;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int it = 0; it < 3; ++it) {
+    cudaEventRecord(e0);
+    int st = fx_fmha_fwd(qkv, sb, sl, qkv + H * 128, sb, sl, qkv + 2 * H * 128, sb, sl, o, (long long)H * 128 * L,
+                         H * 128, B, H, L, L, 0.0883883f, nullptr);
+    cudaEventRecord(e1);
+    if (st != 0) {
+      printf("fx_fmha_fwd failed: %s\n", fx_last_error());
+      return 1;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("kernel failed: %s\n", cudaGetErrorString(e));
+      return 1;
+    }
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    printf("launch %d: %.3f ms, %.1f TFLOP/s\n", it, ms, 4.0 * B * H * L * (double)L * 128 / ms / 1e9);
+  }
+#ifdef FX_FMHA_TRACE
+  long long t[16 * 64];
+  cudaMemcpyFromSymbol(t, fx::fx_fmha_trace, sizeof(t));
+  const char* names[14] = {"mma:v_full", "mma:p0_seen", "mma:pv0+qk0_issued", "mma:p1_seen", "mma:iter_issued", "-",
+                           "sm0:wait_s", "sm0:s_seen", "sm0:exp_done", "sm0:arrived",
+                           "sm0:chunk0", "sm0:chunk1", "sm0:chunk2", "sm0:chunk3"};
+  const long long t0 = t[0 * 64 + 8];
+  printf("%-20s", "event \\ kv step");
+  for (int j = 8; j < 24; ++j) printf("%7d", j);
+  printf("\n");
+  for (int w = 0; w < 14; ++w) {
+    printf("%-20s", names[w]);
+    for (int j = 8; j < 24; ++j) printf("%7lld", t[w * 64 + j] - t0);
+    printf("\n");
+  }
+  printf("period (mma:p0_seen[j+1]-[j]) over steps 8..40: %.0f clk\n", (t[64 + 40] - t[64 + 8]) / 32.0);
+#endif
+  return 0;
+}
