@@ -1,15 +1,19 @@
 // Non-causal flash-attention forward for sm_100a, head_dim 128, bf16 in/out, fp32 softmax statistics.
 //
 // One CTA owns 256 query rows (two 128-row tiles) of one (batch, head) and streams 128-key K/V tiles:
-//   warp 8      TMA producer   Q once, then K_j / V_j into 2-stage rings (SWIZZLE_128B boxes of [128 rows][64 d])
-//   warp 9      MMA issuer     S_w = Q_w K_j^T (SS, both K-major) and O_w += P_w V_j (A = P from TMEM, B = V MN-major)
-//   warps 0-3   softmax for query tile 0: one thread per row, S read from TMEM, P written back over S as bf16
-//   warps 4-7   softmax for query tile 1
-// TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_w aliases the first 64 columns of S_w.
-// While one softmax group works on S_w(j), the tensor core runs the other tile's QK^T / PV, so K/V smem traffic is
-// shared by both tiles and the MMA pipe stays busy. The running maximum is only raised when it grows by more than
-// 2^8 (lazy rescale): the O accumulator is then rescaled in TMEM by the softmax group itself, which is safe because
-// s_full[w] (committed after QK_w(j)) also implies PV_w(j-1) has retired and PV_w(j) is not issued before p_full[w].
+//   warps 0-15  softmax        four warpgroups: (query tile w, column half h) = warp >> 2 -> (w = wg >> 1, h = wg & 1).
+//                              A thread owns one row of S_w and 64 of its 128 keys; the two threads of a row agree on
+//                              the running maximum through shared memory + a 256-thread named barrier per tile. Four
+//                              softmax warps per scheduler (instead of two) is what hides the MUFU/TMEM latencies.
+//   warp 16     TMA producer   Q once, then K_j / V_j into 2-stage rings (SWIZZLE_128B boxes of [128 rows][64 d])
+//   warp 17     MMA issuer     S_w = Q_w K_j^T (SS, both K-major) and O_w += P_w V_j (A = P from TMEM, B = V MN-major)
+// TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_w (bf16 pairs) overwrites S_w in place:
+// keys 0-63 in columns [0,32) and keys 64-127 in columns [64,96) of S_w, i.e. every thread only overwrites scores it
+// has already loaded itself. While one tile's softmax runs, the tensor core works on the other tile's QK^T / PV, so
+// K/V smem traffic is shared by both tiles and the MMA pipe stays busy. The running maximum is only raised when it
+// grows by more than 2^8 (lazy rescale): the O accumulator is then rescaled in TMEM by the softmax threads themselves,
+// which is safe because s_full[w] (committed after QK_w(j)) also implies PV_w(j-1) has retired and PV_w(j) is not
+// issued before p_full[w].
 //
 // Replaces attention()/flash_attention() (FlexAM/models/attention_utils.py:174-233) at its two call sites,
 // wan_transformer3d_FlexAM.py:251-256 (self, Lk = all tokens) and :367 (cross, Lk = 512, unmasked).
@@ -17,15 +21,18 @@
 
 #include "host_common.h"
 #include "ptx.cuh"
+#include "softmax_math.cuh"
 
 namespace fx {
 
-constexpr int kFmhaThreads = 384;  // 3 warpgroups: softmax tile 0, softmax tile 1, {TMA, MMA, 2 idle warps}
+constexpr int kFmhaThreads = 640;  // 5 warpgroups: 4 softmax (tile x column half), {TMA, MMA, 2 idle warps}
 constexpr int kHalfBytes = 128 * 64 * 2;       // one [128 rows][64 d] swizzled sub-tile
 constexpr int kTileBytes = 2 * kHalfBytes;     // [128 rows][128 d]
-constexpr int kFmhaSmem = 2 * kTileBytes /*Q*/ + 2 * kTileBytes /*K ring*/ + 2 * kTileBytes /*V ring*/ + 256 + 1024;
+constexpr int kXchBytes = 2 * 2 * 2 * 128 * 4;  // [slot][tile][half][row] fp32: row maxima / row sums between halves
+constexpr int kFmhaSmem =
+    2 * kTileBytes /*Q*/ + 2 * kTileBytes /*K ring*/ + 2 * kTileBytes /*V ring*/ + kXchBytes + 256 + 1024;
 constexpr float kRescaleThreshold = 8.0f;      // log2 units
-constexpr int kDefaultPoly8 = 3;               // 3 of 8 exponential pairs on the FMA pipe
+constexpr int kDefaultPoly8 = 2;               // 2 of 8 exponential pairs on the FMA pipe (measured best: 0 2 3 4)
 
 // Developer tracing (tests/native/fmha_trace.cu builds this file with -DFX_FMHA_TRACE): CTA (0,0,0) records
 // clock64() at pipeline events of its first 64 KV steps. Compiled out of the library.
@@ -48,93 +55,6 @@ struct FmhaParams {
 };
 
 
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// Packed fp32x2 arithmetic (sm_100): one issue slot for two lanes of work.
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;"
-      : "=l"(reinterpret_cast<unsigned long long&>(d))
-      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)),
-        "l"(reinterpret_cast<const unsigned long long&>(c)));
-  return d;
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-  float2 d;
-  asm("add.rn.f32x2 %0, %1, %2;"
-      : "=l"(reinterpret_cast<unsigned long long&>(d))
-      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
-  return d;
-}
-
-// 2^x for a pair, x <= ~8: n = round(x) via the 1.5*2^23 magic constant (n lands in the low mantissa bits of t),
-// f = x - n in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial, exponent patched in with an integer add.
-__device__ __forceinline__ float2 exp2_poly2(float2 x) {
-  const float kMagic = 12582912.f;
-  x.x = fmaxf(x.x, -126.f);
-  x.y = fmaxf(x.y, -126.f);
-  const float2 t = add2(x, make_float2(kMagic, kMagic));
-  const float2 n = add2(t, make_float2(-kMagic, -kMagic));
-  const float2 f = fma2(n, make_float2(-1.f, -1.f), x);
-  float2 q = fma2(f, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111251f, 0.2426111251f));
-  q = fma2(q, f, make_float2(0.6932609677f, 0.6932609677f));
-  q = fma2(q, f, make_float2(0.9999280572f, 0.9999280572f));
-  float2 r;
-  r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
-  r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
-  return r;
-}
-
-
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-
-// keys at or beyond `valid_in_chunk` (relative to this 32-column chunk) do not exist: score = -inf
-__device__ __forceinline__ void mask_chunk(uint32_t* s, int valid_in_chunk) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i)
-    if (i >= valid_in_chunk) s[i] = 0xff800000u;
-}
-
-// running maximum over one 32-column chunk, two independent 3-input chains
-__device__ __forceinline__ void max_chunk(const uint32_t* s, float& mxa, float& mxb) {
-#pragma unroll
-  for (int i = 0; i < 32; i += 4) {
-    mxa = fmax3(mxa, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-    mxb = fmax3(mxb, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-  }
-}
-
-// P = exp2(S * scale_log2 - m) for one 32-column chunk on packed fp32 pairs, written to TMEM as 16 bf16x2 columns.
-// MUFU.EX2 (16/clk/SM) alone would cost as many cycles per tile as the tile's MMAs, so kPoly8 of every 8 pairs are
-// evaluated on the FMA pipe instead (round-to-nearest range reduction + degree-3 polynomial, rel. error 7.5e-5,
-// far below the bf16 rounding of P).
-template <int kPoly8>
-__device__ __forceinline__ void exp_chunk(const uint32_t* s, float2 sc2, float2 nm2, float2& sum_a, float2& sum_b,
-                                          uint32_t tmem_dst) {
-  uint32_t pk[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float2 x = fma2(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sc2, nm2);
-    float2 e;
-    if ((i & 7) < kPoly8) {
-      e = exp2_poly2(x);
-    } else {
-      e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
-    }
-    if (i & 1) sum_b = add2(sum_b, e); else sum_a = add2(sum_a, e);
-    pk[i] = pack_bf16x2(e.x, e.y);
-  }
-  tmem_st16(tmem_dst, pk);
-}
-
 // kPoly8: of every 8 (x0,x1) pairs of a score row, how many take the FMA-pipe exp2 instead of MUFU.EX2
 template <int kPoly8>
 __global__ void __launch_bounds__(kFmhaThreads, 1)
@@ -145,7 +65,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* sQ = smem;                    // [2 tiles][2 halves][128][64]
   uint8_t* sK = sQ + 2 * kTileBytes;     // [2 stages][2 halves][128][64]
   uint8_t* sV = sK + 2 * kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * kTileBytes);
+  float* xch = reinterpret_cast<float*>(sV + 2 * kTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * kTileBytes + kXchBytes);
   uint64_t* q_full = bars;          // 1
   uint64_t* k_full = bars + 1;      // 2
   uint64_t* k_empty = bars + 3;     // 2
@@ -163,12 +84,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int batch = blockIdx.z;
   const int n_kv = (p.Lk + 127) / 128;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
   }
-  if (warp == 9 && lane == 0) {
+  if (warp == 17 && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
@@ -176,7 +97,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 256);
       mbar_init(&o_done[i], 1);
     }
     fence_mbar_init();
@@ -187,11 +108,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // Register re-partitioning: the data-movement warpgroup (warps 8-11) gives its registers to the two softmax
-  // warpgroups (the pool is what the launch allocated, 3 warps x 168 per sub-partition: 2 x 208 + 88 <= 504).
-  if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-    if (warp == 8) {
+  // Register re-partitioning: the data-movement warpgroup (warps 16-19) gives its registers to the four softmax
+  // warpgroups (the pool is what the launch allocated, 640 x 96: 512 x 104 + 128 x 56 <= 61440).
+  if (warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 16) {
       // ===================== TMA producer (whole warp polls, one elected lane issues) =====================
       const bool leader = elect_one_sync();
       if (leader) {
@@ -217,7 +138,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       }
       __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == 17) {
       // ===================== MMA issuer (whole warp polls, one elected lane issues) =====================
       // The issue path is synchronous: the thread gets about one UMMA ahead of the tensor pipe, so whatever stands
       // between two instruction groups is pipe idle time (tests/native/umma_rate.cu: a barrier probe between groups
@@ -233,7 +154,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const uint32_t v_addr = smem_u32(sV);
 
       auto issue_qk = [&](int w, int kstage) {
-#if defined(FX_FMHA_EXPERIMENT) && FX_FMHA_EXPERIMENT == 3
+#if defined(FX_FMHA_EXPERIMENT) && FX_FMHA_EXPERIMENT >= 3
         return;
 #endif
         const uint32_t a0 = q_addr + w * kTileBytes;
@@ -246,14 +167,15 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       };
       auto issue_pv = [&](int w, int vstage, bool accumulate) {
-#if defined(FX_FMHA_EXPERIMENT) && FX_FMHA_EXPERIMENT == 2
+#if defined(FX_FMHA_EXPERIMENT) && (FX_FMHA_EXPERIMENT == 2 || FX_FMHA_EXPERIMENT == 4)
         return;
 #endif
         const uint32_t b0 = v_addr + vstage * kTileBytes;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // A: 16 keys = 8 packed columns of P_w; B: 16 key rows (2048 B) further down the MN-major V tile
-          umma_ts(tmem_base + 256 + w * 128, tmem_base + w * 128 + k * 8,
+          // (keys 0-63 -> P columns [0,32), keys 64-127 -> [64,96) of S_w)
+          umma_ts(tmem_base + 256 + w * 128, tmem_base + w * 128 + (k >> 2) * 64 + (k & 3) * 8,
                   umma_desc_sw128(b0 + k * 2048, kHalfBytes, 1024), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
         }
       };
@@ -307,27 +229,29 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       __syncwarp();
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-    // ===================== softmax / correction / output: one thread per query row =====================
-    const int w = warp >> 2;         // query tile
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // ===================== softmax / correction / output: one thread per (query row, 64-key half) =====================
+    const int wg = warp >> 2;
+    const int w = wg >> 1;           // query tile
+    const int h = wg & 1;            // which 64 of the tile's 128 keys (and which 64 of the 128 output columns)
     const int quad = warp & 3;       // TMEM lane quadrant
+    const int r = quad * 32 + lane;  // row inside the tile
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t s_tmem = tmem_base + lane_off + w * 128;
-    const uint32_t o_tmem = tmem_base + lane_off + 256 + w * 128;
-    const int row = q0 + w * 128 + quad * 32 + lane;
+    const uint32_t s_tmem = tmem_base + lane_off + w * 128 + h * 64;  // my scores; P goes to its first 32 columns
+    const uint32_t o_tmem = tmem_base + lane_off + 256 + w * 128 + h * 64;
+    const int row = q0 + w * 128 + r;
+    const uint32_t pair_bar = 1 + w;  // named barrier of the tile's two warpgroups
 
     float m_used = 0.f;  // reference maximum (log2 domain) that the stored P / O / l are relative to
-    float l = 0.f;
+    float l = 0.f;       // partial row sum over my keys
     const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
-    uint32_t s[128];
     for (int j = 0; j < n_kv; ++j) {
-      if (quad == 0 && w == 0) FX_TRACE(6, j);
+      if (warp == 0) FX_TRACE(6, j);
       mbar_wait(&s_full[w], j & 1);
-      if (quad == 0 && w == 0) FX_TRACE(7, j);
+      if (warp == 0) FX_TRACE(7, j);
       tc_fence_after();
-      const int valid = p.Lk - j * 128;  // keys of this tile that exist
       float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
-#ifdef FX_FMHA_EXPERIMENT
+#if defined(FX_FMHA_EXPERIMENT) && FX_FMHA_EXPERIMENT < 4
       if (p.Lk > 0) {  // MMA-only experiments: the softmax groups just hand the tile back
         l = 1.f;
         tc_fence_before();
@@ -335,48 +259,40 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         continue;
       }
 #endif
+      uint32_t s[64];
+      tmem_ld32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      tmem_ld32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      tmem_wait_ld();
+      if (warp == 0) FX_TRACE(11, j);
+      const int valid = p.Lk - j * 128 - h * 64;  // keys of my half that exist
+      if (valid < 64) {
+        mask_chunk(&s[0], valid);
+        mask_chunk(&s[32], valid - 32);
+      }
+      float mxa = -INFINITY, mxb = -INFINITY;
+      max_chunk(&s[0], mxa, mxb);
+      max_chunk(&s[32], mxa, mxb);
+      // row maximum over both halves: exchange through shared memory (slots alternate so that a fast warp cannot
+      // overwrite a value its partner has not read yet)
+      float* slot = xch + ((j & 1) * 2 + w) * 256;
+      const float mloc = fmaxf(mxa, mxb);
+      if (warp == 0) FX_TRACE(12, j);
+      slot[h * 128 + r] = mloc;
+      asm volatile("bar.sync %0, 256;" ::"r"(pair_bar) : "memory");
+      const float mx = fmaxf(mloc, slot[(h ^ 1) * 128 + r]) * p.scale_log2;
+      if (warp == 0) FX_TRACE(10, j);
 
       if (j == 0) {
-        // first tile: the reference maximum has to exist before any exponential
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
-        tmem_wait_ld();
-        float mxa = -INFINITY, mxb = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (valid < 128) mask_chunk(&s[c * 32], valid - c * 32);
-          max_chunk(&s[c * 32], mxa, mxb);
-        }
-        m_used = fmaxf(mxa, mxb) * p.scale_log2;
-        const float2 nm2 = make_float2(-m_used, -m_used);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) exp_chunk<kPoly8>(&s[c * 32], sc2, nm2, sum_a, sum_b, s_tmem + c * 16);
+        m_used = mx;
       } else {
-        // Speculative pass: exponentials relative to the CURRENT reference maximum start as soon as the first 32
-        // columns are in registers (the tile maximum is tracked on the side), and the TMEM load of chunk c+1 runs
-        // behind the MUFU/FMA work of chunk c. The reference only has to move when the tile maximum exceeds it by
-        // more than 2^8 (lazy rescale) - rare after the first tiles - and then the tile is redone from registers.
-        const float2 nm2 = make_float2(-m_used, -m_used);
-        float mxa = -INFINITY, mxb = -INFINITY;
-        tmem_ld32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tmem_wait_ld();
-          if (c < 3) tmem_ld32(s_tmem + (c + 1) * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[(c + 1) * 32]));
-          if (valid < 128) mask_chunk(&s[c * 32], valid - c * 32);
-          max_chunk(&s[c * 32], mxa, mxb);
-          exp_chunk<kPoly8>(&s[c * 32], sc2, nm2, sum_a, sum_b, s_tmem + c * 16);
-          if (quad == 0 && w == 0) FX_TRACE(10 + c, j);
-        }
-        const float mx = fmaxf(mxa, mxb) * p.scale_log2;
-        const bool grow = mx > m_used + kRescaleThreshold;
+        const bool grow = mx > m_used + kRescaleThreshold;  // same decision in both threads of the row
         if (__any_sync(0xffffffffu, grow)) {
           const float m_new = grow ? mx : m_used;
           const float f = ex2_approx(m_used - m_new);  // 1 for rows that keep their reference
           m_used = m_new;
           l *= f;
 #pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < 4; ++c) {  // my 64 columns of the output accumulator
             uint32_t o[16];
             tmem_ld16(o_tmem + c * 16, o);
             tmem_wait_ld();
@@ -384,30 +300,35 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
             tmem_st16(o_tmem + c * 16, o);
           }
-          const float2 nm2b = make_float2(-m_used, -m_used);
-          sum_a = make_float2(0.f, 0.f);
-          sum_b = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) exp_chunk<kPoly8>(&s[c * 32], sc2, nm2b, sum_a, sum_b, s_tmem + c * 16);
         }
       }
+      const float2 nm2 = make_float2(-m_used, -m_used);
+      exp_chunk<kPoly8>(&s[0], sc2, nm2, sum_a, sum_b, s_tmem);
+      if (warp == 0) FX_TRACE(13, j);
+      exp_chunk<kPoly8>(&s[32], sc2, nm2, sum_a, sum_b, s_tmem + 16);
       sum_a = add2(sum_a, sum_b);
       l += sum_a.x + sum_a.y;
-      if (quad == 0 && w == 0) FX_TRACE(8, j);
+      if (warp == 0) FX_TRACE(8, j);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[w]);
-      if (quad == 0 && w == 0) FX_TRACE(9, j);
+      if (warp == 0) FX_TRACE(9, j);
     }
 
-    // epilogue: O / l -> bf16 -> global
+    // epilogue: total row sum from both halves, then my 64 output columns: O / l -> bf16 -> global
+    {
+      float* slot = xch + ((n_kv & 1) * 2 + w) * 256;
+      slot[h * 128 + r] = l;
+      asm volatile("bar.sync %0, 256;" ::"r"(pair_bar) : "memory");
+      l += slot[(h ^ 1) * 128 + r];
+    }
     mbar_wait(&o_done[w], 0);
     tc_fence_after();
     const float inv_l = 1.0f / l;
     __nv_bfloat16* orow = p.o + static_cast<long long>(batch) * p.o_stride_b +
-                          static_cast<long long>(row) * p.o_stride_l + head * 128;
+                          static_cast<long long>(row) * p.o_stride_l + head * 128 + h * 64;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t o[32];
       tmem_ld32(o_tmem + c * 32, o);
       tmem_wait_ld();

@@ -57,7 +57,7 @@ int main(int argc, char** argv) {
   cudaMemcpyFromSymbol(t, fx::fx_fmha_trace, sizeof(t));
   const char* names[14] = {"mma:v_full", "mma:p0_seen", "mma:pv0+qk0_issued", "mma:p1_seen", "mma:iter_issued", "-",
                            "sm0:wait_s", "sm0:s_seen", "sm0:exp_done", "sm0:arrived",
-                           "sm0:chunk0", "sm0:chunk1", "sm0:chunk2", "sm0:chunk3"};
+                           "sm0:max_exchanged", "sm0:s_loaded", "sm0:max_done", "sm0:exp_half"};
   const long long t0 = t[0 * 64 + 8];
   printf("%-20s", "event \\ kv step");
   for (int j = 8; j < 24; ++j) printf("%7d", j);

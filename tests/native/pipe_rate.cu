@@ -1,0 +1,163 @@
+// Developer tool (GPU box): issue rate of the instructions the attention softmax is made of, per SM sub-partition,
+// with 1, 2 or 4 warps per scheduler. One CTA of 128/256/512 threads on one SM; every thread runs `iters` rounds of
+// 16 independent operations of one kind; clock64() around the loop gives cycles per warp-instruction per scheduler.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "../../flexam_b200/csrc/softmax_math.cuh"
+
+__device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return d;
+}
+__device__ __forceinline__ unsigned pack(float a, float b) {
+  unsigned r; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d; asm volatile("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d;
+}
+
+template <int KIND>
+__global__ void rate_kernel(int iters, float seed, long long* out, float* sink) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = seed + i * 0.01f + threadIdx.x * 1e-4f;
+  unsigned acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (KIND == 0) v[i] = ex2(v[i]);
+      if (KIND == 1) { float2 t = fma2(make_float2(v[i], v[(i + 1) & 15]), make_float2(0.999f, 0.999f), make_float2(1e-3f, 1e-3f)); v[i] = t.x; }
+      if (KIND == 2) acc ^= pack(v[i], v[(i + 5) & 15]) + it;
+      if (KIND == 3) v[i] = fmax3(v[i], v[(i + 3) & 15], seed);
+      if (KIND == 4) v[i] = fmaf(v[i], 0.999f, 1e-3f);
+      if (KIND == 6) {  // ex2.approx.f16x2: two exponentials per MUFU op
+        unsigned u = __float_as_uint(v[i]), r;
+        asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(u));
+        v[i] = __uint_as_float(r);
+      }
+      if (KIND == 7) {  // cvt.rn.f16x2.f32
+        unsigned r;
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v[i]), "f"(v[(i + 5) & 15]));
+        acc ^= r;
+      }
+      if (KIND == 8) {  // add.f16x2
+        unsigned u = __float_as_uint(v[i]), w2 = __float_as_uint(v[(i + 3) & 15]), r;
+        asm volatile("add.f16x2 %0, %1, %2;" : "=r"(r) : "r"(u), "r"(w2));
+        v[i] = __uint_as_float(r);
+      }
+      if (KIND == 9) {  // f16 softmax mix per pair: fma2, cvt.f16x2, ex2.f16x2, add.f16x2
+        float2 t2 = fma2(make_float2(v[i], v[(i + 1) & 15]), make_float2(0.999f, 0.999f), make_float2(-1.f, -1.f));
+        unsigned hx, e;
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hx) : "f"(t2.y), "f"(t2.x));
+        asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(e) : "r"(hx));
+        asm volatile("add.f16x2 %0, %1, %2;" : "=r"(acc) : "r"(acc), "r"(e));
+        v[i] = v[i] * 0.999f + 1e-4f;
+      }
+      if (KIND == 5) {  // the softmax mix per pair: 1 fma2, 2 ex2, 1 add2-like fma2, 1 pack, 1 fmax3
+        float2 t = fma2(make_float2(v[i], v[(i + 1) & 15]), make_float2(0.999f, 0.999f), make_float2(-1.f, -1.f));
+        const float a = ex2(t.x), b = ex2(t.y);
+        float2 u = fma2(make_float2(a, b), make_float2(1.f, 1.f), make_float2(v[(i + 2) & 15], v[(i + 3) & 15]));
+        acc ^= pack(a, b);
+        v[i] = fmax3(u.x, u.y, seed) * 1e-3f;
+      }
+    }
+  }
+  const long long t1 = clock64();
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sum += v[i];
+  if (sum == 123.456f || acc == 0x12345u) sink[0] = sum;
+  if (threadIdx.x == 0) out[0] = t1 - t0;
+}
+
+// The shipped exponential pass (softmax_math.cuh: exp_pack) on 64 register-resident scores per thread per round,
+// i.e. one thread-tile of the attention kernel without its TMEM traffic and without the row maximum.
+template <int kPoly8, bool kWithMax>
+__global__ void exp_pack_kernel(int iters, float seed, long long* out, float* sink) {
+  uint32_t s[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) s[i] = __float_as_uint(seed * (i + 1) - threadIdx.x * 1e-3f);
+  float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+  unsigned acc = 0;
+  float m = 3.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (kWithMax) {
+      float mxa = -INFINITY, mxb = -INFINITY;
+      fx::max_chunk(&s[0], mxa, mxb);
+      fx::max_chunk(&s[32], mxa, mxb);
+      m = fmaxf(mxa, mxb) * 0.125f;
+    }
+    uint32_t pk[16];
+    fx::exp_pack<kPoly8>(&s[0], make_float2(0.125f, 0.125f), make_float2(-m, -m), sum_a, sum_b, pk);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc ^= pk[i];
+    fx::exp_pack<kPoly8>(&s[32], make_float2(0.125f, 0.125f), make_float2(-m, -m), sum_a, sum_b, pk);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc ^= pk[i];
+    s[it & 63] ^= (acc & 1);  // keep the compiler from hoisting anything out of the loop
+  }
+  const long long t1 = clock64();
+  if (sum_a.x + sum_a.y + sum_b.x + sum_b.y == 123.456f || acc == 0x12345u) sink[0] = sum_a.x;
+  if (threadIdx.x == 0) out[0] = t1 - t0;
+}
+
+template <int kPoly8, bool kWithMax>
+void run_exp(const char* name) {
+  long long* d; float* sink;
+  cudaMalloc(&d, 8); cudaMalloc(&sink, 4);
+  for (int warps_per_sched : {1, 2, 4}) {
+    const int iters = 500;
+    exp_pack_kernel<kPoly8, kWithMax><<<1, 128 * warps_per_sched>>>(iters, 0.05f, d, sink);
+    exp_pack_kernel<kPoly8, kWithMax><<<1, 128 * warps_per_sched>>>(iters, 0.05f, d, sink);
+    cudaDeviceSynchronize();
+    long long h; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    printf("%-28s %d warp/sched: %6.2f clk per pair per scheduler, %7.1f clk per 64-score thread-tile per warp\n", name,
+           warps_per_sched, (double)h / (iters * 32.0 * warps_per_sched), (double)h / iters);
+  }
+  cudaFree(d); cudaFree(sink);
+}
+
+template <int KIND>
+void run(const char* name, double ops_per_round) {
+  long long* d; float* sink;
+  cudaMalloc(&d, 8); cudaMalloc(&sink, 4);
+  for (int warps_per_sched : {1, 2, 4}) {
+    const int iters = 2000;
+    rate_kernel<KIND><<<1, 128 * warps_per_sched>>>(iters, 0.5f, d, sink);
+    rate_kernel<KIND><<<1, 128 * warps_per_sched>>>(iters, 0.5f, d, sink);
+    cudaDeviceSynchronize();
+    long long h; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    printf("%-28s %d warp/sched: %6.2f clk per warp-instr per scheduler (%.2f clk per round of 16 per warp)\n", name,
+           warps_per_sched, (double)h / (iters * ops_per_round * warps_per_sched), (double)h / iters);
+  }
+  cudaFree(d); cudaFree(sink);
+}
+
+int main() {
+  run<0>("MUFU.EX2", 16);
+  run<1>("FFMA2 (fma.rn.f32x2)", 16);
+  run<2>("F2FP (cvt.rn.bf16x2.f32)", 16);
+  run<3>("FMNMX3 (max.f32 x3)", 16);
+  run<4>("FFMA", 16);
+  run<5>("softmax mix (per pair)", 16);
+  run<6>("MUFU.EX2.F16x2", 16);
+  run<7>("F2FP (cvt.rn.f16x2.f32)", 16);
+  run<8>("HADD2 (add.f16x2)", 16);
+  run<9>("f16 softmax mix (per pair)", 16);
+  run_exp<0, false>("exp_pack poly 0/8");
+  run_exp<2, false>("exp_pack poly 2/8");
+  run_exp<3, false>("exp_pack poly 3/8");
+  run_exp<4, false>("exp_pack poly 4/8");
+  run_exp<3, true>("max + exp_pack poly 3/8");
+  return 0;
+}
