@@ -168,10 +168,17 @@ struct RmsParams {
   const __nv_bfloat16* w2;
   const float2* freqs;  // [1024][64] (cos, sin) or nullptr
   int gf, gh, gw, tok_offset, rows_per_batch;
+  // Ulysses head scatter (n_peers > 0): instead of writing in place, every 128-wide head h of tensor `which` of row
+  // (b, t) goes to rank h / heads_per_peer at [(b * ntensors + which) * dst_rows + dst_row0 + t][h % heads_per_peer]
+  // of that rank's exchange buffer (peer memory over NVLink; the own slice is a local pointer). norm_tensors: how
+  // many of the leading tensors are normed + rotated (the rest - v - is moved as is).
+  int n_peers, heads_per_peer, norm_tensors, dst_row0;
+  long long dst_rows;
+  __nv_bfloat16* dst[8];
 };
 
 template <int NV, int WPR>  // NV = 16-byte vectors (8 bf16) per lane = D / (256 * WPR)
-__global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const RmsParams p) {
+__global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const __grid_constant__ RmsParams p) {
   __shared__ float red[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_in_block = warp / WPR, warp_in_row = warp % WPR;
@@ -199,10 +206,13 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const RmsParams p) {
       rsqrtf(row_reduce<WPR>(ss, red, row_in_block, warp_in_row, lane) / static_cast<float>(p.D) + p.eps));
   if (!valid) return;
 
+  const bool normed = which < p.norm_tensors;
   int pf = 0, ph = 0, pw = 0;
   bool rotate = false;
-  if (p.freqs != nullptr) {
-    const int t = p.tok_offset + row % p.rows_per_batch;
+  const int b = row / p.rows_per_batch;
+  const int tl = row - b * p.rows_per_batch;  // token inside this rank's slice of sample b
+  if (p.freqs != nullptr && normed) {
+    const int t = p.tok_offset + tl;
     if (t < p.gf * p.gh * p.gw) {
       rotate = true;
       pf = t / (p.gh * p.gw);
@@ -212,30 +222,44 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const RmsParams p) {
     }
   }
   const uint4* wr = reinterpret_cast<const uint4*>(which == 0 ? p.w : p.w2) + c0;
+  const long long drow = (static_cast<long long>(b) * p.ntensors + which) * p.dst_rows + p.dst_row0 + tl;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = i * 32 + lane;  // vector index inside this warp's span
-    const uint4 wv = __ldg(wr + c);
-    const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-    const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-    uint32_t o[4];
-    const int pair0 = ((c0 + c) & 15) * 4;  // first complex pair of this vector inside its 128-wide head
+    uint4 ov = v[i];
+    if (normed) {
+      const uint4 wv = __ldg(wr + c);
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+      uint32_t o[4];
+      const int pair0 = ((c0 + c) & 15) * 4;  // first complex pair of this vector inside its 128-wide head
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a = bf16_round(bf16_round(bf16_lo(u[j]) * r) * bf16_lo(ww[j]));
-      float b = bf16_round(bf16_round(bf16_hi(u[j]) * r) * bf16_hi(ww[j]));
-      if (rotate) {
-        const int pj = pair0 + j;
-        const int pos = pj < 22 ? pf : (pj < 43 ? ph : pw);
-        const float2 cs = __ldg(p.freqs + pos * 64 + pj);
-        const float re = a * cs.x - b * cs.y;
-        const float im = a * cs.y + b * cs.x;
-        a = re;
-        b = im;
+      for (int j = 0; j < 4; ++j) {
+        float a = bf16_round(bf16_round(bf16_lo(u[j]) * r) * bf16_lo(ww[j]));
+        float bb = bf16_round(bf16_round(bf16_hi(u[j]) * r) * bf16_hi(ww[j]));
+        if (rotate) {
+          const int pj = pair0 + j;
+          const int pos = pj < 22 ? pf : (pj < 43 ? ph : pw);
+          const float2 cs = __ldg(p.freqs + pos * 64 + pj);
+          const float re = a * cs.x - bb * cs.y;
+          const float im = a * cs.y + bb * cs.x;
+          a = re;
+          bb = im;
+        }
+        o[j] = pack_bf16x2(a, bb);
       }
-      o[j] = pack_bf16x2(a, b);
+      ov = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    xr[c] = make_uint4(o[0], o[1], o[2], o[3]);
+    if (p.n_peers == 0) {
+      xr[c] = ov;
+    } else {
+      const int gv = c0 + c;       // 16-byte vector index inside the D-wide row: 16 vectors per head
+      const int head = gv >> 4;
+      const int peer = head / p.heads_per_peer;
+      const int hl = head - peer * p.heads_per_peer;
+      uint4* d = reinterpret_cast<uint4*>(p.dst[peer]) + (drow * p.heads_per_peer + hl) * 16 + (gv & 15);
+      *d = ov;
+    }
   }
 }
 
@@ -306,6 +330,28 @@ extern "C" int fx_ln_affine(const float* x, void* out, int M, int D, float eps, 
   return launch_ln<1>(p, reinterpret_cast<cudaStream_t>(stream), "fx_ln_affine");
 }
 
+namespace fx {
+static int launch_rmsnorm_rope(const RmsParams& p, cudaStream_t s, const char* name) {
+  const int D = p.D;
+  const bool wide = (D % 1024 == 0) && D >= 2048;
+  const int wpr = wide ? 4 : 1;
+  const int nv = D / (256 * wpr);
+  const long long vrows = static_cast<long long>(p.M) * p.ntensors;
+  const int grid = static_cast<int>((vrows + (8 / wpr) - 1) / (8 / wpr));
+#define FX_RMS_CASE(NVV, WPRV)                                   \
+  if (nv == NVV && wpr == WPRV) {                                \
+    rmsnorm_rope_kernel<NVV, WPRV><<<grid, 256, 0, s>>>(p);      \
+    FX_CHECK_LAUNCH(name);                                       \
+    return FX_OK;                                                \
+  }
+  FX_RMS_CASE(1, 1) FX_RMS_CASE(2, 1) FX_RMS_CASE(4, 1) FX_RMS_CASE(6, 1) FX_RMS_CASE(10, 1)
+  FX_RMS_CASE(2, 4) FX_RMS_CASE(3, 4) FX_RMS_CASE(4, 4) FX_RMS_CASE(5, 4) FX_RMS_CASE(6, 4) FX_RMS_CASE(8, 4)
+#undef FX_RMS_CASE
+  set_error("%s: unsupported D=%d (supported: 256,512,1024,1536,2560 and 2048,3072,4096,5120,6144,8192)", name, D);
+  return FX_ERR_ARG;
+}
+}  // namespace fx
+
 extern "C" int fx_rmsnorm_rope(void* x, int64_t ldx, int M, int D, float eps, const void* weight,
                                const void* weight2, const float* freqs, int gf, int gh, int gw, int tok_offset,
                                int rows_per_batch, void* stream) {
@@ -320,29 +366,47 @@ extern "C" int fx_rmsnorm_rope(void* x, int64_t ldx, int M, int D, float eps, co
   } else {
     rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1;
   }
-  RmsParams p;
+  RmsParams p{};
   p.x = reinterpret_cast<__nv_bfloat16*>(x); p.ldx = ldx; p.M = M; p.D = D; p.ntensors = nt; p.eps = eps;
   p.w = reinterpret_cast<const __nv_bfloat16*>(weight);
   p.w2 = reinterpret_cast<const __nv_bfloat16*>(weight2);
   p.freqs = reinterpret_cast<const float2*>(freqs);
   p.gf = gf; p.gh = gh; p.gw = gw; p.tok_offset = tok_offset; p.rows_per_batch = rows_per_batch;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const bool wide = (D % 1024 == 0) && D >= 2048;
-  const int wpr = wide ? 4 : 1;
-  const int nv = D / (256 * wpr);
-  const long long vrows = static_cast<long long>(M) * nt;
-  const int grid = static_cast<int>((vrows + (8 / wpr) - 1) / (8 / wpr));
-#define FX_RMS_CASE(NVV, WPRV)                                   \
-  if (nv == NVV && wpr == WPRV) {                                \
-    rmsnorm_rope_kernel<NVV, WPRV><<<grid, 256, 0, s>>>(p);      \
-    FX_CHECK_LAUNCH("fx_rmsnorm_rope");                          \
-    return FX_OK;                                                \
+  p.norm_tensors = nt;
+  return launch_rmsnorm_rope(p, reinterpret_cast<cudaStream_t>(stream), "fx_rmsnorm_rope");
+}
+
+extern "C" int fx_qkv_norm_rope_scatter(const void* qkv, int64_t ldx, int M, int D, float eps, const void* weight_q,
+                                        const void* weight_k, const float* freqs, int gf, int gh, int gw,
+                                        int tok_offset, int rows_per_batch, void* const* peers, int n_peers,
+                                        int heads_per_peer, int64_t dst_rows, int dst_row0, void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(qkv && weight_q && weight_k && freqs && peers, "fx_qkv_norm_rope_scatter: null pointer");
+  FX_CHECK_ARG(M > 0 && D > 0 && D % 256 == 0 && ldx % 8 == 0 && ldx >= 3LL * D,
+               "fx_qkv_norm_rope_scatter: bad shape M=%d D=%d ldx=%lld", M, D, (long long)ldx);
+  FX_CHECK_ARG(gf > 0 && gh > 0 && gw > 0 && gf <= 1024 && gh <= 1024 && gw <= 1024 && rows_per_batch > 0 &&
+                   M % rows_per_batch == 0,
+               "fx_qkv_norm_rope_scatter: bad grid (%d,%d,%d) / rows_per_batch %d", gf, gh, gw, rows_per_batch);
+  FX_CHECK_ARG(n_peers >= 1 && n_peers <= 8 && heads_per_peer > 0 && n_peers * heads_per_peer * 128 == D,
+               "fx_qkv_norm_rope_scatter: %d peers x %d heads x 128 != D=%d", n_peers, heads_per_peer, D);
+  FX_CHECK_ARG(dst_row0 >= 0 && dst_rows >= static_cast<int64_t>(dst_row0) + rows_per_batch,
+               "fx_qkv_norm_rope_scatter: destination rows [%d, +%d) outside %lld", dst_row0, rows_per_batch,
+               (long long)dst_rows);
+  RmsParams p{};
+  p.x = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(qkv)); p.ldx = ldx; p.M = M; p.D = D; p.ntensors = 3;
+  p.eps = eps;
+  p.w = reinterpret_cast<const __nv_bfloat16*>(weight_q);
+  p.w2 = reinterpret_cast<const __nv_bfloat16*>(weight_k);
+  p.freqs = reinterpret_cast<const float2*>(freqs);
+  p.gf = gf; p.gh = gh; p.gw = gw; p.tok_offset = tok_offset; p.rows_per_batch = rows_per_batch;
+  p.norm_tensors = 2;
+  p.n_peers = n_peers; p.heads_per_peer = heads_per_peer; p.dst_rows = dst_rows; p.dst_row0 = dst_row0;
+  for (int i = 0; i < n_peers; ++i) {
+    FX_CHECK_ARG(peers[i] != nullptr && reinterpret_cast<uintptr_t>(peers[i]) % 16 == 0,
+                 "fx_qkv_norm_rope_scatter: peer buffer %d null or misaligned", i);
+    p.dst[i] = reinterpret_cast<__nv_bfloat16*>(peers[i]);
   }
-  FX_RMS_CASE(1, 1) FX_RMS_CASE(2, 1) FX_RMS_CASE(4, 1) FX_RMS_CASE(6, 1) FX_RMS_CASE(10, 1)
-  FX_RMS_CASE(2, 4) FX_RMS_CASE(3, 4) FX_RMS_CASE(4, 4) FX_RMS_CASE(5, 4) FX_RMS_CASE(6, 4) FX_RMS_CASE(8, 4)
-#undef FX_RMS_CASE
-  set_error("fx_rmsnorm_rope: unsupported D=%d (supported: 256,512,1024,1536,2560 and 2048,3072,4096,5120,6144,8192)", D);
-  return FX_ERR_ARG;
+  return launch_rmsnorm_rope(p, reinterpret_cast<cudaStream_t>(stream), "fx_qkv_norm_rope_scatter");
 }
 
 extern "C" int fx_cfg_euler_step(const void* vu, const void* vc, float guidance, float dsigma, float* lat,

@@ -52,6 +52,11 @@ struct FmhaParams {
   long long o_stride_b, o_stride_l;
   int Lq, Lk;
   float scale_log2;
+  // Ulysses output exchange (rows_per_peer > 0): query row i belongs to rank i / rows_per_peer and is written to
+  // o_peer[rank] + b*o_stride_b + (i % rows_per_peer)*o_stride_l + h*128 (peer memory over NVLink; the caller has
+  // already offset every base by this rank's first head).
+  int rows_per_peer;
+  __nv_bfloat16* o_peer[8];
 };
 
 
@@ -59,7 +64,7 @@ struct FmhaParams {
 template <int kPoly8>
 __global__ void __launch_bounds__(kFmhaThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                const __grid_constant__ CUtensorMap tmap_v, const FmhaParams p) {
+                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ FmhaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                    // [2 tiles][2 halves][128][64]
@@ -325,8 +330,15 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_wait(&o_done[w], 0);
     tc_fence_after();
     const float inv_l = 1.0f / l;
-    __nv_bfloat16* orow = p.o + static_cast<long long>(batch) * p.o_stride_b +
-                          static_cast<long long>(row) * p.o_stride_l + head * 128 + h * 64;
+    __nv_bfloat16* obase = p.o;
+    int orow_idx = row;
+    if (p.rows_per_peer > 0 && row < p.Lq) {
+      const int owner = row / p.rows_per_peer;
+      obase = p.o_peer[owner];
+      orow_idx = row - owner * p.rows_per_peer;
+    }
+    __nv_bfloat16* orow = obase + static_cast<long long>(batch) * p.o_stride_b +
+                          static_cast<long long>(orow_idx) * p.o_stride_l + head * 128 + h * 64;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       uint32_t o[32];
@@ -363,22 +375,22 @@ static bool make_qkv_tmap(CUtensorMap* m, const void* base, int64_t stride_b, in
 
 }  // namespace fx
 
-extern "C" int fx_fmha_fwd(const void* q, int64_t q_stride_b, int64_t q_stride_l, const void* k, int64_t k_stride_b,
-                           int64_t k_stride_l, const void* v, int64_t v_stride_b, int64_t v_stride_l, void* o,
-                           int64_t o_stride_b, int64_t o_stride_l, int B, int H, int Lq, int Lk, float scale,
-                           void* stream) {
-  using namespace fx;
-  FX_CHECK_ARG(q && k && v && o, "fx_fmha_fwd: null pointer");
-  FX_CHECK_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0, "fx_fmha_fwd: empty problem B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
-  FX_CHECK_ARG(H <= 65535 && B <= 65535, "fx_fmha_fwd: H and B must fit a grid dimension");
+namespace fx {
+static int fmha_launch(const void* q, int64_t q_stride_b, int64_t q_stride_l, const void* k, int64_t k_stride_b,
+                       int64_t k_stride_l, const void* v, int64_t v_stride_b, int64_t v_stride_l, void* o,
+                       void* const* o_peers, int n_peers, int rows_per_peer, int64_t o_stride_b, int64_t o_stride_l,
+                       int B, int H, int Lq, int Lk, float scale, void* stream, const char* name) {
+  FX_CHECK_ARG(q && k && v && (o || o_peers), "%s: null pointer", name);
+  FX_CHECK_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0, "%s: empty problem B=%d H=%d Lq=%d Lk=%d", name, B, H, Lq, Lk);
+  FX_CHECK_ARG(H <= 65535 && B <= 65535, "%s: H and B must fit a grid dimension", name);
   const int64_t strides[8] = {q_stride_b, q_stride_l, k_stride_b, k_stride_l, v_stride_b, v_stride_l, o_stride_b,
                               o_stride_l};
-  for (int64_t s : strides) FX_CHECK_ARG(s % 8 == 0 && s >= 0, "fx_fmha_fwd: strides must be multiples of 8 elements");
+  for (int64_t s : strides) FX_CHECK_ARG(s % 8 == 0 && s >= 0, "%s: strides must be multiples of 8 elements", name);
   FX_CHECK_ARG(q_stride_l >= 128LL * H && k_stride_l >= 128LL * H && v_stride_l >= 128LL * H && o_stride_l >= 128LL * H,
-               "fx_fmha_fwd: row stride smaller than H*128");
+               "%s: row stride smaller than H*128", name);
   FX_CHECK_ARG((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                 reinterpret_cast<uintptr_t>(o)) % 16 == 0,
-               "fx_fmha_fwd: pointers must be 16-byte aligned");
+               "%s: pointers must be 16-byte aligned", name);
 
   CUtensorMap tq, tk, tv;
   // a batch stride of 0 is not encodable; with B == 1 any non-zero value is equivalent
@@ -401,20 +413,53 @@ extern "C" int fx_fmha_fwd(const void* q, int64_t q_stride_b, int64_t q_stride_l
   if (!configured[poly]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmhaSmem);
     if (e != cudaSuccess) {
-      set_error("fx_fmha_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      set_error("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
       return FX_ERR_CUDA;
     }
     configured[poly] = true;
   }
-  FmhaParams p;
+  FmhaParams p{};
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.o_stride_b = o_stride_b;
   p.o_stride_l = o_stride_l;
   p.Lq = Lq;
   p.Lk = Lk;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.rows_per_peer = 0;
+  if (o_peers != nullptr) {
+    FX_CHECK_ARG(n_peers >= 1 && n_peers <= 8 && rows_per_peer > 0 &&
+                     static_cast<int64_t>(n_peers) * rows_per_peer >= Lq,
+                 "%s: %d peers x %d rows do not cover Lq=%d", name, n_peers, rows_per_peer, Lq);
+    p.rows_per_peer = rows_per_peer;
+    for (int i = 0; i < n_peers; ++i) {
+      FX_CHECK_ARG(o_peers[i] != nullptr && reinterpret_cast<uintptr_t>(o_peers[i]) % 16 == 0,
+                   "%s: peer buffer %d null or misaligned", name, i);
+      p.o_peer[i] = reinterpret_cast<__nv_bfloat16*>(o_peers[i]);
+    }
+    p.o = p.o_peer[0];
+  }
   dim3 grid((Lq + 255) / 256, H, B);
   kern<<<grid, kFmhaThreads, kFmhaSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
-  FX_CHECK_LAUNCH("fx_fmha_fwd");
+  FX_CHECK_LAUNCH(name);
   return FX_OK;
+}
+}  // namespace fx
+
+extern "C" int fx_fmha_fwd(const void* q, int64_t q_stride_b, int64_t q_stride_l, const void* k, int64_t k_stride_b,
+                           int64_t k_stride_l, const void* v, int64_t v_stride_b, int64_t v_stride_l, void* o,
+                           int64_t o_stride_b, int64_t o_stride_l, int B, int H, int Lq, int Lk, float scale,
+                           void* stream) {
+  return fx::fmha_launch(q, q_stride_b, q_stride_l, k, k_stride_b, k_stride_l, v, v_stride_b, v_stride_l, o, nullptr, 0,
+                         0, o_stride_b, o_stride_l, B, H, Lq, Lk, scale, stream, "fx_fmha_fwd");
+}
+
+extern "C" int fx_fmha_fwd_scatter(const void* q, int64_t q_stride_b, int64_t q_stride_l, const void* k,
+                                   int64_t k_stride_b, int64_t k_stride_l, const void* v, int64_t v_stride_b,
+                                   int64_t v_stride_l, void* const* o_peers, int n_peers, int rows_per_peer,
+                                   int64_t o_stride_b, int64_t o_stride_l, int B, int H, int Lq, int Lk, float scale,
+                                   void* stream) {
+  FX_CHECK_ARG(o_peers != nullptr, "fx_fmha_fwd_scatter: null peer table");
+  return fx::fmha_launch(q, q_stride_b, q_stride_l, k, k_stride_b, k_stride_l, v, v_stride_b, v_stride_l, nullptr,
+                         o_peers, n_peers, rows_per_peer, o_stride_b, o_stride_l, B, H, Lq, Lk, scale, stream,
+                         "fx_fmha_fwd_scatter");
 }

@@ -14,18 +14,37 @@ receives the batch-of-2 ``[uncond, cond]`` tensors (pipeline :850). Inside ``for
 and before returning all-gathers the head output over the SP group (dim 1, as :1103-1104) and the prediction over
 the CFG group (dim 0), so the caller sees the same ``[2, C, F, H, W]`` tensor as on one GPU.
 
-Layouts: 2 GPUs = CFG2 x SP1, 4 = CFG2 x SP2, 8 = CFG2 x SP4 (24 heads -> 6 per rank). Collectives are NCCL
-(all_to_all_single / all_gather_into_tensor) on the compute stream; packing to per-destination buffers is the native
-``fx_swap01_bf16`` kernel. The exchange functions take the permute/attention kernels as arguments so the CPU tests
-(world_size 2, gloo) can drive the same partitioning logic with torch stand-ins.
+Layouts: 2 GPUs = CFG2 x SP1, 4 = CFG2 x SP2, 8 = CFG2 x SP4 (24 heads -> 6 per rank).
+
+Two implementations of the exchange around self-attention:
+
+  * fused (GPUs, the product path): no collective call at all. The q|k RMSNorm+RoPE kernel writes every head straight
+    into the exchange buffer of the rank that owns it, and the attention kernel writes every output row straight into
+    the o-projection input of the rank that owns the token - plain 16-byte stores to peer-mapped memory over
+    NVLink/NVSwitch (``fx_qkv_norm_rope_scatter`` / ``fx_fmha_fwd_scatter``). The buffers are torch symmetric-memory
+    allocations (plumbing: allocation + peer pointers); two stream-ordered cross-rank barriers per layer order the
+    peer writes against their readers. Pack kernels, four all-to-alls and the unpack kernel per layer disappear.
+  * collective (``FLEXAM_SP_EXCHANGE=nccl``, and the gloo CPU tests): NCCL ``all_to_all_single`` with the native
+    ``fx_swap01_bf16`` pack/unpack kernels. The functions take the permute/attention kernels as arguments so the CPU
+    tests (world_size 2, gloo) drive the same partitioning logic with torch stand-ins.
+
+The token all-gather of the head output and the CFG all-gather of the prediction (once per step) stay NCCL.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Callable, List, Optional
 
 import torch
 import torch.distributed as dist
+
+
+@dataclass
+class SymmBuffer:
+    tensor: torch.Tensor
+    handle: object
+    ptrs: List[int]
 
 
 @dataclass
@@ -104,6 +123,51 @@ class Parallel:
             if s == layout.sp_rank:
                 self.cfg_group = g
         self._bufs = {}
+        self._symm = {}
+        self.fused = (os.environ.get("FLEXAM_SP_EXCHANGE", "fused") != "nccl" and layout.sp_size > 1 and
+                      dist.get_backend(self.sp_group) == "nccl")
+
+    # -- symmetric (peer-mapped) buffers for the fused exchange ---------------------------------------------------
+    def symm_buffer(self, name: str, shape, dtype, device) -> "SymmBuffer":
+        """A buffer every rank of the SP group allocates with the same shape, plus the device addresses of all
+        ranks' copies. Collective over the SP group on first use of a (name, shape)."""
+        key = (name, tuple(shape), dtype)
+        b = self._symm.get(key)
+        if b is None:
+            import torch.distributed._symmetric_memory as symm_mem
+            for k in [k for k in self._symm if k[0] == name]:
+                del self._symm[k]
+            t = symm_mem.empty(*shape, dtype=dtype, device=device)
+            hdl = symm_mem.rendezvous(t, self.sp_group)
+            b = SymmBuffer(t, hdl, [int(p) for p in hdl.buffer_ptrs])
+            self._symm[key] = b
+        return b
+
+    def attention_fused(self, qkv: torch.Tensor, attn: "SymmBuffer", w_q, w_k, eps, freqs, grid, L: int, scale: float,
+                        ops, timed=None) -> None:
+        """qkv: [B*Lp, 3D] packed projection output of the local token slices; attn: the symmetric [B*Lp, D] input
+        buffer of the o projection (filled by the peers). One scatter kernel, barrier, attention with scattered
+        output, barrier."""
+        lay = self.layout
+        P = lay.sp_size
+        D = qkv.shape[1] // 3
+        B = attn.tensor.shape[0]
+        Lp = attn.tensor.shape[1]
+        H = D // 128
+        Hl = H // P
+        full = self.symm_buffer("full", (B, 3, P * Lp, Hl * 128), qkv.dtype, qkv.device)
+        ops.qkv_norm_rope_scatter(qkv, D, w_q, w_k, eps, freqs, grid, lay.sp_rank * Lp, Lp, full.ptrs, Hl, P * Lp,
+                                  lay.sp_rank * Lp)
+        full.handle.barrier(0)            # every rank's heads have landed before anyone attends over them
+        f5 = full.tensor.view(B, 3, P * Lp, Hl, 128)
+        esz = attn.tensor.element_size()
+        head0 = lay.sp_rank * Hl * 128 * esz
+        args = (f5[:, 0], f5[:, 1, :L], f5[:, 2, :L], [p + head0 for p in attn.ptrs], Lp, Lp * D, D, scale)
+        if timed is None:
+            ops.fmha_scatter(*args)
+        else:
+            timed("fmha", 4.0 * B * Hl * (P * Lp) * L * 128, ops.fmha_scatter, *args)
+        full.handle.barrier(0)            # every rank's rows have landed before the o projection reads them
 
     def _buf(self, name, shape, like):
         key = (name, tuple(shape), like.dtype)

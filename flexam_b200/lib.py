@@ -25,6 +25,10 @@ SIGNATURES = {
     "fx_ln_affine": [_vp, _vp, _i, _i, _f, _vp, _vp, _vp],
     "fx_rmsnorm_rope": [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fx_fmha_fwd": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _f, _vp],
+    "fx_qkv_norm_rope_scatter": [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_vp), _i, _i, _i64,
+                                 _i, _vp],
+    "fx_fmha_fwd_scatter": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, C.POINTER(_vp), _i, _i, _i64, _i64, _i,
+                            _i, _i, _i, _f, _vp],
     "fx_patchify": [C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _i, _i, _i, _vp, _i64, _vp],
     "fx_unpatchify": [_vp, _i64, _vp, _i, _i, _i, _i, _vp],
     "fx_sinusoid": [_vp, _vp, _i, _i, _vp],

@@ -351,7 +351,12 @@ class NativeEngine:
         # ---- 30 x WanAttentionBlock (:422-472) ---------------------------------------------------------------
         h = self._buf("h", (M, D), bf16)
         qkv = self._buf("qkv", (M, 3 * D), bf16)
-        attn = self._buf("attn", (M, D), bf16)
+        fused_sp = P > 1 and par.fused
+        if fused_sp:    # the o-projection input is written by the peers: symmetric memory
+            attn_sym = par.symm_buffer("attn", (B, Lp, D), bf16, dev)
+            attn = attn_sym.tensor.view(M, D)
+        else:
+            attn = self._buf("attn", (M, D), bf16)
         cq = self._buf("cq", (M, D), bf16)
         ffn = self._buf("ffn", (M, cfg["ffn_dim"]), bf16)
         T = cfg["text_len"]
@@ -380,12 +385,16 @@ class NativeEngine:
             ops.ln_modulate(xs, h, self.eps, mod[0], mod[1], e0v[:, 0], e0v[:, 1], 6 * D, row_idx, dmod[0],
                             de0v[:, 0], 2 * D, Lp)
             self._gemm(h, w["wqkv"], w["bqkv"], qkv, FX_EPI_BF16)
-            ops.rmsnorm_rope(qkv[:, :2 * D], w["nq"], self.eps, self.freqs, grid, tok0, Lp, weight2=w["nk"])
-            if P == 1:
-                self._fmha(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], attn4, scale)
-            else:           # Ulysses: head-scatter all-to-all around attention, one sample at a time
-                for b in range(B):
-                    par.attention(qkv5[b], attn4[b], L, scale)
+            if fused_sp:    # Ulysses with the exchange fused into the norm/rope and attention kernels (peer stores)
+                par.attention_fused(qkv, attn_sym, w["nq"], w["nk"], self.eps, self.freqs, grid, L, scale, ops,
+                                    timed=self._timed)
+            else:
+                ops.rmsnorm_rope(qkv[:, :2 * D], w["nq"], self.eps, self.freqs, grid, tok0, Lp, weight2=w["nk"])
+                if P == 1:
+                    self._fmha(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], attn4, scale)
+                else:       # Ulysses through NCCL all-to-alls, one sample at a time
+                    for b in range(B):
+                        par.attention(qkv5[b], attn4[b], L, scale)
             self._gemm(attn, w["wo"], w["bo"], xs, FX_EPI_RESID_F32, gate_mod=mod[2], gate_e=e0v[:, 2], row_idx=row_idx)
             # cross-attention (no gate, no RoPE, all text_len slots attended)
             ops.ln_affine(xs, h, self.eps, w["n3w"], w["n3b"])

@@ -117,6 +117,41 @@ def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, s
     return out
 
 
+def qkv_norm_rope_scatter(qkv: torch.Tensor, D: int, weight_q: torch.Tensor, weight_k: torch.Tensor, eps: float,
+                          freqs: torch.Tensor, grid: Sequence[int], tok_offset: int, rows_per_batch: int,
+                          peer_ptrs: Sequence[int], heads_per_peer: int, dst_rows: int, dst_row0: int) -> None:
+    """qkv: bf16 [M, 3D] packed projection output of this rank's token slice. q and k are RMS-normed + rotated, v is
+    moved as is, and every head lands in the exchange buffer of the rank that owns it (peer memory). See
+    fx_qkv_norm_rope_scatter."""
+    _req(qkv, bf16, "qkv_norm_rope_scatter.qkv"), _req(weight_q, bf16, "qkv_norm_rope_scatter.weight_q")
+    _req(weight_k, bf16, "qkv_norm_rope_scatter.weight_k"), _req(freqs, f32, "qkv_norm_rope_scatter.freqs")
+    n = len(peer_ptrs)
+    ptrs = (C.c_void_p * n)(*peer_ptrs)
+    st = _l.load().fx_qkv_norm_rope_scatter(_p(qkv), qkv.stride(0), qkv.shape[0], D, eps, _p(weight_q), _p(weight_k),
+                                            _p(freqs), int(grid[0]), int(grid[1]), int(grid[2]), tok_offset,
+                                            rows_per_batch, ptrs, n, heads_per_peer, dst_rows, dst_row0, _stream())
+    _l.check(st, "fx_qkv_norm_rope_scatter")
+
+
+def fmha_scatter(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, peer_ptrs: Sequence[int], rows_per_peer: int,
+                 o_stride_b: int, o_stride_l: int, scale: float) -> None:
+    """fmha whose output row i goes to rank i // rows_per_peer (peer_ptrs: device addresses of every rank's [B, rows,
+    H_total, 128] attention-output buffer, already offset to this rank's first head). See fx_fmha_fwd_scatter."""
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _req(t, bf16, "fmha_scatter." + n)
+        if t.dim() != 4 or t.shape[3] != 128 or t.stride(2) != 128:
+            raise _l.FlexamNativeError(f"fmha_scatter.{n}: expected [B, L, H, 128] with contiguous heads, got "
+                                       f"{tuple(t.shape)} strides {t.stride()}")
+    B, Lq, H, _ = q.shape
+    Lk = k.shape[1]
+    n = len(peer_ptrs)
+    ptrs = (C.c_void_p * n)(*peer_ptrs)
+    st = _l.load().fx_fmha_fwd_scatter(_p(q), q.stride(0), q.stride(1), _p(k), k.stride(0), k.stride(1), _p(v),
+                                       v.stride(0), v.stride(1), ptrs, n, rows_per_peer, o_stride_b, o_stride_l, B, H,
+                                       Lq, Lk, scale, _stream())
+    _l.check(st, "fx_fmha_fwd_scatter")
+
+
 def patchify(srcs: Sequence[torch.Tensor], chan_last: Sequence[bool], F: int, H: int, W: int,
              rows: torch.Tensor) -> torch.Tensor:
     n = len(srcs)

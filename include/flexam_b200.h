@@ -155,6 +155,25 @@ int fx_cfg_euler_step(const void* vu, const void* vc, float guidance, float dsig
  */
 int fx_swap01_bf16(const void* in, int64_t ld_a, void* out, int A, int B, int inner, void* stream);
 
+/* Fused exchange (one kernel = compute + NVLink peer stores; replaces pack + all_to_all + unpack around attention):
+ *   fx_qkv_norm_rope_scatter: fx_rmsnorm_rope on the q and k thirds of the packed [M, 3D] projection output (v is
+ *     moved as is) with the result written head-scattered: head h of tensor w in {q,k,v} of row (b, t),
+ *     b = m / rows_per_batch, goes to peers[h / heads_per_peer] at
+ *     [((b*3 + w) * dst_rows + dst_row0 + t) * heads_per_peer + h % heads_per_peer][128].
+ *     peers: HOST array of n_peers (<= 8) DEVICE pointers to every rank's exchange buffer [B][3][dst_rows][D/n_peers]
+ *     (peer-mapped symmetric memory; entry `own rank` is the local buffer); dst_row0 = own rank * rows_per_batch.
+ *   fx_fmha_fwd_scatter: fx_fmha_fwd whose output row i is written to o_peers[i / rows_per_peer] at
+ *     b*o_stride_b + (i % rows_per_peer)*o_stride_l + h*128 (bases already offset by this rank's first head).
+ * The caller orders the peer writes against their consumers with a cross-rank barrier on the stream. */
+int fx_qkv_norm_rope_scatter(const void* qkv, int64_t ldx, int M, int D, float eps, const void* weight_q,
+                             const void* weight_k, const float* freqs, int gf, int gh, int gw, int tok_offset,
+                             int rows_per_batch, void* const* peers, int n_peers, int heads_per_peer,
+                             int64_t dst_rows, int dst_row0, void* stream);
+int fx_fmha_fwd_scatter(const void* q, int64_t q_stride_b, int64_t q_stride_l, const void* k, int64_t k_stride_b,
+                        int64_t k_stride_l, const void* v, int64_t v_stride_b, int64_t v_stride_l,
+                        void* const* o_peers, int n_peers, int rows_per_peer, int64_t o_stride_b, int64_t o_stride_l,
+                        int B, int H, int Lq, int Lk, float scale, void* stream);
+
 /* TeaCache residual bookkeeping on the fp32 token stream (:1003-1051): dst += src, out = a - b. */
 int fx_add_f32(float* dst, const float* src, int64_t n, void* stream);
 int fx_sub_f32(float* out, const float* a, const float* b, int64_t n, void* stream);

@@ -53,12 +53,15 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    names = sys.argv[1:] or ["tiny", "tiny_ragged", "real2"]
+    args = sys.argv[1:]
+    cfg_size = 1 if "cfg1" in args else None     # "cfg1": no CFG split, all ranks sequence-parallel
+    names = [a for a in args if a in CASES] or ["tiny", "tiny_ragged", "real2"]
     results, ok = [], True
     for name in names:
         cfg_name, grid, gold = CASES[name]
         cfg = synth.CONFIGS[cfg_name]
-        if cfg["num_heads"] % max(world // 2, 1) != 0:
+        sp = world // (cfg_size or (2 if world % 2 == 0 else 1))
+        if cfg["num_heads"] % sp != 0:
             continue
         inp = synth.inputs(cfg, *grid, per_token_t=True)
         kw = dict(x=torch.from_numpy(inp["x"]).to(dev).bfloat16(), t=torch.from_numpy(inp["t"]).to(dev),
@@ -69,7 +72,7 @@ def main():
                   density=torch.from_numpy(inp["density"]).to(dev))
         m = build(cfg, dev)
         single = m(**kw).clone()
-        layout = fdist.setup(m, world, rank)
+        layout = fdist.setup(m, world, rank, cfg_size=cfg_size)
         m.engine()._static_key = None
         multi = m(**kw).clone()
         torch.cuda.synchronize()
@@ -80,7 +83,8 @@ def main():
             rg = rel(multi, g)
         worst = torch.tensor([r, rg or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)
-        res = {"case": name, "world": world, "layout": layout, "rel_vs_single_gpu": worst[0].item(),
+        res = {"case": name, "world": world, "layout": layout,
+               "exchange": "fused" if getattr(m.engine().par, "fused", False) else "nccl", "rel_vs_single_gpu": worst[0].item(),
                "rel_vs_reference_golden": worst[1].item() if gold else None,
                "bit_identical": bool(torch.equal(multi, single))}
         ok = ok and worst[0].item() < 1e-3 and worst[1].item() < 1e-2

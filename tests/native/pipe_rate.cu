@@ -7,6 +7,7 @@
 
 #include "../../flexam_b200/csrc/softmax_math.cuh"
 
+namespace loc {
 __device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
   float2 d;
@@ -22,6 +23,10 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d; asm volatile("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d;
 }
 
+}  // namespace loc
+using loc::ex2;
+using loc::pack;
+
 template <int KIND>
 __global__ void rate_kernel(int iters, float seed, long long* out, float* sink) {
   float v[16];
@@ -34,9 +39,9 @@ __global__ void rate_kernel(int iters, float seed, long long* out, float* sink) 
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       if (KIND == 0) v[i] = ex2(v[i]);
-      if (KIND == 1) { float2 t = fma2(make_float2(v[i], v[(i + 1) & 15]), make_float2(0.999f, 0.999f), make_float2(1e-3f, 1e-3f)); v[i] = t.x; }
+      if (KIND == 1) { float2 t = loc::fma2(make_float2(v[i], v[(i + 1) & 15]), make_float2(0.999f, 0.999f), make_float2(1e-3f, 1e-3f)); v[i] = t.x; }
       if (KIND == 2) acc ^= pack(v[i], v[(i + 5) & 15]) + it;
-      if (KIND == 3) v[i] = fmax3(v[i], v[(i + 3) & 15], seed);
+      if (KIND == 3) v[i] = loc::fmax3(v[i], v[(i + 3) & 15], seed);
       if (KIND == 4) v[i] = fmaf(v[i], 0.999f, 1e-3f);
       if (KIND == 6) {  // ex2.approx.f16x2: two exponentials per MUFU op
         unsigned u = __float_as_uint(v[i]), r;
@@ -54,7 +59,7 @@ __global__ void rate_kernel(int iters, float seed, long long* out, float* sink) 
         v[i] = __uint_as_float(r);
       }
       if (KIND == 9) {  // f16 softmax mix per pair: fma2, cvt.f16x2, ex2.f16x2, add.f16x2
-        float2 t2 = fma2(make_float2(v[i], v[(i + 1) & 15]), make_float2(0.999f, 0.999f), make_float2(-1.f, -1.f));
+        float2 t2 = loc::fma2(make_float2(v[i], v[(i + 1) & 15]), make_float2(0.999f, 0.999f), make_float2(-1.f, -1.f));
         unsigned hx, e;
         asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hx) : "f"(t2.y), "f"(t2.x));
         asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(e) : "r"(hx));
@@ -62,11 +67,11 @@ __global__ void rate_kernel(int iters, float seed, long long* out, float* sink) 
         v[i] = v[i] * 0.999f + 1e-4f;
       }
       if (KIND == 5) {  // the softmax mix per pair: 1 fma2, 2 ex2, 1 add2-like fma2, 1 pack, 1 fmax3
-        float2 t = fma2(make_float2(v[i], v[(i + 1) & 15]), make_float2(0.999f, 0.999f), make_float2(-1.f, -1.f));
+        float2 t = loc::fma2(make_float2(v[i], v[(i + 1) & 15]), make_float2(0.999f, 0.999f), make_float2(-1.f, -1.f));
         const float a = ex2(t.x), b = ex2(t.y);
-        float2 u = fma2(make_float2(a, b), make_float2(1.f, 1.f), make_float2(v[(i + 2) & 15], v[(i + 3) & 15]));
+        float2 u = loc::fma2(make_float2(a, b), make_float2(1.f, 1.f), make_float2(v[(i + 2) & 15], v[(i + 3) & 15]));
         acc ^= pack(a, b);
-        v[i] = fmax3(u.x, u.y, seed) * 1e-3f;
+        v[i] = loc::fmax3(u.x, u.y, seed) * 1e-3f;
       }
     }
   }
@@ -78,9 +83,53 @@ __global__ void rate_kernel(int iters, float seed, long long* out, float* sink) 
   if (threadIdx.x == 0) out[0] = t1 - t0;
 }
 
+namespace var {
+using namespace fx;
+// V1: three passes over a 32-score chunk (arguments, exponentials, packs+sums)
+template <int kPoly8>
+__device__ __forceinline__ void exp_pack_v1(const uint32_t* s, float2 sc2, float2 nm2, float2& sum_a, float2& sum_b,
+                                            uint32_t (&pk)[16]) {
+  float2 e[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    e[i] = fma2(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sc2, nm2);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if ((i & 7) < kPoly8) e[i] = exp2_poly2(e[i]);
+    else { e[i].x = ex2_approx(e[i].x); e[i].y = ex2_approx(e[i].y); }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (i & 1) sum_b = add2(sum_b, e[i]); else sum_a = add2(sum_a, e[i]);
+    pk[i] = pack_bf16x2(e[i].x, e[i].y);
+  }
+}
+// V2: MUFU pairs first (all their ex2 issued up front), then the polynomial pairs (FMA pipe) while the MUFU queue
+// drains, then packs + sums
+template <int kPoly8>
+__device__ __forceinline__ void exp_pack_v2(const uint32_t* s, float2 sc2, float2 nm2, float2& sum_a, float2& sum_b,
+                                            uint32_t (&pk)[16]) {
+  float2 e[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    e[i] = fma2(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sc2, nm2);
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if ((i & 7) >= kPoly8) { e[i].x = ex2_approx(e[i].x); e[i].y = ex2_approx(e[i].y); }
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if ((i & 7) < kPoly8) e[i] = exp2_poly2(e[i]);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (i & 1) sum_b = add2(sum_b, e[i]); else sum_a = add2(sum_a, e[i]);
+    pk[i] = pack_bf16x2(e[i].x, e[i].y);
+  }
+}
+}  // namespace var
+
 // The shipped exponential pass (softmax_math.cuh: exp_pack) on 64 register-resident scores per thread per round,
 // i.e. one thread-tile of the attention kernel without its TMEM traffic and without the row maximum.
-template <int kPoly8, bool kWithMax>
+template <int kPoly8, bool kWithMax, int kVar = 0>
 __global__ void exp_pack_kernel(int iters, float seed, long long* out, float* sink) {
   uint32_t s[64];
 #pragma unroll
@@ -98,10 +147,15 @@ __global__ void exp_pack_kernel(int iters, float seed, long long* out, float* si
       m = fmaxf(mxa, mxb) * 0.125f;
     }
     uint32_t pk[16];
-    fx::exp_pack<kPoly8>(&s[0], make_float2(0.125f, 0.125f), make_float2(-m, -m), sum_a, sum_b, pk);
+    const float2 sc = make_float2(0.125f, 0.125f), nm = make_float2(-m, -m);
+    if (kVar == 0) fx::exp_pack<kPoly8>(&s[0], sc, nm, sum_a, sum_b, pk);
+    if (kVar == 1) var::exp_pack_v1<kPoly8>(&s[0], sc, nm, sum_a, sum_b, pk);
+    if (kVar == 2) var::exp_pack_v2<kPoly8>(&s[0], sc, nm, sum_a, sum_b, pk);
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc ^= pk[i];
-    fx::exp_pack<kPoly8>(&s[32], make_float2(0.125f, 0.125f), make_float2(-m, -m), sum_a, sum_b, pk);
+    if (kVar == 0) fx::exp_pack<kPoly8>(&s[32], sc, nm, sum_a, sum_b, pk);
+    if (kVar == 1) var::exp_pack_v1<kPoly8>(&s[32], sc, nm, sum_a, sum_b, pk);
+    if (kVar == 2) var::exp_pack_v2<kPoly8>(&s[32], sc, nm, sum_a, sum_b, pk);
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc ^= pk[i];
     s[it & 63] ^= (acc & 1);  // keep the compiler from hoisting anything out of the loop
@@ -111,14 +165,14 @@ __global__ void exp_pack_kernel(int iters, float seed, long long* out, float* si
   if (threadIdx.x == 0) out[0] = t1 - t0;
 }
 
-template <int kPoly8, bool kWithMax>
+template <int kPoly8, bool kWithMax, int kVar = 0>
 void run_exp(const char* name) {
   long long* d; float* sink;
   cudaMalloc(&d, 8); cudaMalloc(&sink, 4);
   for (int warps_per_sched : {1, 2, 4}) {
     const int iters = 500;
-    exp_pack_kernel<kPoly8, kWithMax><<<1, 128 * warps_per_sched>>>(iters, 0.05f, d, sink);
-    exp_pack_kernel<kPoly8, kWithMax><<<1, 128 * warps_per_sched>>>(iters, 0.05f, d, sink);
+    exp_pack_kernel<kPoly8, kWithMax, kVar><<<1, 128 * warps_per_sched>>>(iters, 0.05f, d, sink);
+    exp_pack_kernel<kPoly8, kWithMax, kVar><<<1, 128 * warps_per_sched>>>(iters, 0.05f, d, sink);
     cudaDeviceSynchronize();
     long long h; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
     printf("%-28s %d warp/sched: %6.2f clk per pair per scheduler, %7.1f clk per 64-score thread-tile per warp\n", name,
@@ -159,5 +213,10 @@ int main() {
   run_exp<3, false>("exp_pack poly 3/8");
   run_exp<4, false>("exp_pack poly 4/8");
   run_exp<3, true>("max + exp_pack poly 3/8");
+  run_exp<2, false, 1>("v1 3-pass poly 2/8");
+  run_exp<3, false, 1>("v1 3-pass poly 3/8");
+  run_exp<2, false, 2>("v2 mufu-first poly 2/8");
+  run_exp<3, false, 2>("v2 mufu-first poly 3/8");
+  run_exp<4, false, 2>("v2 mufu-first poly 4/8");
   return 0;
 }
