@@ -164,6 +164,45 @@ def test_ln_and_rmsnorm_rope(dev):
     assert _rel(small, ref_small) < 3e-3
 
 
+def test_fused_exchange_kernels_with_local_peers(dev):
+    """The Ulysses scatter variants write through a table of peer pointers; with every 'peer' a local buffer they must
+    reproduce rmsnorm_rope + the head-scatter permutation, and fmha + the row-scatter permutation, bit for bit."""
+    from flexam_b200 import ops
+    from flexam_b200.model import rope_table
+    g = torch.Generator(device=dev).manual_seed(17)
+    B, Lp, H, P = 2, 160, 4, 2          # 2 "ranks", 2 heads each; this process plays sp_rank 1
+    D, Hl, rank = H * 128, H // P, 1
+    grid = (5, 8, 8)                    # 320 tokens = P * Lp
+    qkv = torch.randn(B * Lp, 3 * D, device=dev, generator=g).bfloat16()
+    wq = (1 + 0.1 * torch.randn(D, device=dev, generator=g)).bfloat16()
+    wk = (1 + 0.1 * torch.randn(D, device=dev, generator=g)).bfloat16()
+    fr = rope_table(128).to(dev)
+    bufs = [torch.zeros(B, 3, P * Lp, Hl * 128, device=dev, dtype=torch.bfloat16) for _ in range(P)]
+    ops.qkv_norm_rope_scatter(qkv, D, wq, wk, 1e-6, fr, grid, rank * Lp, Lp, [b.data_ptr() for b in bufs], Hl, P * Lp,
+                              rank * Lp)
+    ref = qkv.clone()
+    ops.rmsnorm_rope(ref[:, :2 * D], wq, 1e-6, fr, grid, rank * Lp, Lp, weight2=wk)
+    r5 = ref.view(B, Lp, 3, P, Hl * 128)
+    for peer in range(P):
+        want = r5[:, :, :, peer].permute(0, 2, 1, 3)             # [B, 3, Lp, Hl*128]
+        assert torch.equal(bufs[peer][:, :, rank * Lp:(rank + 1) * Lp], want)
+        assert bufs[peer][:, :, :rank * Lp].abs().max().item() == 0  # other ranks' rows untouched
+
+    # attention with scattered output rows: owner of row i is i // Lp, destination column block = this rank's heads
+    L = P * Lp
+    q = torch.randn(B, L, Hl, 128, device=dev, generator=g).bfloat16()
+    k = torch.randn(B, L, Hl, 128, device=dev, generator=g).bfloat16()
+    v = torch.randn(B, L, Hl, 128, device=dev, generator=g).bfloat16()
+    want = torch.empty(B, L, Hl, 128, device=dev, dtype=torch.bfloat16)
+    ops.fmha(q, k[:, :L - 7], v[:, :L - 7], want, 128 ** -0.5)
+    outs = [torch.zeros(B, Lp, H, 128, device=dev, dtype=torch.bfloat16) for _ in range(P)]
+    head0 = rank * Hl * 128 * 2
+    ops.fmha_scatter(q, k[:, :L - 7], v[:, :L - 7], [o.data_ptr() + head0 for o in outs], Lp, Lp * D, D, 128 ** -0.5)
+    for owner in range(P):
+        assert torch.equal(outs[owner][:, :, rank * Hl:(rank + 1) * Hl], want[:, owner * Lp:(owner + 1) * Lp])
+        assert outs[owner][:, :, :rank * Hl].abs().max().item() == 0
+
+
 # ------------------------------------------------------------------------------------------------------
 # whole denoising step
 # ------------------------------------------------------------------------------------------------------
