@@ -551,6 +551,23 @@ static bool use_pair_kernel(int M, int N, int bn) {
   return mode == 1 && bn == 256 && N % 256 == 0 && M >= 256;
 }
 
+// M-tiles (256 rows) per rasterisation group of the CTA-pair kernel. Within a group every n-tile reuses the group's A
+// panels; across groups the whole weight matrix is swept again. Measured on B200 (profiles/summary_r1.md, DRAM bytes
+// per launch at M = 23296): a K-heavy problem (ffn.2: A = 668 MB, 7 MB per panel) wants g = 1 so that A is read
+// once; a wide one (ffn.0 / qkv: W = 88 / 57 MB does not stay in L2 next to the streams) wants g = 12-16 so that W is
+// swept few times; with a small weight matrix the choice does not matter. FX_GEMM_GROUP_M overrides (experiments).
+static int pair_group_m(int N, int K) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* env = getenv("FX_GEMM_GROUP_M");
+    forced = env ? atoi(env) : 0;
+  }
+  if (forced > 0) return forced;
+  if (K >= 2 * N) return 1;
+  if (2LL * N * K <= (32LL << 20)) return 4;
+  return 12;
+}
+
 template <int BN, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
                        cudaStream_t stream) {
@@ -655,7 +672,7 @@ extern "C" int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t l
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (use_pair_kernel(M, N, bn)) {
     p.num_m_tiles = (M + 255) / 256;
-    p.group_m = 8;
+    p.group_m = pair_group_m(N, K);
     return dispatch_epi2(epilogue, ta, tb128, tout, p, s);
   }
   switch (bn) {
