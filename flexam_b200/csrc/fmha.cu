@@ -56,6 +56,7 @@ struct FmhaParams {
   // o_peer[rank] + b*o_stride_b + (i % rows_per_peer)*o_stride_l + h*128 (peer memory over NVLink; the caller has
   // already offset every base by this rank's first head).
   int rows_per_peer;
+  int token;  // softmax turn-taking between the two query tiles (see the softmax loop)
   __nv_bfloat16* o_peer[8];
 };
 
@@ -264,6 +265,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         continue;
       }
 #endif
+      // Turn-taking (named barriers 3/4, 256 waiting + 256 arriving threads): the exponential pass of one tile has
+      // the SM's MUFU and issue slots to itself while the tensor pipe works on the other tile, in the fixed order
+      // tile 0 step j, tile 1 step j, tile 0 step j+1, ... Measured +1.3 % (profiles/r1_tools/fmha_sched_*.log).
+      if (p.token && (w == 1 || j > 0)) asm volatile("bar.sync %0, 512;" ::"r"(3 + w) : "memory");
       uint32_t s[64];
       tmem_ld32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
       tmem_ld32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
@@ -311,6 +316,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       exp_chunk<kPoly8>(&s[0], sc2, nm2, sum_a, sum_b, s_tmem);
       if (warp == 0) FX_TRACE(13, j);
       exp_chunk<kPoly8>(&s[32], sc2, nm2, sum_a, sum_b, s_tmem + 16);
+      if (p.token && (w == 0 || j + 1 < n_kv)) asm volatile("bar.arrive %0, 512;" ::"r"(4 - w) : "memory");
       sum_a = add2(sum_a, sum_b);
       l += sum_a.x + sum_a.y;
       if (warp == 0) FX_TRACE(8, j);
@@ -400,11 +406,13 @@ static int fmha_launch(const void* q, int64_t q_stride_b, int64_t q_stride_l, co
   if (!make_qkv_tmap(&tv, v, bs(v_stride_b, v_stride_l, Lk), v_stride_l, B, H, Lk)) return FX_ERR_CUDA;
 
   // exp2 split between MUFU and the FMA pipe, in eighths of the pairs; FX_FMHA_POLY=0|2|3|4 overrides the default
-  static int poly = -1;
+  static int poly = -1, token = 1;
   if (poly < 0) {
     const char* env = getenv("FX_FMHA_POLY");
     poly = kDefaultPoly8;
     if (env && (env[0] == '0' || env[0] == '2' || env[0] == '3' || env[0] == '4')) poly = env[0] - '0';
+    const char* t = getenv("FX_FMHA_TOKEN");
+    if (t) token = t[0] != '0';
   }
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const FmhaParams);
   const Kern kerns[5] = {fmha_fwd_kernel<0>, nullptr, fmha_fwd_kernel<2>, fmha_fwd_kernel<3>, fmha_fwd_kernel<4>};
@@ -426,6 +434,7 @@ static int fmha_launch(const void* q, int64_t q_stride_b, int64_t q_stride_l, co
   p.Lk = Lk;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.rows_per_peer = 0;
+  p.token = token;
   if (o_peers != nullptr) {
     FX_CHECK_ARG(n_peers >= 1 && n_peers <= 8 && rows_per_peer > 0 &&
                      static_cast<int64_t>(n_peers) * rows_per_peer >= Lq,

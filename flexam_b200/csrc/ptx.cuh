@@ -309,12 +309,16 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
-// GELU, tanh approximation (torch.nn.GELU(approximate='tanh')), evaluated in fp32.
+// GELU, tanh approximation (torch.nn.GELU(approximate='tanh')), evaluated in fp32 as x * sigmoid(2u),
+// u = sqrt(2/pi) (x + 0.044715 x^3): 0.5 (1 + tanh u) = 1 / (1 + e^(-2u)). Two MUFU ops (ex2, rcp) and four FMA-pipe
+// ops instead of the ~25-instruction tanhf(); relative error ~1e-6 over the whole range (e^(-2u) -> inf gives -0).
 __device__ __forceinline__ float gelu_tanh(float x) {
-  const float k0 = 0.7978845608028654f;  // sqrt(2/pi)
-  const float k1 = 0.044715f;
-  float inner = k0 * (x + k1 * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(inner));
+  const float c0 = -2.3022081985f;            // -2 log2(e) sqrt(2/pi)
+  const float c1 = -2.3022081985f * 0.044715f;
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * fmaf(c1, x * x, c0)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+  return x * r;
 }
 
 }  // namespace fx
