@@ -35,6 +35,10 @@ struct LnParams {
   // MODE 1
   const __nv_bfloat16* gamma;
   const __nv_bfloat16* beta;
+  // MODE 2: precombined fp32 rows, out = LN(x) * tab_scale[row_idx[m]] + tab_shift[row_idx[m]]
+  const float* tab_scale;
+  const float* tab_shift;
+  long long tab_stride;
 };
 
 // A row is owned by WPR warps (4 for wide rows: 6 float4 per lane at D = 3072 keeps the kernel at ~60 registers and
@@ -111,6 +115,19 @@ __global__ void __launch_bounds__(256) ln_kernel(const LnParams p) {
       uint2 o;
       o.x = pack_bf16x2(y.x, y.y);
       o.y = pack_bf16x2(y.z, y.w);
+      orow[c] = o;
+    }
+  } else if constexpr (MODE == 2) {
+    const long long u = p.row_idx ? p.row_idx[row] : 0;
+    const float4* sc_t = reinterpret_cast<const float4*>(p.tab_scale + u * p.tab_stride) + c0;
+    const float4* sh_t = reinterpret_cast<const float4*>(p.tab_shift + u * p.tab_stride) + c0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = i * 32 + lane;
+      const float4 sc = __ldg(sc_t + c), sh = __ldg(sh_t + c);
+      uint2 o;
+      o.x = pack_bf16x2((v[i].x - mean) * rstd * sc.x + sh.x, (v[i].y - mean) * rstd * sc.y + sh.y);
+      o.y = pack_bf16x2((v[i].z - mean) * rstd * sc.z + sh.z, (v[i].w - mean) * rstd * sc.w + sh.w);
       orow[c] = o;
     }
   } else {
@@ -264,6 +281,30 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const __grid_constant
 }
 
 // -------------------------------------------------------------------------------------------------
+// Per-block modulation rows (:444-449) combined once per (timestep u, sample b) instead of once per token:
+//   tab[s][u*B + b][0][:] = 1 + (mod[3s+1] + e0[u][3s+1])                       s = 0: self-attention LN, 1: ffn LN
+//   tab[s][u*B + b][1][:] = (mod[3s] + e0[u][3s]) + (dmod[s] + de0[b][s])
+// -------------------------------------------------------------------------------------------------
+__global__ void modulation_tables_kernel(const float* mod, const float* dmod, const float* e0, const float* de0, int U,
+                                         int B, int D, float* tab) {
+  const long long total = 2LL * U * B * D;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total; i += stride) {
+    const int d = static_cast<int>(i % D);
+    long long r = i / D;
+    const int b = static_cast<int>(r % B);
+    r /= B;
+    const int u = static_cast<int>(r % U);
+    const int s = static_cast<int>(r / U);
+    const float* e = e0 + static_cast<long long>(u) * 6 * D;
+    float* row = tab + ((static_cast<long long>(s) * U * B + static_cast<long long>(u) * B + b) * 2) * D;
+    row[d] = 1.f + (mod[(3 * s + 1) * D + d] + e[(3 * s + 1) * D + d]);
+    row[D + d] = (mod[3 * s * D + d] + e[3 * s * D + d]) + (dmod[s * D + d] + de0[(static_cast<long long>(b) * 2 + s) * D + d]);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 __global__ void cfg_euler_kernel(const __nv_bfloat16* vu, const __nv_bfloat16* vc, float guidance, float dsigma,
                                  float* lat, const float* mask, const __nv_bfloat16* pinned, long long n) {
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -328,6 +369,30 @@ extern "C" int fx_ln_affine(const float* x, void* out, int M, int D, float eps, 
   p.gamma = reinterpret_cast<const __nv_bfloat16*>(gamma);
   p.beta = reinterpret_cast<const __nv_bfloat16*>(beta);
   return launch_ln<1>(p, reinterpret_cast<cudaStream_t>(stream), "fx_ln_affine");
+}
+
+extern "C" int fx_ln_scale_shift(const float* x, void* out, int M, int D, float eps, const float* scale,
+                                 const float* shift, int64_t row_stride, const int32_t* row_idx, void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(x && out && scale && shift, "fx_ln_scale_shift: null pointer");
+  FX_CHECK_ARG(M > 0 && D > 0 && D % 128 == 0 && row_stride % 4 == 0, "fx_ln_scale_shift: bad shape M=%d D=%d", M, D);
+  FX_CHECK_ARG((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) % 16 == 0,
+               "fx_ln_scale_shift: tables must be 16-byte aligned");
+  LnParams p{};
+  p.x = x; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.M = M; p.D = D; p.eps = eps;
+  p.tab_scale = scale; p.tab_shift = shift; p.tab_stride = row_stride; p.row_idx = row_idx;
+  return launch_ln<2>(p, reinterpret_cast<cudaStream_t>(stream), "fx_ln_scale_shift");
+}
+
+extern "C" int fx_modulation_tables(const float* mod, const float* dmod, const float* e0, const float* de0, int U,
+                                    int B, int D, float* tab, void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(mod && dmod && e0 && de0 && tab, "fx_modulation_tables: null pointer");
+  FX_CHECK_ARG(U > 0 && B > 0 && D > 0, "fx_modulation_tables: bad shape U=%d B=%d D=%d", U, B, D);
+  modulation_tables_kernel<<<ew_grid(2LL * U * B * D), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      mod, dmod, e0, de0, U, B, D, tab);
+  FX_CHECK_LAUNCH("fx_modulation_tables");
+  return FX_OK;
 }
 
 namespace fx {

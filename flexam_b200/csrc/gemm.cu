@@ -2,7 +2,7 @@
 // accumulators double-buffered in TMEM) -> fused epilogues. One CTA per SM, static round-robin tile schedule
 // with M-grouped rasterisation so the concurrently resident tiles share weight and activation panels in L2.
 //
-// Epilogues (include/flexam_b200.h): bf16 store, GELU-tanh + bf16 store, fp32 store, and the gated fp32 residual
+// Epilogues (include/flexam_b200.h): bf16 store, GELU-tanh + bf16 store, fp32 store (rounded / exact), and the gated fp32 residual
 // `x += bf16(acc + bias) * gate`. The residual variant never reads x: each epilogue warp stages its 32 x 32 fp32
 // slab in swizzled shared memory and issues a TMA reduction (`cp.reduce.async.bulk.tensor ... add.f32`), so the
 // read-modify-write happens in L2 with fully coalesced traffic while the next slab is being computed.
@@ -46,16 +46,26 @@ struct GemmParams {
   long long gate_e_stride;
   const int* row_idx;
   int num_m_tiles, num_n_tiles, group_m;
+  int n_span;  // n-tiles per outer slab of the rasterisation (num_n_tiles = one slab)
 };
 
+// Tile order: the N range is cut into slabs of n_span tile columns (outer loop); inside a slab, groups of group_m tile
+// rows are swept column by column with the row index fastest. The tiles in flight therefore form a
+// (group_m x in-flight columns) block: its A panels stay L2-resident across the slab's columns, and a slab's weight
+// panels stay resident while all of M streams past when n_span is small.
 __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& m_tile, int& n_tile) {
-  const int per_group = p.group_m * p.num_n_tiles;
-  const int g = tile / per_group;
+  const int per_slab = p.num_m_tiles * p.n_span;
+  const int slab = tile / per_slab;
+  const int n_first = slab * p.n_span;
+  const int ncols = min(p.n_span, p.num_n_tiles - n_first);
+  const int t = tile - slab * per_slab;
+  const int per_group = p.group_m * ncols;
+  const int g = t / per_group;
   const int first_m = g * p.group_m;
   const int gsize = min(p.group_m, p.num_m_tiles - first_m);
-  const int r = tile - g * per_group;
+  const int r = t - g * per_group;
   m_tile = first_m + r % gsize;
-  n_tile = r / gsize;
+  n_tile = n_first + r / gsize;
 }
 
 // y[j] = accumulator + bias for 8 consecutive columns starting at `col` (col < N guaranteed by the caller)
@@ -96,6 +106,10 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int
       o.w = pack_bf16x2(y[6], y[7]);
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col;
       *reinterpret_cast<uint4*>(dst) = o;
+    } else if constexpr (EPI == FX_EPI_F32_EXACT) {  // verification mode: no rounding after the fp32 accumulator
+      float* dst = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
+      *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
     } else {  // FX_EPI_F32
       float* dst = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
       float4 o0 = make_float4(bf16_round(y[0]), bf16_round(y[1]), bf16_round(y[2]), bf16_round(y[3]));
@@ -536,6 +550,7 @@ static int dispatch_epi2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, 
     case FX_EPI_GELU_BF16: return launch_gemm2<FX_EPI_GELU_BF16>(ta, tb, tout, p, s);
     case FX_EPI_F32: return launch_gemm2<FX_EPI_F32>(ta, tb, tout, p, s);
     case FX_EPI_RESID_F32: return launch_gemm2<FX_EPI_RESID_F32>(ta, tb, tout, p, s);
+    case FX_EPI_F32_EXACT: return launch_gemm2<FX_EPI_F32_EXACT>(ta, tb, tout, p, s);
   }
   set_error("fx_gemm_bf16: unknown epilogue %d", epi);
   return FX_ERR_ARG;
@@ -599,6 +614,7 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
     case FX_EPI_GELU_BF16: return launch_gemm<BN, FX_EPI_GELU_BF16>(ta, tb, tout, p, s);
     case FX_EPI_F32: return launch_gemm<BN, FX_EPI_F32>(ta, tb, tout, p, s);
     case FX_EPI_RESID_F32: return launch_gemm<BN, FX_EPI_RESID_F32>(ta, tb, tout, p, s);
+    case FX_EPI_F32_EXACT: return launch_gemm<BN, FX_EPI_F32_EXACT>(ta, tb, tout, p, s);
   }
   set_error("fx_gemm_bf16: unknown epilogue %d", epi);
   return FX_ERR_ARG;
@@ -640,6 +656,7 @@ extern "C" int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t l
   p.num_m_tiles = (M + kBM - 1) / kBM;
   p.num_n_tiles = (N + bn - 1) / bn;
   p.group_m = 16;
+  p.n_span = p.num_n_tiles;
 
   CUtensorMap ta, tb, tout;
   {
@@ -673,6 +690,12 @@ extern "C" int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t l
   if (use_pair_kernel(M, N, bn)) {
     p.num_m_tiles = (M + 255) / 256;
     p.group_m = pair_group_m(N, K);
+    static int forced_span = -1;  // FX_GEMM_N_SPAN: experiments with the slab width of the rasterisation
+    if (forced_span < 0) {
+      const char* env = getenv("FX_GEMM_N_SPAN");
+      forced_span = env ? atoi(env) : 0;
+    }
+    if (forced_span > 0 && forced_span < p.num_n_tiles) p.n_span = forced_span;
     return dispatch_epi2(epilogue, ta, tb128, tout, p, s);
   }
   switch (bn) {

@@ -23,6 +23,8 @@ SIGNATURES = {
     "fx_gemm_bf16": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _i64, _vp, _vp],
     "fx_ln_modulate": [_vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp],
     "fx_ln_affine": [_vp, _vp, _i, _i, _f, _vp, _vp, _vp],
+    "fx_modulation_tables": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "fx_ln_scale_shift": [_vp, _vp, _i, _i, _f, _vp, _vp, _i64, _vp, _vp],
     "fx_rmsnorm_rope": [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fx_fmha_fwd": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _f, _vp],
     "fx_qkv_norm_rope_scatter": [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_vp), _i, _i, _i64,
@@ -42,9 +44,18 @@ SIGNATURES = {
     "fx_sub_f32": [_vp, _vp, _vp, _i64, _vp],
     "fx_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "fx_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
+    # fp32 verification mode (flexam_b200/precise.py)
+    "fx_split3_f32": [_vp, _i64, _i, _i, _vp, _vp],
+    "fx_join3_f32": [_vp, _i64, _vp, _vp],
+    "fx_ln_f32": [_vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp],
+    "fx_rmsnorm_rope_f32": [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "fx_gelu_f32": [_vp, _i64, _vp],
+    "fx_gated_residual_f32": [_vp, _vp, _i, _i, _vp, _vp, _i64, _vp, _vp],
+    "fx_attention_f32": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _f, _vp],
+    "fx_groupnorm_silu_f32": [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp],
 }
 
-FX_EPI_BF16, FX_EPI_GELU_BF16, FX_EPI_F32, FX_EPI_RESID_F32 = 0, 1, 2, 3
+FX_EPI_BF16, FX_EPI_GELU_BF16, FX_EPI_F32, FX_EPI_RESID_F32, FX_EPI_F32_EXACT = 0, 1, 2, 3, 4
 
 _lib = None
 

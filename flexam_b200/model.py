@@ -366,6 +366,10 @@ class NativeEngine:
         cq4 = cq.view(B, Lp, self.H, 128)
         e0v = e0.view(-1, 6, D)
         de0v = de0.view(B, 2, D)
+        # the block LayerNorms read modulation rows combined once per (distinct timestep, sample): row u*B + b
+        U = e0v.shape[0]
+        row_idx2 = (row_idx.view(B, Lp) * B + torch.arange(B, device=dev, dtype=i32).view(B, 1)).view(-1)
+        modtab = self._buf("modtab", (2, U * B, 2, D), f32)
 
         # ---- TeaCache (:977-1051): skip the block stack and re-apply the previous residual when the modulated
         #      timestep embedding moved little. The decision uses the GLOBAL last token so all SP ranks agree.
@@ -381,9 +385,9 @@ class NativeEngine:
                 ori = xs.clone()
         for i, w in enumerate(self.blk if run_blocks else ()):
             mod, dmod = w["mod"], w["dmod"]
+            ops.modulation_tables(mod, dmod, e0v, de0v, modtab)
             # self-attention
-            ops.ln_modulate(xs, h, self.eps, mod[0], mod[1], e0v[:, 0], e0v[:, 1], 6 * D, row_idx, dmod[0],
-                            de0v[:, 0], 2 * D, Lp)
+            ops.ln_scale_shift(xs, h, self.eps, modtab[0, :, 0], modtab[0, :, 1], 2 * D, row_idx2)
             self._gemm(h, w["wqkv"], w["bqkv"], qkv, FX_EPI_BF16)
             if fused_sp:    # Ulysses with the exchange fused into the norm/rope and attention kernels (peer stores)
                 par.attention_fused(qkv, attn_sym, w["nq"], w["nk"], self.eps, self.freqs, grid, L, scale, ops,
@@ -404,11 +408,10 @@ class NativeEngine:
             self._fmha(cq4, kv5[:, :, 0], kv5[:, :, 1], attn4, scale)
             self._gemm(attn, w["cwo"], w["cbo"], xs, FX_EPI_RESID_F32)
             # ffn
-            ops.ln_modulate(xs, h, self.eps, mod[3], mod[4], e0v[:, 3], e0v[:, 4], 6 * D, row_idx, dmod[1],
-                            de0v[:, 1], 2 * D, Lp)
+            ops.ln_scale_shift(xs, h, self.eps, modtab[1, :, 0], modtab[1, :, 1], 2 * D, row_idx2)
             self._gemm(h, w["w1"], w["b1"], ffn, FX_EPI_GELU_BF16)
             self._gemm(ffn, w["w2"], w["b2"], xs, FX_EPI_RESID_F32, gate_mod=mod[5], gate_e=e0v[:, 5], row_idx=row_idx)
-            self.launches += 5
+            self.launches += 6
             if block_hook is not None:
                 block_hook(i, xs)
         if teacache is not None and run_blocks:

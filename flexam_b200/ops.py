@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import lib as _l
-from .lib import FX_EPI_BF16, FX_EPI_F32, FX_EPI_GELU_BF16, FX_EPI_RESID_F32  # noqa: F401
+from .lib import FX_EPI_BF16, FX_EPI_F32, FX_EPI_F32_EXACT, FX_EPI_GELU_BF16, FX_EPI_RESID_F32  # noqa: F401
 
 bf16, f32, i32 = torch.bfloat16, torch.float32, torch.int32
 
@@ -72,6 +72,33 @@ def ln_modulate(x: torch.Tensor, out: torch.Tensor, eps: float, shift_mod: torch
                                   e_stride, _p(row_idx), _p(dens_mod), _p(dens), dens_stride, rows_per_batch,
                                   _stream())
     _l.check(st, "fx_ln_modulate")
+    return out
+
+
+def modulation_tables(mod: torch.Tensor, dmod: torch.Tensor, e0: torch.Tensor, de0: torch.Tensor,
+                      tab: torch.Tensor) -> torch.Tensor:
+    """tab f32 [2, U*B, 2, D] from mod [6,D], dmod [2,D], e0 [U,6,D], de0 [B,2,D] (all f32, contiguous)."""
+    for n, t in (("mod", mod), ("dmod", dmod), ("e0", e0), ("de0", de0), ("tab", tab)):
+        _req(t, f32, "modulation_tables." + n)
+        if not t.is_contiguous():
+            raise _l.FlexamNativeError(f"modulation_tables.{n}: contiguous tensor required")
+    U, B, D = e0.shape[0], de0.shape[0], mod.shape[1]
+    if tuple(tab.shape) != (2, U * B, 2, D) or tuple(e0.shape) != (U, 6, D) or tuple(de0.shape) != (B, 2, D):
+        raise _l.FlexamNativeError("modulation_tables: shape mismatch")
+    _l.check(_l.load().fx_modulation_tables(_p(mod), _p(dmod), _p(e0), _p(de0), U, B, D, _p(tab), _stream()),
+             "fx_modulation_tables")
+    return tab
+
+
+def ln_scale_shift(x: torch.Tensor, out: torch.Tensor, eps: float, scale: torch.Tensor, shift: torch.Tensor,
+                   row_stride: int, row_idx: Optional[torch.Tensor]) -> torch.Tensor:
+    _req(x, f32, "ln_scale_shift.x"), _req(out, bf16, "ln_scale_shift.out")
+    _req(scale, f32, "ln_scale_shift.scale"), _req(shift, f32, "ln_scale_shift.shift")
+    if row_idx is not None:
+        _req(row_idx, i32, "ln_scale_shift.row_idx")
+    M, D = x.shape
+    st = _l.load().fx_ln_scale_shift(_p(x), _p(out), M, D, eps, _p(scale), _p(shift), row_stride, _p(row_idx), _stream())
+    _l.check(st, "fx_ln_scale_shift")
     return out
 
 
@@ -257,3 +284,93 @@ def sub(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
             raise _l.FlexamNativeError("sub: contiguous tensors of equal size required")
     _l.check(_l.load().fx_sub_f32(_p(out), _p(a), _p(b), a.numel(), _stream()), "fx_sub_f32")
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# fp32 verification mode (see include/flexam_b200.h and flexam_b200/precise.py)
+# ----------------------------------------------------------------------------------------------------------
+def split3(x: torch.Tensor, planes: torch.Tensor) -> torch.Tensor:
+    """planes bf16 [3, M, K] (hi, mid, lo) with hi + mid + lo == x exactly; x f32 [M, K] (row stride free)."""
+    _req(x, f32, "split3.x"), _req(planes, bf16, "split3.planes")
+    M, K = x.shape
+    if tuple(planes.shape) != (3, M, K) or not planes.is_contiguous():
+        raise _l.FlexamNativeError(f"split3: planes must be contiguous [3, {M}, {K}], got {tuple(planes.shape)}")
+    _l.check(_l.load().fx_split3_f32(_p(x), x.stride(0), M, K, _p(planes), _stream()), "fx_split3_f32")
+    return planes
+
+
+def join3(planes: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _req(planes, bf16, "join3.planes"), _req(out, f32, "join3.out")
+    if planes.shape[0] != 3 or planes[0].numel() != out.numel() or not planes.is_contiguous() or not out.is_contiguous():
+        raise _l.FlexamNativeError("join3: planes must be contiguous [3, n...] matching a contiguous out")
+    _l.check(_l.load().fx_join3_f32(_p(planes), out.numel(), _p(out), _stream()), "fx_join3_f32")
+    return out
+
+
+def ln_f32(x: torch.Tensor, out: torch.Tensor, eps: float, shift_mod=None, scale_mod=None, shift_e=None, scale_e=None,
+           e_stride: int = 0, row_idx=None, dens_mod=None, dens=None, dens_stride: int = 0, rows_per_batch: int = 0,
+           gamma=None, beta=None) -> torch.Tensor:
+    _req(x, f32, "ln_f32.x"), _req(out, f32, "ln_f32.out")
+    M, D = x.shape
+    st = _l.load().fx_ln_f32(_p(x), _p(out), M, D, eps, _p(shift_mod), _p(scale_mod), _p(shift_e), _p(scale_e), e_stride,
+                             _p(row_idx), _p(dens_mod), _p(dens), dens_stride, rows_per_batch, _p(gamma), _p(beta),
+                             _stream())
+    _l.check(st, "fx_ln_f32")
+    return out
+
+
+def rmsnorm_rope_f32(x: torch.Tensor, weight: torch.Tensor, eps: float, freqs: Optional[torch.Tensor] = None,
+                     grid: Sequence[int] = (0, 0, 0), tok_offset: int = 0, rows_per_batch: int = 0,
+                     weight2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, f32, "rmsnorm_rope_f32.x"), _req(weight, bf16, "rmsnorm_rope_f32.weight")
+    M, D = x.shape
+    if weight2 is not None:
+        D //= 2
+    st = _l.load().fx_rmsnorm_rope_f32(_p(x), x.stride(0), M, D, eps, _p(weight), _p(weight2), _p(freqs), int(grid[0]),
+                                       int(grid[1]), int(grid[2]), tok_offset,
+                                       rows_per_batch if rows_per_batch > 0 else M, _stream())
+    _l.check(st, "fx_rmsnorm_rope_f32")
+    return x
+
+
+def gelu_f32_(x: torch.Tensor) -> torch.Tensor:
+    _req(x, f32, "gelu_f32.x")
+    if not x.is_contiguous():
+        raise _l.FlexamNativeError("gelu_f32: contiguous tensor required")
+    _l.check(_l.load().fx_gelu_f32(_p(x), x.numel(), _stream()), "fx_gelu_f32")
+    return x
+
+
+def gated_residual_f32_(x: torch.Tensor, y: torch.Tensor, gate_mod=None, gate_e=None, row_idx=None) -> torch.Tensor:
+    _req(x, f32, "gated_residual_f32.x"), _req(y, f32, "gated_residual_f32.y")
+    if x.shape != y.shape or not x.is_contiguous() or not y.is_contiguous():
+        raise _l.FlexamNativeError("gated_residual_f32: x and y must be contiguous and equal-shaped")
+    M, N = x.shape
+    ge_stride = gate_e.stride(0) if (gate_e is not None and gate_e.dim() == 2) else 0
+    st = _l.load().fx_gated_residual_f32(_p(x), _p(y), M, N, _p(gate_mod), _p(gate_e), ge_stride, _p(row_idx), _stream())
+    _l.check(st, "fx_gated_residual_f32")
+    return x
+
+
+def attention_f32(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, scale: float) -> torch.Tensor:
+    for n, t in (("q", q), ("k", k), ("v", v), ("out", out)):
+        _req(t, f32, "attention_f32." + n)
+        if t.dim() != 4 or t.shape[3] != 128 or t.stride(2) != 128:
+            raise _l.FlexamNativeError(f"attention_f32.{n}: expected [B, L, H, 128] with contiguous heads")
+    B, Lq, H, _ = q.shape
+    st = _l.load().fx_attention_f32(_p(q), q.stride(0), q.stride(1), _p(k), k.stride(0), k.stride(1), _p(v),
+                                    v.stride(0), v.stride(1), _p(out), out.stride(0), out.stride(1), B, H, Lq,
+                                    k.shape[1], scale, _stream())
+    _l.check(st, "fx_attention_f32")
+    return out
+
+
+def groupnorm_silu_f32(x: torch.Tensor, groups: int, eps: float, gamma: torch.Tensor, beta: torch.Tensor,
+                       resid: Optional[torch.Tensor], y: torch.Tensor, stats: torch.Tensor) -> torch.Tensor:
+    _req(x, f32, "groupnorm_silu_f32.x"), _req(y, f32, "groupnorm_silu_f32.y")
+    _req(gamma, bf16, "groupnorm_silu_f32.gamma"), _req(beta, bf16, "groupnorm_silu_f32.beta")
+    P, Cc = x.shape
+    st = _l.load().fx_groupnorm_silu_f32(_p(x), P, Cc, groups, eps, _p(gamma), _p(beta), _p(resid), _p(y), _p(stats),
+                                         _stream())
+    _l.check(st, "fx_groupnorm_silu_f32")
+    return y

@@ -56,6 +56,7 @@ int fx_check_device(int device);
 #define FX_EPI_GELU_BF16 1
 #define FX_EPI_F32 2
 #define FX_EPI_RESID_F32 3
+#define FX_EPI_F32_EXACT 4 /* out f32 = acc + bias, no bf16 rounding (fp32 verification mode, see below) */
 int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* out, int64_t ldo,
                  int M, int N, int K, int epilogue, const float* gate_mod, const float* gate_e,
                  int64_t gate_e_stride, const int32_t* row_idx, void* stream);
@@ -75,6 +76,18 @@ int fx_ln_modulate(const float* x, void* out, int M, int D, float eps, const flo
                    int rows_per_batch, void* stream);
 int fx_ln_affine(const float* x, void* out, int M, int D, float eps, const void* gamma, const void* beta,
                  void* stream);
+/* The block-level LayerNorm sites with the modulation combined once per (distinct timestep u, sample b) instead of
+ * per token (same arithmetic as fx_ln_modulate, :444-453,:464-465):
+ *   fx_modulation_tables: tab f32 [2][U*B][2][D]; site s (0 = self-attention LN, 1 = ffn LN), row u*B + b:
+ *     tab[s][u*B+b][0][:] = 1 + (mod[3s+1] + e0[u][3s+1]);  tab[s][u*B+b][1][:] = (mod[3s] + e0[u][3s]) + (dmod[s] + de0[b][s])
+ *     mod f32 [6,D] (blocks.i.modulation), dmod f32 [2,D], e0 f32 [U,6,D], de0 f32 [B,2,D].
+ *   fx_ln_scale_shift: out[m,:] = bf16(LN(x[m,:]) * scale[r,:] + shift[r,:]), r = row_idx[m] (NULL -> 0); scale/shift
+ *     rows are row_stride floats apart (for the table above: scale = tab[s], shift = tab[s] + D, row_stride = 2D,
+ *     row_idx[m] = u(m)*B + b(m)). */
+int fx_modulation_tables(const float* mod, const float* dmod, const float* e0, const float* de0, int U, int B, int D,
+                         float* tab, void* stream);
+int fx_ln_scale_shift(const float* x, void* out, int M, int D, float eps, const float* scale, const float* shift,
+                      int64_t row_stride, const int32_t* row_idx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Full-width RMSNorm (+ optional 3-axis RoPE), in place on bf16 rows (WanRMSNorm :173-189 applied to the
@@ -173,6 +186,37 @@ int fx_fmha_fwd_scatter(const void* q, int64_t q_stride_b, int64_t q_stride_l, c
                         int64_t k_stride_l, const void* v, int64_t v_stride_b, int64_t v_stride_l,
                         void* const* o_peers, int n_peers, int rows_per_peer, int64_t o_stride_b, int64_t o_stride_l,
                         int B, int H, int Lq, int Lk, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * fp32 verification mode (flexam_b200/precise.py): the same step with fp32 activations, for the north-star check
+ * "<= 1e-4 relative L2 against an fp32 run" of the reference. Contractions stay on tcgen05: an fp32 matrix is split
+ * EXACTLY into three bf16 planes (hi + mid + lo), each plane runs through fx_gemm_bf16 with FX_EPI_F32_EXACT and the
+ * three results are added with fx_add_f32; the bf16 gather kernels above move fp32 data losslessly plane by plane.
+ *   fx_split3_f32 : planes bf16 [3][M][K] (hi, mid, lo) from in f32 [M,K] (ldi); in == hi + mid + lo exactly
+ *   fx_join3_f32  : out f32 [n] = (lo + mid) + hi from planes bf16 [3][n]
+ *   fx_ln_f32     : fx_ln_modulate (gamma == NULL) or fx_ln_affine (gamma/beta bf16 [D]) with fp32 output, any D
+ *   fx_rmsnorm_rope_f32 : fx_rmsnorm_rope on fp32 rows without the bf16 roundings (the reference's fp32 flow :186-189)
+ *   fx_gelu_f32   : x = gelu_tanh(x) in place (:415)
+ *   fx_gated_residual_f32 : x[m,n] += y[m,n] * gate[m,n], gate as in FX_EPI_RESID_F32 (:456,:461,:468)
+ *   fx_attention_f32 : fx_fmha_fwd semantics on fp32 tensors (strides in elements), fp32 SIMT arithmetic
+ *   fx_groupnorm_silu_f32 : fx_groupnorm_silu on an fp32 conv output, fp32 result
+ */
+int fx_split3_f32(const float* in, int64_t ldi, int M, int K, void* planes, void* stream);
+int fx_join3_f32(const void* planes, int64_t n, float* out, void* stream);
+int fx_ln_f32(const float* x, float* out, int M, int D, float eps, const float* shift_mod, const float* scale_mod,
+              const float* shift_e, const float* scale_e, int64_t e_stride, const int32_t* row_idx,
+              const float* dens_mod, const float* dens, int64_t dens_stride, int rows_per_batch, const void* gamma,
+              const void* beta, void* stream);
+int fx_rmsnorm_rope_f32(float* x, int64_t ldx, int M, int D, float eps, const void* weight, const void* weight2,
+                        const float* freqs, int gf, int gh, int gw, int tok_offset, int rows_per_batch, void* stream);
+int fx_gelu_f32(float* x, int64_t n, void* stream);
+int fx_gated_residual_f32(float* x, const float* y, int M, int N, const float* gate_mod, const float* gate_e,
+                          int64_t gate_e_stride, const int32_t* row_idx, void* stream);
+int fx_attention_f32(const float* q, int64_t q_stride_b, int64_t q_stride_l, const float* k, int64_t k_stride_b,
+                     int64_t k_stride_l, const float* v, int64_t v_stride_b, int64_t v_stride_l, float* o,
+                     int64_t o_stride_b, int64_t o_stride_l, int B, int H, int Lq, int Lk, float scale, void* stream);
+int fx_groupnorm_silu_f32(const float* x, int64_t P, int C, int G, float eps, const void* gamma, const void* beta,
+                          const float* resid, float* y, float* stats, void* stream);
 
 /* TeaCache residual bookkeeping on the fp32 token stream (:1003-1051): dst += src, out = a - b. */
 int fx_add_f32(float* dst, const float* src, int64_t n, void* stream);

@@ -18,6 +18,9 @@ def gemm(a, w, bias, out, epilogue, gate_mod=None, gate_e=None, row_idx=None):
     y = a.double() @ w.double().t()
     if bias is not None:
         y = y + bias.double()
+    if epilogue == 4:      # FX_EPI_F32_EXACT: fp32 accumulator + bias, no bf16 rounding
+        out.copy_(y.float())
+        return out
     y = _rb(y.float())
     if epilogue == 0:
         out.copy_(y.to(bf16))
@@ -52,6 +55,23 @@ def ln_modulate(x, out, eps, shift_mod, scale_mod, shift_e, scale_e, e_stride, r
             d = d + dens_mod
         y = y + d
     out.copy_(y.to(bf16))
+    return out
+
+
+def modulation_tables(mod, dmod, e0, de0, tab):
+    U, B = e0.shape[0], de0.shape[0]
+    for s_ in range(2):
+        for u in range(U):
+            for b in range(B):
+                tab[s_, u * B + b, 0] = 1 + (mod[3 * s_ + 1] + e0[u, 3 * s_ + 1])
+                tab[s_, u * B + b, 1] = (mod[3 * s_] + e0[u, 3 * s_]) + (dmod[s_] + de0[b, s_])
+    return tab
+
+
+def ln_scale_shift(x, out, eps, scale, shift, row_stride, row_idx):
+    M, D = x.shape
+    idx = row_idx.long() if row_idx is not None else torch.zeros(M, dtype=torch.long)
+    out.copy_((F.layer_norm(x, (D,), eps=eps) * scale[idx] + shift[idx]).to(bf16))
     return out
 
 
@@ -165,8 +185,100 @@ def sub(a, b, out):
     return out.copy_(a - b)
 
 
+# ---- fp32 verification mode (csrc/precise.cu) ------------------------------------------------------------
+def split3(x, planes):
+    hi = x.to(bf16)
+    r1 = x - hi.float()
+    mid = r1.to(bf16)
+    lo = (r1 - mid.float()).to(bf16)
+    planes[0].copy_(hi), planes[1].copy_(mid), planes[2].copy_(lo)
+    return planes
+
+
+def join3(planes, out):
+    out.copy_(((planes[2].float() + planes[1].float()) + planes[0].float()).view(out.shape))
+    return out
+
+
+def ln_f32(x, out, eps, shift_mod=None, scale_mod=None, shift_e=None, scale_e=None, e_stride=0, row_idx=None,
+           dens_mod=None, dens=None, dens_stride=0, rows_per_batch=0, gamma=None, beta=None):
+    M, D = x.shape
+    ln = F.layer_norm(x, (D,), eps=eps)
+    if gamma is not None:
+        out.copy_(ln * gamma.float() + beta.float())
+        return out
+    idx = row_idx.long() if row_idx is not None else torch.zeros(M, dtype=torch.long)
+    y = ln * (1 + (scale_mod + scale_e[idx])) + (shift_mod + shift_e[idx])
+    if dens is not None:
+        d = dens[torch.arange(M) // rows_per_batch]
+        if dens_mod is not None:
+            d = d + dens_mod
+        y = y + d
+    out.copy_(y)
+    return out
+
+
+def rmsnorm_rope_f32(x, weight, eps, freqs=None, grid=(0, 0, 0), tok_offset=0, rows_per_batch=0, weight2=None):
+    if weight2 is not None:
+        D2 = x.shape[1] // 2
+        rmsnorm_rope_f32(x[:, :D2], weight, eps, freqs, grid, tok_offset, rows_per_batch or x.shape[0])
+        rmsnorm_rope_f32(x[:, D2:], weight2, eps, freqs, grid, tok_offset, rows_per_batch or x.shape[0])
+        return x
+    M, D = x.shape
+    y = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * weight.float()
+    if freqs is not None:
+        gf, gh, gw = grid
+        rpb = rows_per_batch if rows_per_batch > 0 else M
+        t = tok_offset + torch.arange(M) % rpb
+        valid = t < gf * gh * gw
+        tt = t.clamp(max=gf * gh * gw - 1)
+        f, h, w = tt // (gh * gw), (tt // gw) % gh, tt % gw
+        cs = torch.cat([freqs[f, :22], freqs[h, 22:43], freqs[w, 43:]], dim=1)
+        yv = y.view(M, D // 128, 64, 2)
+        c, s_ = cs[:, None, :, 0], cs[:, None, :, 1]
+        rot = torch.stack([yv[..., 0] * c - yv[..., 1] * s_, yv[..., 0] * s_ + yv[..., 1] * c], -1).reshape(M, D)
+        y = torch.where(valid[:, None], rot, y)
+    x.copy_(y)
+    return x
+
+
+def gelu_f32_(x):
+    return x.copy_(F.gelu(x, approximate="tanh"))
+
+
+def gated_residual_f32_(x, y, gate_mod=None, gate_e=None, row_idx=None):
+    if gate_mod is None and gate_e is None:
+        return x.add_(y)
+    gate = 0.0
+    if gate_mod is not None:
+        gate = gate + gate_mod[None]
+    if gate_e is not None:
+        idx = row_idx.long() if row_idx is not None else torch.zeros(x.shape[0], dtype=torch.long)
+        gate = gate + gate_e[idx]
+    return x.add_(y * gate)
+
+
+def attention_f32(q, k, v, out, scale):
+    s = torch.einsum("bqhd,bkhd->bhqk", q.double(), k.double()) * scale
+    out.copy_(torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), v.double()).float())
+    return out
+
+
+def groupnorm_silu_f32(x, groups, eps, gamma, beta, resid, y, stats):
+    P, C = x.shape
+    g = F.group_norm(x.t().reshape(1, C, P), groups, gamma.float(), beta.float(), eps=eps)
+    r = F.silu(g)[0].t()
+    y.copy_(r if resid is None else r + resid)
+    return y
+
+
+NAMES = ("gemm", "ln_modulate", "modulation_tables", "ln_scale_shift", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
+                 "linear_f32", "nchw_to_nhwc", "im2col3x3", "groupnorm_silu", "swap01", "add_", "sub", "split3", "join3",
+                 "ln_f32", "rmsnorm_rope_f32", "gelu_f32_", "gated_residual_f32_", "attention_f32",
+                 "groupnorm_silu_f32")
+
+
 def install(monkeypatch):
     from flexam_b200 import ops
-    for name in ("gemm", "ln_modulate", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
-                 "linear_f32", "nchw_to_nhwc", "im2col3x3", "groupnorm_silu", "swap01", "add_", "sub"):
+    for name in NAMES:
         monkeypatch.setattr(ops, name, globals()[name])

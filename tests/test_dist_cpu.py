@@ -25,8 +25,7 @@ def _free_port():
 def _patch_ops():
     import cpu_ops_emul
     from flexam_b200 import ops
-    for name in ("gemm", "ln_modulate", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
-                 "linear_f32", "nchw_to_nhwc", "im2col3x3", "groupnorm_silu", "swap01", "add_", "sub"):
+    for name in cpu_ops_emul.NAMES:
         setattr(ops, name, getattr(cpu_ops_emul, name))
 
 

@@ -78,3 +78,27 @@ def test_static_cache_tracks_in_place_edits(monkeypatch):
         m.blocks[0].self_attn.q.weight.mul_(0.5)
     b, _, _ = call(m, inp)
     assert rel(b, a) > 1e-4
+
+
+@pytest.mark.parametrize("per_tok,k_chunk", [(True, None), (False, 128)])
+def test_precise_engine_host_logic_matches_fp32_oracle(monkeypatch, per_tok, k_chunk):
+    """fp32 verification engine (flexam_b200/precise.py): plane splitting, plane-wise gathers and the launch order,
+    with the kernels replaced by their torch specifications, against the fp32 oracle and the reference golden."""
+    import os
+    from flexam_b200.precise import precise_engine
+    cpu_ops_emul.install(monkeypatch)
+    cfg = synth.CONFIGS["tiny"]
+    m, np_sd = build(cfg)
+    inp = synth.inputs(cfg, 3, 8, 12, per_token_t=per_tok)
+    tt = {k: torch.from_numpy(inp[k]) for k in ("x", "y", "additional_control", "full_ref", "t", "density")}
+    ctx = [torch.from_numpy(c) for c in inp["context"]]
+    eng = precise_engine(m)
+    eng.k_chunk = k_chunk
+    out = eng.forward(tt["x"], tt["t"], ctx, inp["seq_len"], tt["y"], tt["full_ref"], tt["additional_control"],
+                      tt["density"])
+    assert out.shape == (2, 48, 3, 8, 12) and out.dtype == torch.float32
+    want = O.forward(O.to_torch_sd(np_sd), cfg, tt["x"], tt["t"], ctx, inp["seq_len"], tt["y"], tt["full_ref"],
+                     tt["additional_control"], tt["density"], policy="fp32")
+    assert rel(out, want) < 2e-5
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "tiny_tok.npz" if per_tok else "tiny_sample.npz"))
+    assert rel(out, torch.from_numpy(gold["out"])) < 1e-4

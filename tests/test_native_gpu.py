@@ -277,6 +277,106 @@ def test_forward_is_deterministic_and_cache_consistent(dev):
     assert torch.equal(a, b) and torch.equal(a, c)
 
 
+# ------------------------------------------------------------------------------------------------------
+# fp32 verification mode (north star: <= 1e-4 relative L2 against the reference's fp32 run)
+# ------------------------------------------------------------------------------------------------------
+FP32_GATE = 1e-4
+
+
+def test_split3_is_exact_and_exact_epilogue_gemm_matches_fp64(dev):
+    """fp32 = hi + mid + lo bf16 planes exactly; three tcgen05 passes with the exact fp32 epilogue reproduce an fp64
+    matmul of the fp32 activations to fp32 round-off, at the longest reduction of the model (K = 14336)."""
+    from flexam_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(21)
+    M, N, K = 384, 512, 14336
+    a = torch.randn(M, K, device=dev, generator=g) * 3.0
+    a[0, :8] = torch.tensor([0.0, 1.0, -1.0, 1e-30, 3.0e38, -2.5e-30, 1.0 + 2 ** -23, 65504.0], device=dev)
+    planes = torch.empty(3, M, K, device=dev, dtype=torch.bfloat16)
+    ops.split3(a, planes)
+    back = torch.empty(M, K, device=dev)
+    ops.join3(planes, back)
+    assert torch.equal(back, a)
+    a[0, :8] = 0.5
+    ops.split3(a, planes)
+    w = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    b = torch.randn(N, device=dev, generator=g).bfloat16()
+    out, tmp = torch.empty(M, N, device=dev), torch.empty(M, N, device=dev)
+    ops.gemm(planes[2], w, None, out, ops.FX_EPI_F32_EXACT)
+    ops.gemm(planes[1], w, None, tmp, ops.FX_EPI_F32_EXACT)
+    ops.add_(out, tmp)
+    ops.gemm(planes[0], w, b, tmp, ops.FX_EPI_F32_EXACT)
+    ops.add_(out, tmp)
+    want = a.double() @ w.double().t() + b.double()
+    rel = (torch.linalg.vector_norm(out.double() - want) / torch.linalg.vector_norm(want)).item()
+    print(f"split-3 tcgen05 linear vs fp64, K={K}: rel-L2 {rel:.3e}")
+    assert rel < 2e-6
+
+
+def test_fp32_row_kernels_and_attention(dev):
+    from flexam_b200 import ops
+    from oracle import flexam_oracle as O
+    g = torch.Generator(device=dev).manual_seed(22)
+    B, L, H = 2, 208, 2
+    D = H * 128
+    q = torch.randn(B, L, H, 128, device=dev, generator=g)
+    k = torch.randn(B, 77, H, 128, device=dev, generator=g)
+    v = torch.randn(B, 77, H, 128, device=dev, generator=g)
+    out = torch.full((B, L, H, 128), float("nan"), device=dev)
+    ops.attention_f32(q, k, v, out, 128 ** -0.5)
+    s = torch.einsum("bqhd,bkhd->bhqk", q.double(), k.double()) * 128 ** -0.5
+    want = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), v.double())
+    assert _rel(out.double(), want) < 2e-6
+    # RMSNorm + RoPE against the oracle's fp32 policy (fp64 rotation)
+    grid = (2, 8, 13)
+    x = torch.randn(L, D, device=dev, generator=g)
+    wq = (1 + 0.1 * torch.randn(D, device=dev, generator=g)).bfloat16()
+    ang = O.rope_angles(128).to(dev)
+    want = O.rope_apply(O._rmsnorm(x, wq.float(), 1e-6, "fp32").view(L, H, 128), grid, ang).reshape(L, D)
+    got = x.clone()
+    ops.rmsnorm_rope_f32(got, wq, 1e-6, O.rope_table_f32(128).to(dev), grid, 0, L)
+    assert _rel(got, want) < 2e-6
+    # LayerNorm + modulation, GELU, gated residual
+    mod = torch.randn(6, D, device=dev, generator=g)
+    e = torch.randn(3, 6, D, device=dev, generator=g)
+    dens = torch.randn(2, 2, D, device=dev, generator=g)
+    idx = torch.randint(0, 3, (L,), device=dev, generator=g, dtype=torch.int32)
+    h = torch.empty(L, D, device=dev)
+    ops.ln_f32(x, h, 1e-6, mod[0], mod[1], e[:, 0], e[:, 1], 6 * D, idx, mod[2], dens[:, 0], 2 * D, L // 2)
+    ln = torch.nn.functional.layer_norm(x.double(), (D,), eps=1e-6)
+    bidx = torch.arange(L, device=dev) // (L // 2)
+    want = ln * (1 + mod[1] + e[idx.long(), 1]).double() + (mod[0] + e[idx.long(), 0]).double() + \
+        (mod[2] + dens[bidx, 0]).double()
+    assert _rel(h.double(), want) < 2e-6
+    gam, bet = (1 + 0.1 * torch.randn(D, device=dev, generator=g)).bfloat16(), torch.randn(D, device=dev, generator=g).bfloat16()
+    ops.ln_f32(x, h, 1e-6, gamma=gam, beta=bet)
+    assert _rel(h.double(), ln * gam.double() + bet.double()) < 2e-6
+    y = torch.randn(L, D, device=dev, generator=g)
+    gy = y.clone()
+    ops.gelu_f32_(gy)
+    assert _rel(gy.double(), torch.nn.functional.gelu(y.double(), approximate="tanh")) < 2e-6
+    xr = x.clone()
+    ops.gated_residual_f32_(xr, y, gate_mod=mod[5], gate_e=e[:, 5], row_idx=idx)
+    assert _rel(xr.double(), x.double() + y.double() * (mod[5] + e[idx.long(), 5]).double()) < 2e-6
+
+
+@pytest.mark.parametrize("name", ["tiny_tok", "tiny_sample", "real2_tok"])
+def test_precise_forward_matches_fp32_reference_golden(dev, golden_dir, name):
+    """The fp32 verification engine (split-3 tcgen05 GEMMs + fp32 row/attention kernels) vs the REAL reference's
+    fp32 CPU output: relative L2 <= 1e-4 (north star)."""
+    from flexam_b200.precise import precise_engine
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    F, H, W, per_tok = (int(v) for v in g["meta"])
+    model, cfg = _native_model(str(g["config"]), dev)
+    tt, ctx, seq_len = _inputs(cfg, (F, H, W), bool(per_tok), dev)
+    eng = precise_engine(model)
+    out = eng.forward(tt["x"], tt["t"], ctx, seq_len, tt["y"], tt["full_ref"], tt["additional_control"], tt["density"])
+    torch.cuda.synchronize()
+    assert out.shape == (2, cfg["out_dim"], F, H, W) and out.dtype == torch.float32
+    rel = _rel(out.cpu(), torch.from_numpy(g["out"]))
+    print(f"{name}: fp32 verification engine vs reference golden rel-L2 {rel:.3e} ({eng.launches} launches)")
+    assert rel < FP32_GATE
+
+
 def test_missing_extension_fails_loudly(monkeypatch):
     from flexam_b200 import lib
     monkeypatch.setattr(lib, "_lib", None)
