@@ -313,9 +313,10 @@ __global__ void cfg_euler_kernel(const __nv_bfloat16* vu, const __nv_bfloat16* v
     const float u = __bfloat162float(vu[i]);
     const float c = __bfloat162float(vc[i]);
     // the reference combines in the model dtype (bf16, one rounding per tensor op) at pipeline :928; the Euler
-    // update runs in fp32 and is cast back to the model dtype, so `lat` holds bf16-representable values.
+    // update adds (sigma' - sigma) * v — a 0-dim fp32 tensor times a bf16 tensor, i.e. a bf16 product under torch's
+    // type promotion — to the fp32 sample and casts back to the model dtype, so `lat` holds bf16-representable values.
     const float v = bf16_round(u + bf16_round(guidance * bf16_round(c - u)));
-    float x = bf16_round(lat[i] + dsigma * v);
+    float x = bf16_round(lat[i] + bf16_round(dsigma * v));
     if (mask != nullptr) {
       const float m = mask[i];
       x = bf16_round(bf16_round((1.f - m) * __bfloat162float(pinned[i])) + bf16_round(m * x));

@@ -180,9 +180,11 @@ def block_forward(sd, cfg, i, x, e0, dens0, grid, angles, ctx, policy, taps: Opt
 def forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, t: torch.Tensor, context: List[torch.Tensor],
             seq_len: int, y: torch.Tensor, full_ref: torch.Tensor, additional_control: torch.Tensor,
             density: torch.Tensor, policy: str = "fp32", num_layers: Optional[int] = None,
-            taps: Optional[dict] = None) -> torch.Tensor:
+            taps: Optional[dict] = None, teacache: Optional["TeaCacheOracle"] = None,
+            cond_flag: bool = True) -> torch.Tensor:
     """Restates forward() :817-1123 for the FlexAM configuration (y, full_ref, additional_control, density given;
-    clip_fea / y_camera / subject_ref absent; no TeaCache; sp_world_size 1). Returns [B, out_dim, F, H, W] fp32."""
+    clip_fea / y_camera / subject_ref absent; sp_world_size 1; TeaCache :977-1051 when `teacache` is given).
+    Returns [B, out_dim, F, H, W] fp32."""
     D, C = cfg["dim"], cfg["out_dim"]
     B, _, Fr, H, W = x.shape
     Hp, Wp = H // 2, W // 2
@@ -219,14 +221,30 @@ def forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, t: torch.Te
     if taps is not None:
         taps["x0"], taps["e"], taps["e0"], taps["ctx"], taps["cnn_out"] = xs.clone(), e, e0, ctx, cnn_out
 
+    # TeaCache :977-1051: decide from the modulated timestep embedding of the LAST token, then either run the block
+    # stack (remembering x_after - x_before) or re-apply the remembered residual of the last len(x) samples
+    run_blocks = True
+    if teacache is not None:
+        run_blocks = teacache.decide(e0[:, -1, :] if per_token else e0, cond_flag)
+    if run_blocks:
+        after = []
+        for b in range(B):
+            xb = xs[b]
+            for i in range(nl):
+                xb = block_forward(sd, cfg, i, xb, e0[b], de0[b], grid, angles, ctx[b], policy,
+                                   taps if (taps is not None and b == 0) else None)
+            after.append(xb)
+        after = torch.stack(after)
+        if teacache is not None:
+            teacache.store(after - xs, cond_flag)
+    else:
+        after = xs + teacache.residual(cond_flag)[-B:]
+    if taps is not None:
+        taps["x_final"] = after[0].clone()
+
     outs = []
     for b in range(B):
-        xb = xs[b]
-        for i in range(nl):
-            xb = block_forward(sd, cfg, i, xb, e0[b], de0[b], grid, angles, ctx[b], policy,
-                               taps if (taps is not None and b == 0) else None)
-        if taps is not None and b == 0:
-            taps["x_final"] = xb.clone()
+        xb = after[b]
         # head :493-507 — uses e (not e0) and a single density chunk
         hm = sd["head.modulation"][0] + e[b].unsqueeze(-2)               # [.., 2, D]
         hd = sd["head.modulation_density"][0, 0] + de[b]
@@ -237,7 +255,70 @@ def forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, t: torch.Te
         o = o.view(Fr, Hp, Wp, 1, 2, 2, C)
         o = torch.einsum("fhwpqrc->cfphqwr", o).reshape(C, Fr, H, W)
         outs.append(o)
+    if teacache is not None and cond_flag:                               # :1119-1122
+        teacache.cnt += 1
+        if teacache.cnt == teacache.num_steps:
+            teacache.reset()
     return torch.stack(outs)
+
+
+def forward_cfg_skip(sd, cfg, x, t, context, seq_len, y, full_ref, additional_control, density, cfg_skip_ratio,
+                     current_step: int, num_steps: int, **kw) -> torch.Tensor:
+    """forward() under its @cfg_skip() wrapper (FlexAM/utils/cfg_optimization.py:5-38): late in sampling only the
+    second (conditional) half of the batch is evaluated and the result is duplicated."""
+    bs = len(x)
+    skip = bs >= 2 and cfg_skip_ratio is not None and current_step >= num_steps * (1 - cfg_skip_ratio)
+    if skip:
+        h = bs // 2
+        x, t, context, y, full_ref, additional_control, density = (
+            u[h:] for u in (x, t, context, y, full_ref, additional_control, density))
+    out = forward(sd, cfg, x, t, context, seq_len, y, full_ref, additional_control, density, **kw)
+    return torch.cat([out, out], dim=0) if skip else out
+
+
+class TeaCacheOracle:
+    """Restates FlexAM/models/cache_utils.py:21-76 (state) and the decision block of forward :978-1000."""
+
+    def __init__(self, coefficients, num_steps: int, rel_l1_thresh: float = 0.0, num_skip_start_steps: int = 0):
+        self.coefficients = [float(c) for c in coefficients]
+        self.num_steps, self.rel_l1_thresh, self.num_skip_start_steps = num_steps, rel_l1_thresh, num_skip_start_steps
+        self.decisions = []          # test instrumentation: one bool per cond_flag forward
+        self.reset()
+
+    def reset(self):
+        self.cnt, self.should_calc, self.acc = 0, True, 0.0
+        self.prev_mod = self.res_cond = self.res_uncond = None
+
+    def rescale(self, d: float) -> float:      # np.poly1d(coefficients)(d): highest power first
+        y = 0.0
+        for c in self.coefficients:
+            y = y * d + c
+        return y
+
+    def decide(self, modulated_inp: torch.Tensor, cond_flag: bool) -> bool:
+        if not cond_flag:
+            return self.should_calc
+        if self.cnt < self.num_skip_start_steps:
+            self.should_calc, self.acc = True, 0.0
+        else:
+            d = ((modulated_inp - self.prev_mod).abs().mean() / self.prev_mod.abs().mean()).item()
+            self.acc += self.rescale(d)
+            if self.acc < self.rel_l1_thresh:
+                self.should_calc = False
+            else:
+                self.should_calc, self.acc = True, 0.0
+        self.prev_mod = modulated_inp.clone()
+        self.decisions.append(self.should_calc)
+        return self.should_calc
+
+    def store(self, residual: torch.Tensor, cond_flag: bool):
+        if cond_flag:
+            self.res_cond = residual
+        else:
+            self.res_uncond = residual
+
+    def residual(self, cond_flag: bool) -> torch.Tensor:
+        return self.res_cond if cond_flag else self.res_uncond
 
 
 def to_torch_sd(np_sd: dict, device="cpu") -> Dict[str, torch.Tensor]:

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — generates tests/golden/*.npz by running the REAL reference module (build container only).
 
-    python oracle/make_golden.py            # writes tests/golden/{tiny_tok,tiny_sample,real2_tok}.npz
+    python oracle/make_golden.py            # writes tests/golden/{tiny_tok,tiny_sample,real2_tok,tiny_loop}.npz
 
 Each fixture stores the reference's fp32 CPU output for ``oracle.synth`` weights/inputs (which are regenerated
 from names, so they are not stored), plus a few small intermediate slices used to localise a mismatch.
@@ -59,7 +59,75 @@ def run_case(name: str):
         meta=np.array([F, H, W, int(per_tok)], dtype=np.int64), config=np.array(cfg_name))
 
 
+# the sampling-loop fixture: 6 Euler steps (shift 5, guidance 6, density 10 = `full_edit`) around the REAL reference
+# module with TeaCache and cfg_skip enabled, so skipped block stacks and halved batches are both on the path
+LOOP = dict(config="tiny", grid=(3, 8, 12), steps=6, shift=5.0, guidance=6.0, density=10.0, cfg_skip_ratio=0.34,
+            # synthetic weights move the timestep embedding by a relative L1 of ~1 per step, so the rescale polynomial
+            # is the identity and the threshold sits between one and two steps' worth (with an 8 % margin)
+            teacache=dict(coefficients=[1.0, 0.0], rel_l1_thresh=1.9, num_skip_start_steps=1))
+
+
+def loop_tensors(cfg, F, H, W):
+    li = synth.loop_inputs(cfg, F, H, W)
+    return {k: ([torch.from_numpy(u) for u in v] if isinstance(v, list) else torch.from_numpy(v)) for k, v in li.items()}
+
+
+def run_loop(name: str = "tiny_loop"):
+    from oracle import sampler_oracle as S
+    cfg = synth.CONFIGS[LOOP["config"]]
+    F, H, W = LOOP["grid"]
+    sd = O.to_torch_sd(synth.state_dict(cfg))
+    model = ref_import.build_reference_model(cfg).eval()
+    model.load_state_dict(sd, strict=True)
+    tc = LOOP["teacache"]
+    model.enable_teacache(tc["coefficients"], LOOP["steps"], tc["rel_l1_thresh"], tc["num_skip_start_steps"], offload=False)
+    model.enable_cfg_skip(LOOP["cfg_skip_ratio"], LOOP["steps"])
+    ts, sig = S.euler_schedule(LOOP["steps"], LOOP["shift"])
+    # custom timesteps (the pipeline accepts them): the schedule rounded to bf16-representable values, so that the
+    # bf16 pipeline's `mask * t` (which rounds t to bf16) and this fp32 run see identical timesteps
+    ts = synth.to_bf16_f32(ts)
+    sig = np.concatenate([ts / np.float32(1000.0), np.zeros(1, np.float32)]).astype(np.float32)
+    decisions, batches = [], []
+
+    def ref_fn(**kw):
+        batches.append(len(kw["x"]))
+        out = model(**kw)
+        decisions.append(bool(model.should_calc))
+        return out
+
+    def set_ref(i, n):
+        model.current_steps, model.num_inference_steps = i, n
+
+    lt = loop_tensors(cfg, F, H, W)
+    trace = []
+    with torch.no_grad():
+        ref = S.denoise_loop(ref_fn, density=LOOP["density"], guidance_scale=LOOP["guidance"], timesteps=ts, sigmas=sig,
+                             set_step=set_ref, trace=trace, **lt)
+        # the same loop around the oracle forward (TeaCache / cfg_skip restated) must agree with it
+        otc = O.TeaCacheOracle(tc["coefficients"], LOOP["steps"], tc["rel_l1_thresh"], tc["num_skip_start_steps"])
+        state = {}
+
+        def set_or(i, n):
+            state["i"], state["n"] = i, n
+
+        def or_fn(x, context, t, density, seq_len, y, full_ref, additional_control):
+            return O.forward_cfg_skip(sd, cfg, x, t, context, seq_len, y, full_ref, additional_control, density,
+                                      cfg_skip_ratio=LOOP["cfg_skip_ratio"], current_step=state["i"],
+                                      num_steps=state["n"], teacache=otc)
+        mine = S.denoise_loop(or_fn, density=LOOP["density"], guidance_scale=LOOP["guidance"], timesteps=ts, sigmas=sig,
+                              set_step=set_or, **lt)
+    rel = ((ref - mine).norm() / ref.norm()).item()
+    print(f"{name}: TeaCache decisions {decisions} (oracle {otc.decisions}), forward batch sizes seen by cfg_skip "
+          f"wrapper input {batches}; oracle-loop rel-L2 {rel:.2e}")
+    assert decisions == otc.decisions and not all(decisions) and any(decisions[1:]), "want a mixed skip pattern"
+    assert rel < 2e-5
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), out=ref.numpy().astype(np.float32),
+                        decisions=np.array(decisions), timesteps=ts, sigmas=sig,
+                        step_norms=np.array([t.norm().item() for t in trace], dtype=np.float64),
+                        step0=trace[0].numpy().astype(np.float32))
+
+
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
-    for n in (sys.argv[1:] or list(CASES)):
-        run_case(n)
+    for n in (sys.argv[1:] or list(CASES) + ["tiny_loop"]):
+        run_loop(n) if n == "tiny_loop" else run_case(n)

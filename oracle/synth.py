@@ -128,3 +128,23 @@ def inputs(cfg: dict, F: int, H: int, W: int, B: int = 2, per_token_t: bool = Tr
         t = np.full((B,), t_value, np.float32)
     dens = np.full((B,), density, np.float32)
     return dict(x=x, y=y, additional_control=add, full_ref=full_ref, context=context, t=t, density=dens, seq_len=L0)
+
+
+def loop_inputs(cfg: dict, F: int, H: int, W: int, tag: str = "loop", prompt_lens=(37, 120)):
+    """Synthetic arguments of the sampling loop (pipeline_wan2_2_fun_control_FlexAM.py:843-934) for ONE video:
+    noisy latents, the latent mask with the first frame pinned, masked-video / mask / control / additional-control
+    latents, the reference-image latents and the negative / positive prompt embeddings."""
+    C = cfg["out_dim"]
+    mask = np.ones((1, 1, F, H, W), np.float32)
+    mask[:, :, 0] = 0.0
+    return dict(
+        latents=tensor(f"{tag}/latents", (1, C, F, H, W)),
+        mask=mask,
+        masked_video_latents=tensor(f"{tag}/masked_video", (1, C, F, H, W)),
+        mask_latents=np.broadcast_to(1.0 - mask, (1, 4, F, H, W)).astype(np.float32).copy(),
+        control_video_latents=tensor(f"{tag}/control", (1, C, F, H, W)),
+        additional_control=tensor(f"{tag}/additional_control", (1, cfg["in_dim_cnn"] - C, F, H, W)),
+        ref_image_latents=tensor(f"{tag}/ref", (1, C, H, W)),
+        negative_prompt_embeds=[tensor(f"{tag}/neg", (prompt_lens[0], cfg["text_dim"]))],
+        prompt_embeds=[tensor(f"{tag}/pos", (prompt_lens[1], cfg["text_dim"]))],
+    )

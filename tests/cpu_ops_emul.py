@@ -177,6 +177,15 @@ def swap01(src, out):
     return out
 
 
+def cfg_euler_step(vu, vc, guidance, dsigma, lat, mask, pinned):
+    u, c = vu.float(), vc.float()
+    v = _rb(u + _rb(guidance * _rb(c - u)))
+    x = _rb(lat + _rb(torch.tensor(dsigma, dtype=f32) * v))
+    if mask is not None:
+        x = _rb(_rb((1 - mask) * pinned.float()) + _rb(mask * x))
+    return lat.copy_(x)
+
+
 def add_(dst, src):
     return dst.add_(src)
 
@@ -273,7 +282,7 @@ def groupnorm_silu_f32(x, groups, eps, gamma, beta, resid, y, stats):
 
 
 NAMES = ("gemm", "ln_modulate", "modulation_tables", "ln_scale_shift", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
-                 "linear_f32", "nchw_to_nhwc", "im2col3x3", "groupnorm_silu", "swap01", "add_", "sub", "split3", "join3",
+                 "linear_f32", "nchw_to_nhwc", "im2col3x3", "groupnorm_silu", "swap01", "cfg_euler_step", "add_", "sub", "split3", "join3",
                  "ln_f32", "rmsnorm_rope_f32", "gelu_f32_", "gated_residual_f32_", "attention_f32",
                  "groupnorm_silu_f32")
 

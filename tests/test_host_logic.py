@@ -102,3 +102,21 @@ def test_precise_engine_host_logic_matches_fp32_oracle(monkeypatch, per_tok, k_c
     assert rel(out, want) < 2e-5
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "tiny_tok.npz" if per_tok else "tiny_sample.npz"))
     assert rel(out, torch.from_numpy(gold["out"])) < 1e-4
+
+
+def test_sampling_loop_host_logic_matches_reference_golden(monkeypatch, golden_dir):
+    """DenoiseLoop (CFG combine + Euler + re-pin kernel, TeaCache skipping, cfg_skip batch halving, static cache across
+    steps) with emulated kernels vs the fixture made with the real reference module."""
+    import loop_case
+    cpu_ops_emul.install(monkeypatch)
+    m, _ = build(synth.CONFIGS["tiny"])
+    g = loop_case.golden(golden_dir)
+    out, decisions, loop = loop_case.run_native_loop(m, g, "cpu")
+    assert decisions == [bool(d) for d in g["decisions"]]
+    assert out.dtype == torch.bfloat16 and loop.launches == 6
+    r = rel(out, torch.from_numpy(g["out"]))
+    print(f"emulated native loop vs reference loop golden: rel-L2 {r:.3e}")
+    assert r < 1e-2
+    # two bf16 paths with different rounding points, 6 guided steps (guidance 6 amplifies the CFG difference)
+    want, _ = loop_case.run_oracle_loop(g, policy="bf16", dtype=torch.bfloat16)
+    assert rel(out, want) < 1e-2

@@ -85,3 +85,28 @@ def test_param_tree_matches_between_product_and_oracle():
                              out_dim_cnn_block=cfg["out_dim_cnn"]))
     orc = {n: tuple(s) for n, s, _, _ in synth.param_specs(cfg)}
     assert prod == orc
+
+
+def test_oracle_sampling_loop_matches_reference_golden(golden_dir):
+    """The restated pipeline loop + TeaCache + cfg_skip around the oracle forward reproduces the fixture made with the
+    real reference module (and its real TeaCache / @cfg_skip) inside the same loop."""
+    import loop_case
+    g = loop_case.golden(golden_dir)
+    out, decisions = loop_case.run_oracle_loop(g)
+    assert decisions == [bool(d) for d in g["decisions"]] and not all(decisions)
+    assert _rel(out, torch.from_numpy(g["out"])) < 2e-5
+
+
+def test_euler_schedule_restatements_agree():
+    """Product and oracle restate diffusers' FlowMatchEulerDiscreteScheduler independently (parity unpinned: diffusers
+    is absent); they must agree with each other and with the closed form at the ends."""
+    from flexam_b200.sampler import flow_match_euler_schedule
+    from oracle import sampler_oracle
+    for n in (1, 6, 50):
+        t1, s1 = flow_match_euler_schedule(n, 5.0)
+        t2, s2 = sampler_oracle.euler_schedule(n, 5.0)
+        np.testing.assert_allclose(t1, t2, rtol=1e-6)
+        np.testing.assert_allclose(s1, s2, rtol=1e-6, atol=1e-9)
+        assert s1[0] == 1.0 and s1[-1] == 0.0 and len(s1) == n + 1 and np.all(np.diff(s1) < 0)
+    smin = 5.0 * 1e-3 / (1 + 4.0 * 1e-3)                    # the constructor's shifted sigma_min
+    np.testing.assert_allclose(s1[-2], 5.0 * smin / (1 + 4.0 * smin), rtol=1e-5)
