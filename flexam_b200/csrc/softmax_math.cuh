@@ -80,11 +80,15 @@ __device__ __forceinline__ void exp_pack(const uint32_t* s, float2 sc2, float2 n
   for (int i = 0; i < 16; ++i) {
     const float2 x = fma2(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sc2, nm2);
     float2 e;
+#if defined(FX_FMHA_EXPERIMENT) && FX_FMHA_EXPERIMENT == 5
+    e = x;  // timing experiment: no exponential at all (results are wrong)
+#else
     if ((i & 7) < kPoly8) {
       e = exp2_poly2(x);
     } else {
       e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
     }
+#endif
     if (i & 1) sum_b = add2(sum_b, e); else sum_a = add2(sum_a, e);
     pk[i] = pack_bf16x2(e.x, e.y);
   }

@@ -42,8 +42,12 @@ def bench_fmha():
     out = torch.empty(B, L, H, 128, device=dev, dtype=torch.bfloat16)
     ms = timeit(lambda: ops.fmha(v5[:, :, 0], v5[:, :, 1], v5[:, :, 2], out, 128 ** -0.5))
     fl = 4.0 * B * H * L * L * 128
-    print(json.dumps({"case": "fmha_self", "poly": os.environ.get("FX_FMHA_POLY", "default"), "ms": ms,
-                      "tflops": fl / ms / 1e9}))
+    torch.cuda.synchronize()
+    i16 = out.view(torch.int16).to(torch.int64).view(-1)
+    checksum = int((i16 * (torch.arange(i16.numel(), device=dev) % 8191 + 1)).sum().item())  # same for every FX_FMHA_PIPE
+    print(json.dumps({"case": "fmha_self", "poly": os.environ.get("FX_FMHA_POLY", "default"),
+                      "pipe": os.environ.get("FX_FMHA_PIPE", "default"), "token": os.environ.get("FX_FMHA_TOKEN", "default"),
+                      "ms": ms, "tflops": fl / ms / 1e9, "checksum": checksum}))
     # accuracy of the exp2 split against fp32 softmax on a slice
     q, k, v = v5[:1, :512, 0, :2].float(), v5[:1, :, 1, :2].float(), v5[:1, :, 2, :2].float()
     s = torch.einsum("bqhd,bkhd->bhqk", q, k) * 128 ** -0.5

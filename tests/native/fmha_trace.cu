@@ -13,9 +13,7 @@
 #include "../../include/flexam_b200.h"
 
 #ifdef FX_FMHA_TRACE
-namespace fx {
-extern __device__ long long fx_fmha_trace[16 * 64];
-}
+extern "C" int fx_fmha_trace_read(long long* dst);
 #endif
 
 int main(int argc, char** argv) {
@@ -53,13 +51,20 @@ int main(int argc, char** argv) {
     cudaEventElapsedTime(&ms, e0, e1);
     printf("launch %d: %.3f ms, %.1f TFLOP/s\n", it, ms, 4.0 * B * H * L * (double)L * 128 / ms / 1e9);
   }
-  {  // accuracy on 16 rows of (batch 0, head 1) against a double-precision softmax(QK^T/sqrt(d))V on the host
+  {  // accuracy on 16 rows of (batch 0, head 1) spread over both query tiles, all four TMEM lane quadrants and the
+     // ragged last CTA, against a double-precision softmax(QK^T/sqrt(d))V on the host; plus a checksum of the whole
+     // output (the pipelines selected by FX_FMHA_PIPE compute the same arithmetic: their checksums must agree)
     const int hh = 1, nrows = 16;
-    std::vector<__nv_bfloat16> ho(static_cast<size_t>(nrows) * H * 128);
+    const int rows[nrows] = {0, 37, 70, 127, 128, 161, 200, 255, 256, 300, 511, 5000, L - 130, L - 65, L - 2, L - 1};
+    std::vector<__nv_bfloat16> ho(n / 3);
     cudaMemcpy(ho.data(), o, ho.size() * 2, cudaMemcpyDeviceToHost);
+    unsigned long long fnv = 1469598103934665603ULL;
+    const unsigned short* raw = reinterpret_cast<const unsigned short*>(ho.data());
+    for (size_t i = 0; i < ho.size(); ++i) fnv = (fnv ^ raw[i]) * 1099511628211ULL;
     double num = 0, den = 0;
     std::vector<double> sc(L), acc(128);
-    for (int r = 0; r < nrows; ++r) {
+    for (int ri = 0; ri < nrows; ++ri) {
+      const int r = ((rows[ri] % L) + L) % L;
       const __nv_bfloat16* qr = h.data() + static_cast<size_t>(r) * sl + hh * 128;
       double mx = -1e300;
       for (int k = 0; k < L; ++k) {
@@ -83,19 +88,24 @@ int main(int argc, char** argv) {
         den += want * want;
       }
     }
-    printf("accuracy: rel-L2 %.3e over %d rows\n", sqrt(num / den), nrows);
+    printf("accuracy: rel-L2 %.3e over %d rows; output checksum %016llx\n", sqrt(num / den), nrows, fnv);
   }
 #ifdef FX_FMHA_TRACE
-  long long t[16 * 64];
-  cudaMemcpyFromSymbol(t, fx::fx_fmha_trace, sizeof(t));
-  const char* names[14] = {"mma:v_full", "mma:p0_seen", "mma:pv0+qk0_issued", "mma:p1_seen", "mma:iter_issued", "-",
+  long long t[24 * 64];
+  fx_fmha_trace_read(t);
+  // pipeline 1 meaning / pipeline 2-3 meaning (FX_FMHA_PIPE): rows 2 and 4 are "PV0 (+QK1) issued", "PV1 (+QK0) issued",
+  // row 5 is the QK issuer's "QK1(j) issued" (pipeline 3 only)
+  const char* names[24] = {"mma:v_full", "mma:p0_seen", "mma:pv0+qk_issued", "mma:p1_seen", "mma:iter_issued", "qk:qk1_issued",
                            "sm0:wait_s", "sm0:s_seen", "sm0:exp_done", "sm0:arrived",
-                           "sm0:max_exchanged", "sm0:s_loaded", "sm0:max_done", "sm0:exp_half"};
+                           "sm0:max_exchanged", "sm0:s_loaded", "sm0:max_done", "sm0:exp_half",
+                           // pipeline 2/3 only: tile 0 after the token barrier / after p_free; tile 1 (warp 8)
+                           "sm0:exp_start", "sm0:p_free_seen", "sm1:wait_s", "sm1:s_seen", "sm1:s_loaded",
+                           "sm1:max_exchanged", "sm1:exp_start", "sm1:exp_half", "sm1:exp_done", "sm1:arrived"};
   const long long t0 = t[0 * 64 + 8];
   printf("%-20s", "event \\ kv step");
   for (int j = 8; j < 24; ++j) printf("%7d", j);
   printf("\n");
-  for (int w = 0; w < 14; ++w) {
+  for (int w = 0; w < 24; ++w) {
     printf("%-20s", names[w]);
     for (int j = 8; j < 24; ++j) printf("%7lld", t[w * 64 + j] - t0);
     printf("\n");

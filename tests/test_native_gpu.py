@@ -101,6 +101,27 @@ def test_fmha_matches_softmax_attention(dev, B, H, Lq, Lk):
     assert _rel(out, want) < 6e-3
 
 
+@pytest.mark.parametrize("B,H,Lq,Lk", [(1, 2, 512, 2048), (2, 2, 300, 11648), (1, 1, 256, 44000)])
+def test_fmha_with_growing_row_maxima(dev, B, H, Lq, Lk):
+    """Peaked logits whose magnitude grows along the key axis: the running row maximum rises by far more than the lazy
+    rescale threshold (2^8) several times per row, so the in-TMEM rescale of the output accumulator and its ordering
+    against the PV MMAs are exercised (plain N(0,1) inputs never trigger it). The last case is the key length of the
+    long-clip configuration (193 frames 704x1280, 44,000 tokens; BASELINE config 5)."""
+    from flexam_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(Lq * 7 + Lk)
+    q = (torch.randn(B, Lq, H, 128, device=dev, generator=g) * 3).bfloat16()
+    ramp = torch.linspace(0.5, 4.0, Lk, device=dev).view(1, Lk, 1, 1)
+    k = (torch.randn(B, Lk, H, 128, device=dev, generator=g) * ramp).bfloat16()
+    v = torch.randn(B, Lk, H, 128, device=dev, generator=g).bfloat16()
+    out = torch.full((B, Lq, H, 128), float("nan"), device=dev, dtype=torch.bfloat16)
+    ops.fmha(q, k, v, out, 128 ** -0.5)
+    s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * 128 ** -0.5
+    assert (s.max(-1).values - s[..., :128].max(-1).values).min().item() > 8 / 1.4427  # every row does rescale
+    want = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), v.float())
+    assert not torch.isnan(out.float()).any()
+    assert _rel(out, want) < 8e-3
+
+
 def test_fmha_rows_are_convex_combinations_of_v(dev):
     """Property that holds at any size: with v == const the output is that constant (softmax weights sum to 1)."""
     from flexam_b200 import ops
@@ -305,9 +326,10 @@ def test_split3_is_exact_and_exact_epilogue_gemm_matches_fp64(dev):
 
     def linear(kc):
         first = True
-        for pl in (planes[2], planes[1], planes[0]):             # smallest contribution first
+        for i in (2, 1, 0):                                       # smallest contribution first
+            pl = planes[i]
             for c0 in range(0, K, kc):
-                last = pl is planes[0] and c0 + kc >= K
+                last = i == 0 and c0 + kc >= K
                 ops.gemm(pl[:, c0:c0 + kc], w[:, c0:c0 + kc], b if last else None, out if first else tmp,
                          ops.FX_EPI_F32_EXACT)
                 if not first:
