@@ -53,6 +53,17 @@ def step_flops(cfg, B=2):
     return B * float(cfg["num_layers"] * per_layer + front + cnn)
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the largest GEMM of the step (ffn.0, FX_EPI_GELU_BF16) from the committed
+    `ncu --set full` capture (profiles/traffic.json, written from profiles/summary_*.md), next to its algorithmic
+    bytes; None when the file is absent."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -205,6 +216,14 @@ def run_native(args):
     ev1.record()
     barrier()
     ms_value = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    # host time to enqueue ONE step into an empty stream (outside the timed region; inside it the launch queue is
+    # full and the host is throttled by the GPU): what bounds the step once the kernels get short (8 GPUs)
+    saved_timing, eng.timing = eng.timing, None
+    t_host0 = time.perf_counter()
+    call(resident)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
+    barrier()
+    eng.timing = saved_timing
     timing, eng.timing = eng.timing, None
     launches = eng.launches * args.steps
     fam = {}
@@ -214,7 +233,8 @@ def run_native(args):
 
     if args.quick:   # profiling runs (ncu) only need the resident region
         if rank == 0:
-            print(json.dumps({"quick": True, "ms_per_step": ms_value, "gpu_launches": launches}))
+            print(json.dumps({"quick": True, "ms_per_step": ms_value, "gpu_launches": launches,
+                              "host_enqueue_ms_per_step": host_enqueue_ms}))
         if clocks:
             clocks.stop()
         return
@@ -230,6 +250,7 @@ def run_native(args):
     ms_hoisted = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
 
     # ---------------- end-to-end region: pinned host -> device copies and device -> host result every step ----------
+    eng.cache_static = False    # like `value`: every end-to-end step does all the work, nothing is reused across steps
     out_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
     h2d = sum(v.numel() * v.element_size() for k, v in host.items() if hasattr(v, "numel")) + \
         sum(c.numel() * c.element_size() for c in host["context"])
@@ -257,6 +278,7 @@ def run_native(args):
     att = fam.get("fmha", [0.0, 1e-9, 0])
     gemm_tfs = gem[0] / (gem[1] * 1e-3) / 1e12
     att_tfs = att[0] / (att[1] * 1e-3) / 1e12
+    traffic = ncu_traffic()
     line = {
         "metric": METRIC, "value": 1e3 / ms_value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True, "scaling": "strong",
@@ -269,12 +291,13 @@ def run_native(args):
                     "note": "control fuser, text embedding and cross K/V cached across steps as in the 50-step sampler"},
         "e2e": {"value": 1e3 / ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches,
+        "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
         "roofline": {"kernel": "gemm_bf16_kernel (tcgen05, all epilogues)", "bound": "tensor", "achieved": gemm_tfs,
-                     "peak": sustained, "unit": "TFLOP/s", "frac": gemm_tfs / sustained, "traffic": None,
+                     "peak": sustained, "unit": "TFLOP/s", "frac": gemm_tfs / sustained,
+                     "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "traffic_detail": traffic,
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src}); burst {burst}",
                      "launches": gem[2], "share_of_step": gem[1] / args.steps / ms_value},
-        "roofline_fmha": {"kernel": "fmha_fwd_kernel (tcgen05)", "bound": "tensor", "achieved": att_tfs,
+        "roofline_fmha": {"kernel": "fmha2_fwd_kernel (tcgen05)", "bound": "tensor", "achieved": att_tfs,
                           "peak": sustained, "unit": "TFLOP/s", "frac": att_tfs / sustained, "launches": att[2],
                           "share_of_step": att[1] / args.steps / ms_value},
         "clocks": clk,

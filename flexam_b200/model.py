@@ -258,9 +258,12 @@ class NativeEngine:
             out.append(kv)
         return out
 
-    @staticmethod
-    def _ident(ts) -> tuple:
-        return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
+    def _static_hit(self, srcs) -> bool:
+        """True when every step-invariant input equals the copy the cached results were computed from."""
+        old = self._static_key
+        if old is None or len(old) != len(srcs) or any(a.shape != b.shape for a, b in zip(old, srcs)):
+            return False
+        return bool(torch.stack([(a == b).all() for a, b in zip(old, srcs)]).all().item())
 
     # -- the denoising step ----------------------------------------------------------------------------------
     @torch.no_grad()
@@ -306,13 +309,18 @@ class NativeEngine:
         M = B * Lp
 
         # ---- step-invariant work: control fuser, context embedding, cross-attention K/V ----------------------
-        skey = (self._ident([y, add]), self._ident(context))
-        if not (self.cache_static and self._static_key == skey):
+        # Cached across calls only when the inputs they derive from are unchanged, judged by CONTENT against private
+        # copies (a fresh tensor per step with the same values, as the sampler's per-step torch.cat produces, hits;
+        # a different clip that the caching allocator happens to place at the same address misses). One tiny D2H
+        # read per step, next to the one torch.unique below already needs.
+        srcs = [y, add] + list(context)
+        if not (self.cache_static and self._static_hit(srcs)):
             st = {}
             st["cnn"] = [self._cnn_fuser(y[b, :C], add[b]) for b in range(B)]
             st["ctx"] = self._context(context)
             st["kv"] = self._cross_kv(st["ctx"])
-            self._static, self._static_key = st, skey
+            self._static = st
+            self._static_key = [u.clone() for u in srcs] if self.cache_static else None
         st = self._static
 
         # ---- patch + ref embedding straight into the fp32 residual stream (:885-899) --------------------------
@@ -568,8 +576,9 @@ def native_forward(self, x, t, context, seq_len, clip_fea=None, y=None, y_camera
         x, t, context, y, full_ref, additional_control, density = (
             x[h:], t[h:], context[h:], y[h:], full_ref[h:], additional_control[h:], density[h:])
     eng = self.engine() if hasattr(self, "engine") else self._flexam_engine
-    out = eng.forward(x, t, context, seq_len, y, full_ref, additional_control, density,
-                      teacache=getattr(self, "teacache", None), cond_flag=cond_flag)
+    with ops.stream_scope():
+        out = eng.forward(x, t, context, seq_len, y, full_ref, additional_control, density,
+                          teacache=getattr(self, "teacache", None), cond_flag=cond_flag)
     if skip:
         out = torch.cat([out, out], dim=0)
     return out
@@ -577,8 +586,17 @@ def native_forward(self, x, t, context, seq_len, clip_fea=None, y=None, y_camera
 
 def install(module: nn.Module) -> nn.Module:
     """Rebind ``module.forward`` (a reference ``Wan2_2Transformer3DModel_FlexAM`` instance, bf16, on a B200) to the
-    native path — the same method-rebinding plug-in pattern the reference uses for USP (:807-815)."""
+    native path — the same method-rebinding plug-in pattern the reference uses for USP (:807-815).
+    ``FLEXAM_BACKEND=reference`` turns the call into a no-op (the module keeps its torch forward); anything other than
+    ``native`` / ``reference`` raises. There is no silent fallback: with ``native`` a missing library or a CPU module
+    raises."""
+    import os
     import types
+    backend = os.environ.get("FLEXAM_BACKEND", "native")
+    if backend == "reference":   # SURVEY §8b env switch: leave the module's own torch forward in place
+        return module
+    if backend != "native":
+        raise FlexamNativeError(f"FLEXAM_BACKEND must be 'native' or 'reference', got {backend!r}")
     params = {k: v.detach() for k, v in module.named_parameters()}
     cfg = dict(module.config)
     cfg.setdefault("in_dim_ref_conv", params["ref_conv.weight"].shape[1])
