@@ -268,6 +268,27 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m,
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 eviction-priority policies for TMA loads: 1 = evict_first (streamed once), 2 = evict_last (keep: re-read by later
+// tiles), anything else = evict_normal.
+__device__ __forceinline__ uint64_t l2_policy(int kind) {
+  uint64_t pol;
+  if (kind == 1) {
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  } else if (kind == 2) {
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  } else {
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  }
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_2sm_hint(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                     int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_slot) {  // same warp id in both CTAs of the pair
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
