@@ -233,7 +233,8 @@ def run_native(args):
 
     if args.quick:   # profiling runs (ncu) only need the resident region
         if rank == 0:
-            print(json.dumps({"quick": True, "ms_per_step": ms_value, "gpu_launches": launches,
+            print(json.dumps({"quick": True, "workload": WORKLOAD, "n_gpus": world, "ms_per_step": ms_value,
+                              "step_tflops": step_flops(cfg) / 1e12, "gpu_launches": launches,
                               "host_enqueue_ms_per_step": host_enqueue_ms}))
         if clocks:
             clocks.stop()
@@ -388,7 +389,14 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="resident region only (for ncu runs)")
+    ap.add_argument("--workload", default="config2", choices=["config2", "long"],
+                    help="config2 = the metric's workload (default); long = BASELINE config 5, 193 frames 704x1280 "
+                         "(43,120 tokens + 880 ref): a parity/stress case, not the bench line")
     a = ap.parse_args()
+    if a.workload == "long":
+        GRID = (49, 44, 80)
+        WORKLOAD = ("FlexAM Wan2.2-5B one denoising step, 193 frames 704x1280 (43,120 tokens + 880 ref), bf16, "
+                    "CFG batch 2 (long-clip stress case, BASELINE config 5)")
     if a.impl == "reference":
         run_reference(a)
     else:
