@@ -258,12 +258,33 @@ class NativeEngine:
             out.append(kv)
         return out
 
+    @staticmethod
+    def _ident(ts) -> tuple:
+        return tuple((t.data_ptr(), t._version, tuple(t.shape), t.stride(), t.dtype) for t in ts)
+
+    @staticmethod
+    def _same_content(a_list, b_list) -> bool:
+        return bool(torch.stack([(a == b).all() for a, b in zip(a_list, b_list)]).all().item())   # one D2H read
+
     def _static_hit(self, srcs) -> bool:
-        """True when every step-invariant input equals the copy the cached results were computed from."""
-        old = self._static_key
-        if old is None or len(old) != len(srcs) or any(a.shape != b.shape for a, b in zip(old, srcs)):
+        """True when every step-invariant input is unchanged since the cached results were computed.
+
+        Fast path, no device work: the very same storage at the same version. This is sound only because the engine
+        keeps a reference to the tensors it saw (``refs``), so the caching allocator cannot hand their addresses to
+        other data in the meantime. Otherwise the contents are compared on the device against private copies (one
+        small D2H read): a fresh tensor with the same values - the sampler's per-step ``torch.cat`` - still hits."""
+        key = self._static_key
+        if key is None:
             return False
-        return bool(torch.stack([(a == b).all() for a, b in zip(old, srcs)]).all().item())
+        ident, refs, copies = key
+        if ident == self._ident(srcs):
+            return True
+        if len(copies) != len(srcs) or any(a.shape != b.shape for a, b in zip(copies, srcs)):
+            return False
+        if not self._same_content(copies, srcs):
+            return False
+        self._static_key = (self._ident(srcs), list(srcs), copies)    # same values at a new address: follow them
+        return True
 
     # -- the denoising step ----------------------------------------------------------------------------------
     @torch.no_grad()
@@ -320,7 +341,8 @@ class NativeEngine:
             st["ctx"] = self._context(context)
             st["kv"] = self._cross_kv(st["ctx"])
             self._static = st
-            self._static_key = [u.clone() for u in srcs] if self.cache_static else None
+            self._static_key = ((self._ident(srcs), list(srcs), [u.clone() for u in srcs])
+                                if self.cache_static else None)
         st = self._static
 
         # ---- patch + ref embedding straight into the fp32 residual stream (:885-899) --------------------------

@@ -178,3 +178,29 @@ def test_static_cache_is_keyed_by_content(monkeypatch):
     fresh, _ = build(cfg)
     want_b, _, _ = call(fresh, b)
     assert torch.equal(out_b, want_b) and not torch.equal(out_a, out_b)
+
+
+def test_static_cache_identity_fast_path(monkeypatch):
+    """Passing the very same tensors again must hit the cache without comparing contents (no device read-back); an
+    in-place edit of one of them bumps its version and must miss."""
+    cpu_ops_emul.install(monkeypatch)
+    cfg = synth.CONFIGS["tiny"]
+    m, _ = build(cfg)
+    inp = synth.inputs(cfg, 2, 4, 8, per_token_t=True)
+    kw = dict(x=torch.from_numpy(inp["x"]).bfloat16(), t=torch.from_numpy(inp["t"]),
+              context=[torch.from_numpy(c).bfloat16() for c in inp["context"]], seq_len=inp["seq_len"],
+              y=torch.from_numpy(inp["y"]).bfloat16(), full_ref=torch.from_numpy(inp["full_ref"]).bfloat16(),
+              additional_control=torch.from_numpy(inp["additional_control"]).bfloat16(),
+              density=torch.from_numpy(inp["density"]))
+    eng = m.engine()
+    fuser_calls, compares = [], []
+    real_fuser, real_same = eng._cnn_fuser, eng._same_content
+    monkeypatch.setattr(eng, "_cnn_fuser", lambda *a, **k: (fuser_calls.append(1), real_fuser(*a, **k))[1])
+    out1 = m(**kw)
+    n = len(fuser_calls)
+    monkeypatch.setattr(eng, "_same_content", lambda *a, **k: (compares.append(1), real_same(*a, **k))[1])
+    out2 = m(**kw)
+    assert len(fuser_calls) == n and not compares and torch.equal(out1, out2)
+    kw["additional_control"].mul_(0.5)                       # in place: same address, new version
+    out3 = m(**kw)
+    assert len(fuser_calls) == 2 * n and not torch.equal(out1, out3)
