@@ -60,7 +60,7 @@ def bench_fmha():
 
 
 def bench_gemm():
-    M = 2 * 11648
+    M = int(os.environ.get("FX_BENCH_M", 2 * 11648))   # 2912 = rows per rank at 8 GPUs (cfg2 x sp4)
     g = torch.Generator(device=dev).manual_seed(0)
     for name, N, K, epi in (("qkv", 9216, 3072, 0), ("o_resid", 3072, 3072, 3), ("cq", 3072, 3072, 0),
                             ("ffn1_gelu", 14336, 3072, 1), ("ffn2_resid", 3072, 14336, 3)):
@@ -76,7 +76,7 @@ def bench_gemm():
         else:
             fn = lambda: ops.gemm(a, w, b, out, epi)  # noqa: E731
         ms = timeit(fn)
-        print(json.dumps({"case": "gemm_" + name, "mode": os.environ.get("FX_GEMM_MODE", "default"), "ms": ms,
+        print(json.dumps({"case": "gemm_" + name, "M": M, "mode": os.environ.get("FX_GEMM_MODE", "default"), "ms": ms,
                           "tflops": 2.0 * M * N * K / ms / 1e9}))
 
 
