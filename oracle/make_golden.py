@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE — generates tests/golden/*.npz by running the REAL reference module (build container only).
 
     python oracle/make_golden.py            # writes tests/golden/{tiny_tok,tiny_sample,real2_tok,tiny_loop}.npz
+    python oracle/make_golden.py real_tok   # the full-depth fixture (minutes, ~45 GB RAM)
 
 Each fixture stores the reference's fp32 CPU output for ``oracle.synth`` weights/inputs (which are regenerated
 from names, so they are not stored), plus a few small intermediate slices used to localise a mismatch.
@@ -25,7 +26,11 @@ CASES = {
     "tiny_tok": ("tiny", (3, 8, 12), True),
     "tiny_sample": ("tiny", (3, 8, 12), False),
     "real2_tok": ("real2", (5, 16, 28), True),   # BASELINE config-1 grid (560 + 112 tokens), 2 of 30 layers
+    # BASELINE config 1 itself: the full 30-layer, 5.0 B-parameter model at 17 frames 256x448 (fp32 on CPU: ~6 min of
+    # weight hashing + 20 s forward, ~45 GB of RAM). Not part of the default list: `make_golden.py real_tok`.
+    "real_tok": ("real", (5, 16, 28), True),
 }
+DEFAULT = ("tiny_tok", "tiny_sample", "real2_tok", "tiny_loop")
 
 
 def run_case(name: str):
@@ -129,5 +134,5 @@ def run_loop(name: str = "tiny_loop"):
 
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
-    for n in (sys.argv[1:] or list(CASES) + ["tiny_loop"]):
+    for n in (sys.argv[1:] or DEFAULT):
         run_loop(n) if n == "tiny_loop" else run_case(n)

@@ -108,6 +108,44 @@ def state_dict(cfg: dict, tag: str = "w"):
     return {name: tensor(f"{tag}/{name}", shape, std, mean) for name, shape, std, mean in param_specs(cfg)}
 
 
+def tensor_torch(name: str, shape, std: float = 1.0, mean: float = 0.0, device="cpu", dtype=None,
+                 chunk: int = 1 << 24):
+    """``tensor()`` evaluated with torch on ``device``: bit-identical values (tests/test_oracle.py), so that the 5 B
+    parameters of the full-depth model can be generated on the GPU in seconds instead of minutes of numpy hashing.
+    uint64 arithmetic is done in int64 (two's-complement wrap-around is the same ring; logical right shifts are
+    arithmetic shifts with the sign extension masked off). Returns fp32 (bf16-representable) or ``dtype``."""
+    import torch
+
+    def i64(c: int) -> int:          # a 64-bit constant as the int64 with the same bit pattern
+        c &= 0xFFFFFFFFFFFFFFFF
+        return c - (1 << 64) if c >= (1 << 63) else c
+
+    def lsr(x, k: int):
+        return (x >> k) & ((1 << (64 - k)) - 1)
+
+    n = int(np.prod(shape))
+    seed = i64(zlib.crc32(name.encode("utf-8")) * 0x100000001B3)
+    scale = float(np.float32(2.0 * np.sqrt(3.0) * std))
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        x = torch.arange(s, e, dtype=torch.int64, device=device) + seed
+        x = x + i64(0x9E3779B97F4A7C15)
+        x = (x ^ lsr(x, 30)) * i64(0xBF58476D1CE4E5B9)
+        x = (x ^ lsr(x, 27)) * i64(0x94D049BB133111EB)
+        x = x ^ lsr(x, 31)
+        u = lsr(x, 40).to(torch.float32) * float(np.float32(1.0 / (1 << 24)))
+        out[s:e] = (u - 0.5) * scale + float(np.float32(mean))
+    out = out.reshape(tuple(shape)).to(torch.bfloat16)       # round to nearest even, like to_bf16_f32
+    return out.to(dtype if dtype is not None else torch.float32)
+
+
+def state_dict_torch(cfg: dict, device, dtype=None, tag: str = "w"):
+    """``state_dict()`` generated on ``device`` (see tensor_torch)."""
+    return {name: tensor_torch(f"{tag}/{name}", shape, std, mean, device=device, dtype=dtype)
+            for name, shape, std, mean in param_specs(cfg)}
+
+
 def inputs(cfg: dict, F: int, H: int, W: int, B: int = 2, per_token_t: bool = True, tag: str = "in",
            prompt_lens=(37, 120), t_value: float = 875.0, density: float = 0.1):
     """Synthetic forward() arguments on the latent grid (F, H, W)."""

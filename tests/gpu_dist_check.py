@@ -43,8 +43,7 @@ def build(cfg, dev):
         num_heads=cfg["num_heads"], num_layers=cfg["num_layers"], eps=cfg["eps"], add_ref_conv=True,
         in_dim_ref_conv=cfg["out_dim"], add_cnn_block=True, in_dim_cnn_block=cfg["in_dim_cnn"],
         out_dim_cnn_block=cfg["out_dim_cnn"], device=dev)
-    sd = {k: torch.from_numpy(v).to(dev, torch.bfloat16) for k, v in synth.state_dict(cfg).items()}
-    m.load_state_dict(sd, strict=True)
+    m.load_state_dict(synth.state_dict_torch(cfg, dev, torch.bfloat16), strict=True)   # bit-identical to state_dict()
     return m
 
 

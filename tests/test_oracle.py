@@ -110,3 +110,16 @@ def test_euler_schedule_restatements_agree():
         assert s1[0] == 1.0 and s1[-1] == 0.0 and len(s1) == n + 1 and np.all(np.diff(s1) < 0)
     smin = 5.0 * 1e-3 / (1 + 4.0 * 1e-3)                    # the constructor's shifted sigma_min
     np.testing.assert_allclose(s1[-2], 5.0 * smin / (1 + 4.0 * smin), rtol=1e-5)
+
+
+def test_torch_generator_is_bit_identical_to_numpy():
+    """synth.tensor_torch (used to build the 5 B-parameter model on the GPU) == synth.tensor, bit for bit, including
+    across the 16 Mi-element chunk boundary and for non-zero means."""
+    for name, shape, std, mean in (("w/blocks.3.ffn.0.weight", (1000, 777), 0.018, 0.0), ("in/x", (3, 5, 7), 1.0, 0.0),
+                                   ("w/blocks.0.norm3.weight", (3072,), 0.1, 1.0), ("w/big", (4200, 4099), 0.3, 0.0)):
+        a = synth.tensor(name, shape, std, mean)
+        b = synth.tensor_torch(name, shape, std, mean).numpy()
+        assert a.dtype == b.dtype and np.array_equal(a, b), name
+    cfg = synth.CONFIGS["tiny"]
+    sd_np, sd_t = synth.state_dict(cfg), synth.state_dict_torch(cfg, "cpu")
+    assert sd_np.keys() == sd_t.keys() and all(np.array_equal(sd_np[k], sd_t[k].numpy()) for k in sd_np)
