@@ -1,5 +1,6 @@
 // Library-level C-ABI entry points and the host helpers the kernel translation units share.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "host_common.h"
@@ -13,6 +14,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* env = getenv("FX_PDL");
+    v = (env && env[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 int num_sms() {

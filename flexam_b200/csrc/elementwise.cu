@@ -58,6 +58,8 @@ __device__ __forceinline__ float row_reduce(float v, float* red, int row_in_bloc
 
 template <int NV, int WPR, int MODE>  // NV = float4 vectors per lane = D / (128 * WPR)
 __global__ void __launch_bounds__(256) ln_kernel(const LnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_in_block = warp / WPR, warp_in_row = warp % WPR;
@@ -160,7 +162,7 @@ static int launch_ln(const LnParams& p, cudaStream_t s, const char* name) {
   const int grid = (p.M + rows_per_block - 1) / rows_per_block;
 #define FX_LN_CASE(NVV, WPRV)                                   \
   if (nv == NVV && wpr == WPRV) {                               \
-    ln_kernel<NVV, WPRV, MODE><<<grid, 256, 0, s>>>(p);         \
+    launch_kernel(ln_kernel<NVV, WPRV, MODE>, dim3(grid), dim3(256), 0, s, p); \
     FX_CHECK_LAUNCH(name);                                      \
     return FX_OK;                                               \
   }
@@ -196,6 +198,8 @@ struct RmsParams {
 
 template <int NV, int WPR>  // NV = 16-byte vectors (8 bf16) per lane = D / (256 * WPR)
 __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const __grid_constant__ RmsParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_in_block = warp / WPR, warp_in_row = warp % WPR;
@@ -406,7 +410,7 @@ static int launch_rmsnorm_rope(const RmsParams& p, cudaStream_t s, const char* n
   const int grid = static_cast<int>((vrows + (8 / wpr) - 1) / (8 / wpr));
 #define FX_RMS_CASE(NVV, WPRV)                                   \
   if (nv == NVV && wpr == WPRV) {                                \
-    rmsnorm_rope_kernel<NVV, WPRV><<<grid, 256, 0, s>>>(p);      \
+    launch_kernel(rmsnorm_rope_kernel<NVV, WPRV>, dim3(grid), dim3(256), 0, s, p); \
     FX_CHECK_LAUNCH(name);                                       \
     return FX_OK;                                                \
   }

@@ -129,6 +129,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();  // global memory (TMA loads, output stores) is touched only below
 
   // Register re-partitioning: the data-movement warpgroup (warps 16-19) gives its registers to the four softmax
   // warpgroups (the pool is what the launch allocated, 640 x 96: 512 x 104 + 128 x 56 <= 61440).
@@ -465,6 +467,8 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();  // global memory (TMA loads, output stores) is touched only below
   constexpr uint32_t kColP = 128, kColO = 256;
 
   if (warp >= 16) {
@@ -918,7 +922,7 @@ static int fmha_launch(const void* q, int64_t q_stride_b, int64_t q_stride_l, co
     p.o = p.o_peer[0];
   }
   dim3 grid((Lq + 255) / 256, H, B);
-  kern<<<grid, kFmhaThreads, kFmhaSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  launch_kernel(kern, grid, dim3(kFmhaThreads), kFmhaSmem, reinterpret_cast<cudaStream_t>(stream), tq, tk, tv, p);
   FX_CHECK_LAUNCH(name);
   return FX_OK;
 }

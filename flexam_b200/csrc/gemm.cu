@@ -203,6 +203,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp polls, one elected lane issues) =====================
@@ -394,6 +396,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   cluster_sync_all();  // peer barriers initialised and TMEM allocated before any cross-CTA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -541,7 +545,7 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int pairs = num_sms() / 2;
   const int grid = 2 * (total < pairs ? total : pairs);
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tout, p);
+  launch_kernel(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, tout, p);
   FX_CHECK_LAUNCH("fx_gemm_bf16(2cta)");
   return FX_OK;
 }
@@ -604,7 +608,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   }
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tout, p);
+  launch_kernel(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, tout, p);
   FX_CHECK_LAUNCH("fx_gemm_bf16");
   return FX_OK;
 }

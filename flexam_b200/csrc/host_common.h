@@ -21,6 +21,34 @@ bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t
 bool make_tmap(CUtensorMap* out, bool is_f32, const void* base, int rank, const uint64_t* dims,
                const uint64_t* strides_bytes, const uint32_t* box);
 
+// Programmatic dependent launch (FX_PDL=1, default off): the grid may be scheduled while its predecessor in the stream
+// is still draining, so its prologue (barrier init, TMEM allocation, descriptor prefetch) and the launch latency overlap
+// the predecessor's tail. Every kernel launched through launch_kernel() executes griddepcontrol.wait before its first
+// global-memory access, which restores stream order for the data.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                          Args&&... args) {
+#ifdef __CUDACC__
+  if (!pdl_enabled()) {
+    kern<<<grid, block, smem, stream>>>(static_cast<KArgs>(args)...);
+    return;
+  }
+#endif
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr = {};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 #define FX_CHECK_ARG(cond, ...)   \
   do {                            \
     if (!(cond)) {                \

@@ -81,6 +81,12 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// Programmatic dependent launch (see host_common.h launch_kernel): no-ops for grids launched without the attribute.
+// pdl_launch_dependents(): the next grid in the stream may be scheduled once every CTA of this one has got here;
+// pdl_wait(): returns when the preceding grid has completed and its memory operations are visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // TMA loads (tile mode). Coordinates are innermost-first.
 // ----------------------------------------------------------------------------------------------

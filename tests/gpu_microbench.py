@@ -105,6 +105,51 @@ def bench_rows():
     print(json.dumps({"case": "rmsnorm_cq", "ms": ms, "gbs": M * D * 4 / ms / 1e6}))
 
 
+def bench_chain():
+    """One rank's share of a transformer block at 8 GPUs (cfg2 x sp4: 2912 tokens, 6 heads over all 11,648 keys),
+    repeated 30 times back to back: what FX_PDL (programmatic dependent launch) is meant to speed up."""
+    M, D, Fd, H, L = int(os.environ.get("FX_BENCH_M", 2912)), 3072, 14336, 6, 11648
+    g = torch.Generator(device=dev).manual_seed(0)
+    rnd = lambda *sh: torch.randn(*sh, device=dev, generator=g)  # noqa: E731
+    x = rnd(M, D)
+    h = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    gam = torch.ones(D, device=dev, dtype=torch.bfloat16)
+    wqkv, bqkv = (rnd(3 * D, D) * D ** -0.5).bfloat16(), rnd(3 * D).bfloat16()
+    wo, bo = (rnd(D, D) * D ** -0.5).bfloat16(), rnd(D).bfloat16()
+    w1, b1 = (rnd(Fd, D) * D ** -0.5).bfloat16(), rnd(Fd).bfloat16()
+    w2, b2 = (rnd(D, Fd) * Fd ** -0.5).bfloat16(), rnd(D).bfloat16()
+    qkv = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
+    ffn = torch.empty(M, Fd, device=dev, dtype=torch.bfloat16)
+    cq = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    aqkv = rnd(L, 3 * H * 128).bfloat16().view(1, L, 3, H, 128)       # the rank's heads over the whole sequence
+    aout = torch.empty(1, L, H, 128, device=dev, dtype=torch.bfloat16)
+    ckv = rnd(512, 2 * 24 * 128).bfloat16().view(1, 512, 2, 24, 128)
+    cout = torch.empty(1, M, 24, 128, device=dev, dtype=torch.bfloat16)
+
+    def block():
+        ops.ln_affine(x, h, 1e-6, gam, gam)
+        ops.gemm(h, wqkv, bqkv, qkv, 0)
+        ops.rmsnorm_rope(qkv[:, :2 * D], gam, 1e-6, weight2=gam)
+        ops.fmha(aqkv[:, :, 0], aqkv[:, :, 1], aqkv[:, :, 2], aout, 128 ** -0.5)
+        ops.gemm(h, wo, bo, x, 3)
+        ops.ln_affine(x, h, 1e-6, gam, gam)
+        ops.gemm(h, wo, bo, cq, 0)
+        ops.rmsnorm_rope(cq, gam, 1e-6)
+        ops.fmha(cq.view(1, M, 24, 128), ckv[:, :, 0], ckv[:, :, 1], cout, 128 ** -0.5)
+        ops.gemm(cout.view(M, D), wo, bo, x, 3)
+        ops.ln_affine(x, h, 1e-6, gam, gam)
+        ops.gemm(h, w1, b1, ffn, 1)
+        ops.gemm(ffn, w2, b2, x, 3)
+
+    def step():
+        for _ in range(30):
+            block()
+
+    ms = timeit(step, reps=5, warm=2, flush=False)
+    print(json.dumps({"case": "block_chain_x30", "M": M, "pdl": os.environ.get("FX_PDL", "0"), "ms": ms,
+                      "launches": 13 * 30, "checksum": int(x.view(torch.int32).to(torch.int64).sum().item())}))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["fmha", "gemm", "rows"]
     if "fmha" in which:
@@ -113,3 +158,5 @@ if __name__ == "__main__":
         bench_gemm()
     if "rows" in which:
         bench_rows()
+    if "chain" in which:
+        bench_chain()
