@@ -30,7 +30,7 @@ CASES = {
     # weight hashing + 20 s forward, ~45 GB of RAM). Not part of the default list: `make_golden.py real_tok`.
     "real_tok": ("real", (5, 16, 28), True),
 }
-DEFAULT = ("tiny_tok", "tiny_sample", "real2_tok", "tiny_loop")
+DEFAULT = ("tiny_tok", "tiny_sample", "real2_tok", "tiny_loop", "rope_tables")
 
 
 def run_case(name: str):
@@ -132,7 +132,25 @@ def run_loop(name: str = "tiny_loop"):
                         step0=trace[0].numpy().astype(np.float32))
 
 
+def run_rope(name: str = "rope_tables"):
+    """RoPE tables of the REAL reference module, default and after enable_riflex() with its default arguments
+    (:774-788): a few position rows of the complex128 / complex64 tables as float64 (cos, sin)."""
+    cfg = synth.CONFIGS["tiny"]
+    model = ref_import.build_reference_model(cfg)
+    rows = np.array([0, 1, 2, 7, 24, 65, 66, 511, 1023])
+    plain = torch.view_as_real(model.freqs.to(torch.complex128))[rows].numpy()
+    model.enable_riflex()                      # k = 6, L_test = 66, L_test_scale = 4.886
+    riflex = torch.view_as_real(model.freqs.to(torch.complex128))[rows].numpy()
+    model.enable_riflex(k=4, L_test=49, L_test_scale=None)
+    riflex2 = torch.view_as_real(model.freqs.to(torch.complex128))[rows].numpy()
+    assert not np.allclose(plain, riflex) and plain.shape == (len(rows), 64, 2)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), rows=rows, plain=plain, riflex=riflex,
+                        riflex_k4_L49=riflex2)
+    print(f"{name}: head_dim {model.d if hasattr(model, 'd') else 128}, {len(rows)} rows, "
+          f"max |plain - riflex| {np.abs(plain - riflex).max():.3f}")
+
+
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     for n in (sys.argv[1:] or DEFAULT):
-        run_loop(n) if n == "tiny_loop" else run_case(n)
+        run_loop(n) if n == "tiny_loop" else run_rope(n) if n == "rope_tables" else run_case(n)

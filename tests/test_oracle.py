@@ -123,3 +123,28 @@ def test_torch_generator_is_bit_identical_to_numpy():
     cfg = synth.CONFIGS["tiny"]
     sd_np, sd_t = synth.state_dict(cfg), synth.state_dict_torch(cfg, "cpu")
     assert sd_np.keys() == sd_t.keys() and all(np.array_equal(sd_np[k], sd_t[k].numpy()) for k in sd_np)
+
+
+def test_rope_tables_with_and_without_riflex_match_the_reference(golden_dir):
+    """rope_table() (what the RMSNorm+RoPE kernels read) against the REAL module's `freqs`, default and after
+    enable_riflex() (wan_transformer3d_FlexAM.py:56-113, :774-788): fixture rows from oracle/make_golden.py, and the
+    mirror class's enable_riflex/disable_riflex switch the engine's table accordingly."""
+    from flexam_b200.model import Wan2_2Transformer3DModel_FlexAM, rope_table
+    g = np.load(os.path.join(golden_dir, "rope_tables.npz"))
+    rows = torch.from_numpy(g["rows"])
+    cases = (("plain", None), ("riflex", dict(k=6, L_test=66, L_test_scale=4.886)),
+             ("riflex_k4_L49", dict(k=4, L_test=49, L_test_scale=None)))
+    for key, rf in cases:
+        got = rope_table(128, riflex=rf)[rows].double().numpy()
+        np.testing.assert_allclose(got, g[key], rtol=0, atol=6e-8, err_msg=key)      # fp32 rounding of cos / sin
+    cfg = synth.CONFIGS["tiny"]
+    m = Wan2_2Transformer3DModel_FlexAM(
+        model_type="ti2v", patch_size=cfg["patch_size"], text_len=cfg["text_len"], in_dim=cfg["in_dim"], dim=cfg["dim"],
+        ffn_dim=cfg["ffn_dim"], freq_dim=cfg["freq_dim"], text_dim=cfg["text_dim"], out_dim=cfg["out_dim"],
+        num_heads=cfg["num_heads"], num_layers=cfg["num_layers"], eps=cfg["eps"], add_ref_conv=True,
+        in_dim_ref_conv=cfg["out_dim"], add_cnn_block=True, in_dim_cnn_block=cfg["in_dim_cnn"],
+        out_dim_cnn_block=cfg["out_dim_cnn"], device="cpu")
+    m.enable_riflex()
+    np.testing.assert_allclose(m.engine().freqs[rows].double().numpy(), g["riflex"], rtol=0, atol=6e-8)
+    m.disable_riflex()
+    np.testing.assert_allclose(m.engine().freqs[rows].double().numpy(), g["plain"], rtol=0, atol=6e-8)
