@@ -598,12 +598,30 @@ def native_forward(self, x, t, context, seq_len, clip_fea=None, y=None, y_camera
         x, t, context, y, full_ref, additional_control, density = (
             x[h:], t[h:], context[h:], y[h:], full_ref[h:], additional_control[h:], density[h:])
     eng = self.engine() if hasattr(self, "engine") else self._flexam_engine
+    if not hasattr(self, "engine"):
+        _sync_rope_table(self, eng)      # an installed reference module: follow ITS freqs (enable_riflex() etc.)
     with ops.stream_scope():
         out = eng.forward(x, t, context, seq_len, y, full_ref, additional_control, density,
                           teacache=getattr(self, "teacache", None), cond_flag=cond_flag)
     if skip:
         out = torch.cat([out, out], dim=0)
     return out
+
+
+def _sync_rope_table(module: nn.Module, eng: NativeEngine) -> None:
+    """Keep the engine's (cos, sin) table equal to the reference module's complex ``freqs`` buffer (:655-665), which
+    its own ``enable_riflex`` / ``disable_riflex`` (:774-799) replace at any time. Converted once per distinct buffer."""
+    fr = getattr(module, "freqs", None)
+    if not torch.is_tensor(fr) or not fr.is_complex():
+        return
+    key = (fr.data_ptr(), fr._version, tuple(fr.shape))
+    if getattr(eng, "_freqs_key", None) == key:
+        return
+    if fr.dim() != 2 or tuple(fr.shape) != tuple(eng.freqs.shape[:2]):
+        raise FlexamNativeError(f"module.freqs has shape {tuple(fr.shape)}, expected {tuple(eng.freqs.shape[:2])}")
+    eng.freqs = torch.view_as_real(fr.detach().to("cpu", torch.complex128)).to(f32).contiguous().to(eng.device)
+    eng._freqs_key = key
+    eng._freqs_ref = fr          # keeps the storage alive so the key cannot be recycled
 
 
 def install(module: nn.Module) -> nn.Module:

@@ -148,3 +148,39 @@ def test_rope_tables_with_and_without_riflex_match_the_reference(golden_dir):
     np.testing.assert_allclose(m.engine().freqs[rows].double().numpy(), g["riflex"], rtol=0, atol=6e-8)
     m.disable_riflex()
     np.testing.assert_allclose(m.engine().freqs[rows].double().numpy(), g["plain"], rtol=0, atol=6e-8)
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="reference tree not mounted")
+def test_installed_module_follows_the_reference_riflex_switch(monkeypatch):
+    """install() on a REAL reference module: calling the reference's own enable_riflex()/disable_riflex() afterwards
+    (they replace module.freqs) must change the table the native kernels read, and the native result must track the
+    reference's torch forward in both states."""
+    import cpu_ops_emul
+    import flexam_b200.model as fx
+    cpu_ops_emul.install(monkeypatch)
+    cfg = synth.CONFIGS["tiny"]
+    ref = ref_import.build_reference_model(cfg).eval()
+    sd = O.to_torch_sd(synth.state_dict(cfg))
+    ref.load_state_dict(sd, strict=True)
+    inp = synth.inputs(cfg, 3, 4, 8, per_token_t=True, tag="riflex")
+    kw = dict(x=torch.from_numpy(inp["x"]), t=torch.from_numpy(inp["t"]),
+              context=[torch.from_numpy(c) for c in inp["context"]], seq_len=inp["seq_len"],
+              y=torch.from_numpy(inp["y"]), full_ref=torch.from_numpy(inp["full_ref"]),
+              additional_control=torch.from_numpy(inp["additional_control"]), density=torch.from_numpy(inp["density"]))
+    torch_forward = type(ref).forward
+    outs = {}
+    with torch.no_grad():
+        for state in ("plain", "riflex"):
+            if state == "riflex":
+                ref.enable_riflex()
+            outs[state] = torch_forward(ref, **kw)
+        ref.disable_riflex()
+    assert _rel(outs["riflex"], outs["plain"]) > 1e-3          # the switch matters for these inputs
+    native = fx.install(ref.bfloat16())
+    for state in ("plain", "riflex"):
+        if state == "riflex":
+            native.enable_riflex()                              # the REFERENCE's method: replaces module.freqs
+        got = native(**{k: ([c.bfloat16() for c in v] if k == "context" else
+                            v.bfloat16() if torch.is_tensor(v) and v.dtype == torch.float32 and k not in ("t", "density")
+                            else v) for k, v in kw.items()})
+        assert _rel(got, outs[state]) < 1e-2, state
