@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import teacache as _tc
 from .lib import FX_EPI_BF16, FX_EPI_F32, FX_EPI_GELU_BF16, FX_EPI_RESID_F32, FlexamNativeError
 
 bf16, f32, i32 = torch.bfloat16, torch.float32, torch.int32
@@ -406,7 +407,10 @@ class NativeEngine:
         run_blocks = True
         ori = None
         if teacache is not None:
-            run_blocks = teacache.decide(e0v[last_idx], cond_flag)
+            # this package's TeaCache has decide()/step_done(); the reference's own class (an installed module whose
+            # pipeline called the reference's enable_teacache) has the same state and is driven through the functions
+            run_blocks = (teacache.decide(e0v[last_idx], cond_flag) if hasattr(teacache, "decide")
+                          else _tc.decide(teacache, e0v[last_idx], cond_flag))
             if not run_blocks:
                 prev = teacache.previous_residual_cond if cond_flag else teacache.previous_residual_uncond
                 ops.add_(xs, prev[-M:].contiguous())
@@ -465,7 +469,7 @@ class NativeEngine:
         if cfg_split:
             out = par.gather_cfg(out)
         if teacache is not None:
-            teacache.step_done(cond_flag)
+            teacache.step_done(cond_flag) if hasattr(teacache, "step_done") else _tc.step_done(teacache, cond_flag)
         return out
 
     def _swap01(self, src, out):

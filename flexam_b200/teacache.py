@@ -45,27 +45,39 @@ class TeaCache:
         self.previous_residual_cond = None
         self.previous_residual_uncond = None
 
-    # -- decision for one forward call (:978-1000) -----------------------------------------------------------
     def decide(self, modulated_inp: torch.Tensor, cond_flag: bool) -> bool:
-        if not cond_flag:
-            return self.should_calc
-        if self.cnt < self.num_skip_start_steps:
-            should = True
-            self.accumulated_rel_l1_distance = 0.0
-        else:
-            d = self.compute_rel_l1_distance(self.previous_modulated_input, modulated_inp)
-            self.accumulated_rel_l1_distance += self.rescale_func(d)
-            if self.accumulated_rel_l1_distance < self.rel_l1_thresh:
-                should = False
-            else:
-                should = True
-                self.accumulated_rel_l1_distance = 0.0
-        self.previous_modulated_input = modulated_inp.clone()
-        self.should_calc = should
-        return should
+        return decide(self, modulated_inp, cond_flag)
 
     def step_done(self, cond_flag: bool):
-        if cond_flag:                   # :1119-1122
-            self.cnt += 1
-            if self.cnt == self.num_steps:
-                self.reset()
+        step_done(self, cond_flag)
+
+
+# The control flow of the reference forward around its TeaCache object, written against the object's ATTRIBUTES so
+# that it drives this module's TeaCache and the reference's own class (FlexAM/models/cache_utils.py:21-76, which has the
+# same state and no decide()/step_done()) alike: an installed reference module whose pipeline called the reference's
+# enable_teacache() keeps working.
+def decide(tc, modulated_inp: torch.Tensor, cond_flag: bool) -> bool:
+    """Decision for one forward call (:978-1000)."""
+    if not cond_flag:
+        return tc.should_calc
+    if tc.cnt < tc.num_skip_start_steps:
+        should = True
+        tc.accumulated_rel_l1_distance = 0.0
+    else:
+        d = tc.compute_rel_l1_distance(tc.previous_modulated_input, modulated_inp)
+        tc.accumulated_rel_l1_distance += float(tc.rescale_func(d))
+        if tc.accumulated_rel_l1_distance < tc.rel_l1_thresh:
+            should = False
+        else:
+            should = True
+            tc.accumulated_rel_l1_distance = 0.0
+    tc.previous_modulated_input = modulated_inp.clone()
+    tc.should_calc = should
+    return should
+
+
+def step_done(tc, cond_flag: bool) -> None:
+    if cond_flag:                       # :1119-1122
+        tc.cnt += 1
+        if tc.cnt == tc.num_steps:
+            tc.reset()

@@ -184,3 +184,38 @@ def test_installed_module_follows_the_reference_riflex_switch(monkeypatch):
                             v.bfloat16() if torch.is_tensor(v) and v.dtype == torch.float32 and k not in ("t", "density")
                             else v) for k, v in kw.items()})
         assert _rel(got, outs[state]) < 1e-2, state
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="reference tree not mounted")
+def test_installed_reference_module_with_its_own_teacache_and_cfg_skip(monkeypatch, golden_dir):
+    """Drop-in check around the REAL module: install() rebinds its forward, the REFERENCE's enable_teacache() /
+    enable_cfg_skip() set up the reference's own TeaCache object and counters, and the 6-step sampling loop (kernels
+    emulated on the CPU) reproduces the fixture the unmodified module produced: same skip decisions, same latents."""
+    import cpu_ops_emul
+    import loop_case
+    import flexam_b200.model as fx
+    from flexam_b200.sampler import DenoiseLoop
+    cpu_ops_emul.install(monkeypatch)
+    g = loop_case.golden(golden_dir)
+    L = loop_case.LOOP
+    cfg = synth.CONFIGS[L["config"]]
+    ref = ref_import.build_reference_model(cfg).eval()
+    ref.load_state_dict(O.to_torch_sd(synth.state_dict(cfg)), strict=True)
+    native = fx.install(ref.bfloat16())
+    tc = L["teacache"]
+    native.enable_teacache(tc["coefficients"], L["steps"], tc["rel_l1_thresh"], tc["num_skip_start_steps"], offload=False)
+    native.enable_cfg_skip(L["cfg_skip_ratio"], L["steps"])
+    assert type(native.teacache).__module__.endswith("cache_utils")      # the reference's class, not this package's
+    decisions = []
+    real_decide = fx._tc.decide
+    monkeypatch.setattr(fx._tc, "decide", lambda t, m, c: (lambda r: (decisions.append(bool(r)) if c else None, r)[1])(
+        real_decide(t, m, c)))
+    from oracle import make_golden
+    lt = make_golden.loop_tensors(cfg, *L["grid"])
+    loop = DenoiseLoop(native, lt["latents"], lt["mask"], lt["masked_video_latents"], lt["mask_latents"],
+                       lt["control_video_latents"], lt["additional_control"], lt["ref_image_latents"],
+                       lt["negative_prompt_embeds"], lt["prompt_embeds"], density=L["density"],
+                       guidance_scale=L["guidance"])
+    out = loop.run(g["timesteps"], g["sigmas"])
+    assert decisions == [bool(d) for d in g["decisions"]]
+    assert _rel(out, torch.from_numpy(g["out"])) < 1e-2
