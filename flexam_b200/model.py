@@ -535,6 +535,66 @@ class Wan2_2Transformer3DModel_FlexAM(nn.Module):
         self._riflex = None
         self._engine: Optional[NativeEngine] = None
 
+    # -- loading (:1190-1332) ------------------------------------------------------------------------------------
+    @classmethod
+    def from_config(cls, config: dict, **kwargs):
+        """Constructor arguments from a diffusers-style config dict (unknown keys such as ``_class_name`` ignored), like
+        ``ConfigMixin.from_config`` as the reference uses it (:1227, :1289)."""
+        import inspect
+        accepted = set(inspect.signature(cls.__init__).parameters) - {"self"}
+        merged = {k: v for k, v in dict(config, **kwargs).items() if k in accepted}
+        return cls(**merged)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_path, subfolder=None, transformer_additional_kwargs={},
+                        low_cpu_mem_usage=False, torch_dtype=torch.bfloat16):
+        """Same contract as the reference (:1190-1332): ``config.json`` + ``diffusion_pytorch_model.{bin,safetensors}``
+        or ``*.safetensors`` shards under ``path[/subfolder]``; ``dict_mapping``; a checkpoint ``patch_embedding.weight``
+        with fewer / more input channels is copied into the leading channels and the rest zero-filled; tensors whose size
+        does not match are skipped; non-strict load; cast to ``torch_dtype``. ``low_cpu_mem_usage`` is accepted and gives
+        the same result (the reference's meta-device path is an optimisation of the same load)."""
+        import glob
+        import json
+        import os
+        if subfolder is not None:
+            pretrained_model_path = os.path.join(pretrained_model_path, subfolder)
+        config_file = os.path.join(pretrained_model_path, "config.json")
+        if not os.path.isfile(config_file):
+            raise RuntimeError(f"{config_file} does not exist")
+        with open(config_file, "r") as f:
+            config = json.load(f)
+        kwargs = dict(transformer_additional_kwargs)
+        for key, target in dict(kwargs.pop("dict_mapping", {})).items():
+            kwargs[target] = config[key]
+        model = cls.from_config(config, **kwargs)
+        model_file = os.path.join(pretrained_model_path, "diffusion_pytorch_model.bin")      # diffusers WEIGHTS_NAME
+        model_file_safetensors = model_file.replace(".bin", ".safetensors")
+        if os.path.exists(model_file):
+            state_dict = torch.load(model_file, map_location="cpu")
+        else:
+            from safetensors.torch import load_file
+            files = ([model_file_safetensors] if os.path.exists(model_file_safetensors)
+                     else sorted(glob.glob(os.path.join(pretrained_model_path, "*.safetensors"))))
+            state_dict = {}
+            for fn in files:
+                state_dict.update(load_file(fn))
+        own = model.state_dict()
+        pe = "patch_embedding.weight"
+        if pe in state_dict and own[pe].size() != state_dict[pe].size():
+            n_ckpt, n_own = state_dict[pe].size(1), own[pe].size(1)
+            w = torch.zeros_like(own[pe])
+            w[:, :min(n_ckpt, n_own)] = state_dict[pe][:, :min(n_ckpt, n_own)].to(w.dtype)
+            state_dict[pe] = w
+        kept = {}
+        for key, val in state_dict.items():
+            if key in own and own[key].size() == val.size():
+                kept[key] = val
+            else:
+                print(key, "Size don't match, skip")
+        missing, unexpected = model.load_state_dict(kept, strict=False)
+        print(f"### missing keys: {len(missing)}; \n### unexpected keys: {len(unexpected)};")
+        return model.to(torch_dtype)
+
     # -- feature toggles with the reference's names (:730-815) -----------------------------------------------
     def enable_cfg_skip(self, cfg_skip_ratio, num_steps):
         self.cfg_skip_ratio = cfg_skip_ratio if cfg_skip_ratio != 0 else None

@@ -204,3 +204,38 @@ def test_static_cache_identity_fast_path(monkeypatch):
     kw["additional_control"].mul_(0.5)                       # in place: same address, new version
     out3 = m(**kw)
     assert len(fuser_calls) == 2 * n and not torch.equal(out1, out3)
+
+
+def test_from_pretrained_follows_the_reference_contract(tmp_path):
+    """config.json + safetensors shards under path/subfolder, dict_mapping, patch-embedding channel padding, skipping of
+    mis-sized tensors, dtype cast and the missing-config error (reference :1190-1332)."""
+    import json
+    from safetensors.torch import save_file
+    cfg = synth.CONFIGS["tiny"]
+    sd = {k: torch.from_numpy(v) for k, v in synth.state_dict(cfg).items()}
+    root = tmp_path / "ckpt" / "transformer"
+    root.mkdir(parents=True)
+    conf = dict(_class_name="Wan2_2Transformer3DModel", _diffusers_version="0.33.0", model_type="ti2v",
+                patch_size=[1, 2, 2], text_len=cfg["text_len"], in_dim=cfg["in_dim"] - 4, dim=cfg["dim"],
+                ffn_dim=cfg["ffn_dim"], freq_dim=cfg["freq_dim"], text_dim=cfg["text_dim"], out_dim=cfg["out_dim"],
+                num_heads=cfg["num_heads"], num_layers=cfg["num_layers"], eps=cfg["eps"], base_channels=cfg["in_dim"])
+    (root / "config.json").write_text(json.dumps(conf))
+    ckpt = dict(sd)
+    ckpt["patch_embedding.weight"] = sd["patch_embedding.weight"][:, :cfg["in_dim"] - 4].contiguous()   # fewer channels
+    ckpt["head.modulation"] = torch.zeros(1, 3, cfg["dim"])                                              # wrong size
+    keys = sorted(ckpt)
+    save_file({k: ckpt[k].contiguous() for k in keys[::2]}, str(root / "model-00001-of-00002.safetensors"))
+    save_file({k: ckpt[k].contiguous() for k in keys[1::2]}, str(root / "model-00002-of-00002.safetensors"))
+    extra = dict(add_ref_conv=True, in_dim_ref_conv=cfg["out_dim"], add_cnn_block=True, in_dim_cnn_block=cfg["in_dim_cnn"],
+                 out_dim_cnn_block=cfg["out_dim_cnn"], dict_mapping={"base_channels": "in_dim"})
+    m = Wan2_2Transformer3DModel_FlexAM.from_pretrained(str(tmp_path / "ckpt"), subfolder="transformer",
+                                                        transformer_additional_kwargs=extra, torch_dtype=torch.bfloat16)
+    got = m.state_dict()
+    assert m.config.in_dim == cfg["in_dim"] and all(v.dtype == torch.bfloat16 for v in got.values())
+    assert torch.equal(got["patch_embedding.weight"][:, :cfg["in_dim"] - 4], ckpt["patch_embedding.weight"].bfloat16())
+    assert got["patch_embedding.weight"][:, cfg["in_dim"] - 4:].abs().max().item() == 0
+    for k in ("blocks.1.ffn.2.weight", "cnn_conv3.0.bias", "time_projection.1.weight"):
+        assert torch.equal(got[k], sd[k].bfloat16()), k
+    assert "dict_mapping" in extra                                       # the caller's dict is not consumed
+    with pytest.raises(RuntimeError, match="config.json does not exist"):
+        Wan2_2Transformer3DModel_FlexAM.from_pretrained(str(tmp_path / "ckpt"), subfolder="nope")
