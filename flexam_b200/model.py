@@ -73,7 +73,12 @@ def param_shapes(cfg: dict) -> Dict[str, tuple]:
 
 
 def rope_table(head_dim: int, theta: float = 10000.0, max_len: int = 1024, riflex: Optional[dict] = None) -> torch.Tensor:
-    """fp32 [max_len, head_dim/2, 2] (cos, sin), from the float64 construction of rope_params (:44-52, :655-665);
+    """fp32 [max_len, head_dim/2, 2] (cos, sin) table the RMSNorm+RoPE kernels read (rope_table_f64 rounded once)."""
+    return rope_table_f64(head_dim, theta, max_len, riflex).to(f32).contiguous()
+
+
+def rope_table_f64(head_dim: int, theta: float = 10000.0, max_len: int = 1024, riflex: Optional[dict] = None) -> torch.Tensor:
+    """float64 [max_len, head_dim/2, 2] (cos, sin), the construction of rope_params (:44-52, :655-665);
     RIFLEx (:56-113, :774-788) changes one temporal frequency."""
     d = head_dim
     cols = []
@@ -86,7 +91,13 @@ def rope_table(head_dim: int, theta: float = 10000.0, max_len: int = 1024, rifle
                 inv[k - 1] = inv[k - 1] / riflex["L_test_scale"]
         cols.append(torch.outer(torch.arange(max_len, dtype=torch.float64), inv))
     ang = torch.cat(cols, dim=1)
-    return torch.stack([ang.cos(), ang.sin()], dim=-1).to(f32).contiguous()
+    return torch.stack([ang.cos(), ang.sin()], dim=-1)
+
+
+def rope_complex(head_dim: int, riflex: Optional[dict] = None) -> torch.Tensor:
+    """The reference's ``freqs`` attribute: complex128 [1024, head_dim/2] (:655-665; enable_riflex :774-788)."""
+    t = rope_table_f64(head_dim, riflex=riflex)
+    return torch.complex(t[..., 0], t[..., 1])
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -532,8 +543,17 @@ class Wan2_2Transformer3DModel_FlexAM(nn.Module):
         self.gradient_checkpointing = False
         self.sp_world_size = 1
         self.sp_world_rank = 0
-        self._riflex = None
+        self.freqs = rope_complex(self.d)          # plain attribute like the reference's (callers read and re-assign it)
         self._engine: Optional[NativeEngine] = None
+
+    # diffusers' ModelMixin conveniences the pipelines rely on
+    @property
+    def dtype(self) -> torch.dtype:
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self) -> torch.device:
+        return next(self.parameters()).device
 
     # -- loading (:1190-1332) ------------------------------------------------------------------------------------
     @classmethod
@@ -610,14 +630,11 @@ class Wan2_2Transformer3DModel_FlexAM(nn.Module):
         self.cfg_skip_ratio, self.current_steps, self.num_inference_steps = None, 0, None
 
     def enable_riflex(self, k=6, L_test=66, L_test_scale=4.886):
-        self._riflex = dict(k=k, L_test=L_test, L_test_scale=L_test_scale)
-        if self._engine is not None:
-            self._engine.freqs = rope_table(128, riflex=self._riflex).to(self._engine.device)
+        """Replaces ``self.freqs`` like the reference (:774-788); the engine's table follows it at the next forward."""
+        self.freqs = rope_complex(self.d, riflex=dict(k=k, L_test=L_test, L_test_scale=L_test_scale)).to(self.freqs.device)
 
     def disable_riflex(self):
-        self._riflex = None
-        if self._engine is not None:
-            self._engine.freqs = rope_table(128).to(self._engine.device)
+        self.freqs = rope_complex(self.d).to(self.freqs.device)
 
     def enable_teacache(self, coefficients, num_steps, rel_l1_thresh, num_skip_start_steps=0, offload=True):
         from .teacache import TeaCache
@@ -639,8 +656,6 @@ class Wan2_2Transformer3DModel_FlexAM(nn.Module):
             params = {k: v.detach() for k, v in self.named_parameters()}   # detach() shares the version counter
             dev = next(iter(params.values())).device
             self._engine = NativeEngine(params, self.config, dev)
-            if self._riflex is not None:
-                self._engine.freqs = rope_table(128, riflex=self._riflex).to(dev)
         return self._engine
 
     def forward(self, x, t, context, seq_len, clip_fea=None, y=None, y_camera=None, full_ref=None, subject_ref=None,
@@ -662,8 +677,7 @@ def native_forward(self, x, t, context, seq_len, clip_fea=None, y=None, y_camera
         x, t, context, y, full_ref, additional_control, density = (
             x[h:], t[h:], context[h:], y[h:], full_ref[h:], additional_control[h:], density[h:])
     eng = self.engine() if hasattr(self, "engine") else self._flexam_engine
-    if not hasattr(self, "engine"):
-        _sync_rope_table(self, eng)      # an installed reference module: follow ITS freqs (enable_riflex() etc.)
+    _sync_rope_table(self, eng)          # the module's `freqs` attribute is the source of truth (enable_riflex() etc.)
     with ops.stream_scope():
         out = eng.forward(x, t, context, seq_len, y, full_ref, additional_control, density,
                           teacache=getattr(self, "teacache", None), cond_flag=cond_flag)

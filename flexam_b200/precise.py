@@ -242,4 +242,7 @@ def precise_engine(model) -> PreciseEngine:
     dev = next(iter(params.values())).device
     cfg = dict(model.config)
     cfg.setdefault("in_dim_ref_conv", params["ref_conv.weight"].shape[1])
-    return PreciseEngine(params, cfg, dev)
+    eng = PreciseEngine(params, cfg, dev)
+    from .model import _sync_rope_table
+    _sync_rope_table(model, eng)         # RoPE table from the module's `freqs` (RIFLEx on / off), like the bf16 path
+    return eng

@@ -144,10 +144,16 @@ def test_rope_tables_with_and_without_riflex_match_the_reference(golden_dir):
         num_heads=cfg["num_heads"], num_layers=cfg["num_layers"], eps=cfg["eps"], add_ref_conv=True,
         in_dim_ref_conv=cfg["out_dim"], add_cnn_block=True, in_dim_cnn_block=cfg["in_dim_cnn"],
         out_dim_cnn_block=cfg["out_dim_cnn"], device="cpu")
-    m.enable_riflex()
-    np.testing.assert_allclose(m.engine().freqs[rows].double().numpy(), g["riflex"], rtol=0, atol=6e-8)
-    m.disable_riflex()
-    np.testing.assert_allclose(m.engine().freqs[rows].double().numpy(), g["plain"], rtol=0, atol=6e-8)
+    import flexam_b200.model as fx
+    assert m.freqs.dtype == torch.complex128 and tuple(m.freqs.shape) == (1024, 64)      # the reference's attribute
+    for call, key in ((m.enable_riflex, "riflex"), (m.disable_riflex, "plain")):
+        call()
+        np.testing.assert_allclose(torch.view_as_real(m.freqs)[rows].numpy(), g[key], rtol=0, atol=1e-15)
+        fx._sync_rope_table(m, m.engine())                    # what every forward does first
+        np.testing.assert_allclose(m.engine().freqs[rows].double().numpy(), g[key], rtol=0, atol=6e-8)
+    m.freqs = m.freqs.to(device="cpu")                        # callers re-assign it (comfyui nodes.py:324)
+    fx._sync_rope_table(m, m.engine())
+    assert torch.equal(m.engine().freqs, rope_table(128))
 
 
 @pytest.mark.skipif(not ref_import.reference_available(), reason="reference tree not mounted")
