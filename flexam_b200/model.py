@@ -170,6 +170,18 @@ class NativeEngine:
         if self._pvers() != self._versions:
             self._pack()
 
+    def refresh(self, params: Optional[Dict[str, torch.Tensor]] = None):
+        """Re-derive everything that is a COPY of a weight (packed q|k|v, cross k|v, fp32 modulation rows) and drop the
+        step-invariant cache; with ``params`` also adopt new parameter storages. Version counters catch in-place torch
+        ops on the parameters, but not edits through ``param.data`` (the reference's merge_lora / unmerge_lora,
+        FlexAM/utils/lora_utils.py:481-485, :595-599): hosts call ``flexam_b200.model.refresh(module)`` after those."""
+        if params is not None:
+            self.params = params
+        self._pack()
+
+    def _storage_ids(self):
+        return tuple(p.data_ptr() for p in self.params.values())
+
     # -- buffers -------------------------------------------------------------------------------------------
     def _buf(self, name: str, shape: Sequence[int], dtype) -> torch.Tensor:
         key = (name, tuple(shape), dtype)
@@ -677,6 +689,9 @@ def native_forward(self, x, t, context, seq_len, clip_fea=None, y=None, y_camera
         x, t, context, y, full_ref, additional_control, density = (
             x[h:], t[h:], context[h:], y[h:], full_ref[h:], additional_control[h:], density[h:])
     eng = self.engine() if hasattr(self, "engine") else self._flexam_engine
+    # parameters whose storage was replaced since the engine saw them (module.to(...), `param.data = ...`): adopt them
+    if eng._storage_ids() != tuple(p.data_ptr() for p in self.parameters()):
+        eng.refresh({k: v.detach() for k, v in self.named_parameters()})
     _sync_rope_table(self, eng)          # the module's `freqs` attribute is the source of truth (enable_riflex() etc.)
     with ops.stream_scope():
         out = eng.forward(x, t, context, seq_len, y, full_ref, additional_control, density,
@@ -700,6 +715,14 @@ def _sync_rope_table(module: nn.Module, eng: NativeEngine) -> None:
     eng.freqs = torch.view_as_real(fr.detach().to("cpu", torch.complex128)).to(f32).contiguous().to(eng.device)
     eng._freqs_key = key
     eng._freqs_ref = fr          # keeps the storage alive so the key cannot be recycled
+
+
+def refresh(module: nn.Module) -> None:
+    """Tell the native engine of ``module`` (a mirror instance or an ``install``-ed reference module) that weights were
+    edited behind autograd's back (``param.data += ...``, e.g. LoRA merge / unmerge): re-packs the copied weights."""
+    eng = module._engine if hasattr(module, "engine") else getattr(module, "_flexam_engine", None)
+    if eng is not None:
+        eng.refresh({k: v.detach() for k, v in module.named_parameters()})
 
 
 def install(module: nn.Module) -> nn.Module:

@@ -239,3 +239,36 @@ def test_from_pretrained_follows_the_reference_contract(tmp_path):
     assert "dict_mapping" in extra                                       # the caller's dict is not consumed
     with pytest.raises(RuntimeError, match="config.json does not exist"):
         Wan2_2Transformer3DModel_FlexAM.from_pretrained(str(tmp_path / "ckpt"), subfolder="nope")
+
+
+def test_weight_edits_are_picked_up(monkeypatch):
+    """In-place torch ops on a parameter (version counter), replaced storages (`param.data = ...`, module.to()) and -
+    after refresh() - edits through `param.data` (the reference's LoRA merge, lora_utils.py:481-485) all reach the
+    packed q|k|v copy the kernels read; the result equals a freshly built model with the same weights."""
+    import flexam_b200.model as fx
+    cpu_ops_emul.install(monkeypatch)
+    cfg = synth.CONFIGS["tiny"]
+    m, np_sd = build(cfg)
+    inp = synth.inputs(cfg, 2, 4, 8, per_token_t=True)
+    base, _, _ = call(m, inp)
+    key = "blocks.1.self_attn.k.weight"
+    p = dict(m.named_parameters())[key]
+    delta = torch.from_numpy(synth.tensor("lora/delta", tuple(p.shape), 0.02)).bfloat16()
+
+    def fresh(weight):
+        f, _ = build(cfg)
+        dict(f.named_parameters())[key].data.copy_(weight)
+        return call(f, inp)[0]
+
+    with torch.no_grad():
+        p.add_(delta)                                           # version counter bumps: automatic
+    want1 = fresh(p.data)
+    got1, _, _ = call(m, inp)
+    assert torch.equal(got1, want1) and not torch.equal(got1, base)
+    p.data = (p.data.float() - delta.float()).bfloat16()       # new storage: automatic
+    got2, _, _ = call(m, inp)
+    assert torch.equal(got2, fresh(p.data))
+    p.data += delta                                             # invisible to autograd: needs refresh()
+    fx.refresh(m)
+    got3, _, _ = call(m, inp)
+    assert torch.equal(got3, fresh(p.data)) and not torch.equal(got3, got2)
