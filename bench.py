@@ -12,7 +12,12 @@ random-init weights of that architecture. Prints ONE JSON line (rank 0).
            copied back inside the timed region
   roofline GEMM family (dominant: ~2/3 of the FLOPs): algorithmic FLOPs / CUDA-event time of those launches inside
            the timed region, against MEASURED_PEAKS.json's sustained bf16 figure
-  cpu_baseline  the oracle (CPU port of the reference forward, fp32) on a bounded sample, extrapolated to a step
+  cpu_baseline  the oracle (CPU port of the reference forward, fp32) on a bounded sample, extrapolated to a step,
+           plus a MEASURED full 30-layer forward at BASELINE config 1 (17 frames 256x448)
+  parity   (outside every timed region, every N) the step output against the bf16-policy oracle run in torch on
+           rank 0's GPU, and a SHA-256 of the output bytes: the N = 2/4/8 checksums must equal the N = 1 one
+  library_baseline  (N = 1) the reference's own GPU path restated in stock torch (oracle/library_step.py: cuBLAS
+           Linear, cuDNN conv, flash-attn 2 / SDPA under bf16 autocast) on the same B200, CUDA-event timed
 """
 from __future__ import annotations
 
@@ -156,6 +161,136 @@ def init_weights(torch, model, seed=1234):
             p.data.copy_((torch.randn(p.shape, device=p.device, generator=g) * fan_in ** -0.5).to(p.dtype))
 
 
+class _LazyF32(dict):
+    """{key: bf16 device tensor} that hands the oracle fp32 copies on access (one layer's worth alive at a time)."""
+
+    def __getitem__(self, k):
+        return dict.__getitem__(self, k).float()
+
+
+def output_checksum(out):
+    """SHA-256 (first 16 hex digits) of the prediction's bf16 bytes: equal across N iff the outputs are bit-identical."""
+    import hashlib
+    return hashlib.sha256(out.contiguous().view(-1).view(__import__("torch").int16).cpu().numpy().tobytes()).hexdigest()[:16]
+
+
+def parity_check(torch, model, cfg, d, out):
+    """Checker leg, outside every timed region: the whole step output against the bf16-policy oracle
+    (oracle/flexam_oracle.py, fp32 torch math on this GPU with the reference's bf16 rounding points) on the SAME
+    weights and inputs, at the benchmarked shape. Gate: north star, relative L2 <= 1e-2."""
+    from oracle import flexam_oracle as O
+    t0 = time.perf_counter()
+    sd = _LazyF32({k: v.detach() for k, v in model.state_dict().items()})
+    ocfg = dict(cfg, in_dim_cnn=cfg["in_dim_cnn_block"], out_dim_cnn=cfg["out_dim_cnn_block"])
+    with torch.no_grad():
+        want = O.forward(sd, ocfg, d["x"].float(), d["t"], [c.float() for c in d["context"]], d["seq_len"], d["y"].float(),
+                         d["full_ref"].float(), d["additional_control"].float(), d["density"], policy="bf16")
+    rel = (torch.linalg.vector_norm(out.float() - want) / torch.linalg.vector_norm(want)).item()
+    torch.cuda.synchronize()
+    return {"rel_l2_vs_oracle": rel, "gate": 1e-2, "ok": bool(rel <= 1e-2), "oracle": "oracle/flexam_oracle.py, policy "
+            "bf16, all 30 layers, whole output, fp32 torch math on the GPU", "oracle_seconds": time.perf_counter() - t0,
+            "finite": bool(torch.isfinite(out.float()).all().item())}
+
+
+def library_baseline(torch, model, cfg, d, out_native, steps=10, warmup=3):
+    """The reference's library path (oracle/library_step.py) on this GPU, sharing the native model's weights:
+    `warmup` + `steps` steps under bf16 autocast, CUDA events; then one instrumented step for the Linear / attention
+    family times (events around every nn.Linear and attention call). Both attention backends the reference can take
+    here are tried: flash-attn 2 (its default when the package imports) and SDPA."""
+    from oracle import library_step as LS
+    res = {}
+    flash_err = LS.flash_attn_usable(d["x"].device)
+    backends = (["flash"] if flash_err is None else []) + ["sdpa"]
+    if flash_err is not None:
+        res["flash_attn_unusable"] = flash_err
+    flops = step_flops(cfg)
+    for be in backends:
+        try:
+            lm = LS.LibraryStep(cfg, backend=be)
+            lm.load_state_dict(model.state_dict(), assign=True)       # shares the bf16 weights, no copy
+            lm = lm.to(d["x"].device)
+
+            def lcall():
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return lm(d["x"], d["t"], d["context"], d["seq_len"], d["y"], d["full_ref"], d["additional_control"],
+                              d["density"])
+            for _ in range(warmup):
+                o = lcall()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                o = lcall()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            # instrumented step: per-family device time
+            ev = {"linear": [], "attn": []}
+            hooks = []
+
+            def pre(kind, name):
+                def f(mod, inp):
+                    a = torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    ev[kind].append([a, None, (name, mod.in_features, mod.out_features), inp[0].shape])
+                return f
+
+            def post(kind):
+                def f(mod, inp, outp):
+                    b = torch.cuda.Event(enable_timing=True)
+                    b.record()
+                    ev[kind][-1][1] = b
+                return f
+            for name, mod in lm.named_modules():
+                if isinstance(mod, torch.nn.Linear):
+                    hooks += [mod.register_forward_pre_hook(pre("linear", name)),
+                              mod.register_forward_hook(post("linear"))]
+            orig_attend = LS.Attention.attend
+
+            def timed_attend(self, q, k, v, dtype):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                r = orig_attend(self, q, k, v, dtype)
+                b.record()
+                ev["attn"].append([a, b, None, (q.shape, k.shape)])
+                return r
+            LS.Attention.attend = timed_attend
+            try:
+                lcall()
+                torch.cuda.synchronize()
+            finally:
+                LS.Attention.attend = orig_attend
+                for h in hooks:
+                    h.remove()
+            lin_ms = sum(a.elapsed_time(b) for a, b, _, _ in ev["linear"])
+            # the bf16 projections of the 30 blocks at M = B*L rows (everything the native GEMM roofline covers)
+            blk = [(a, b, m, sh) for a, b, m, sh in ev["linear"] if m[0].startswith("blocks.") and math.prod(sh[:-1]) >= 1024]
+            lin_fl = sum(2.0 * math.prod(sh[:-1]) * m[1] * m[2] for _, _, m, sh in blk)
+            lin_big_ms = sum(a.elapsed_time(b) for a, b, _, _ in blk)
+            att_ms = sum(a.elapsed_time(b) for a, b, _, _ in ev["attn"])
+            att_fl = sum(4.0 * q[0] * q[2] * q[1] * k[1] * q[3] for _, _, _, (q, k) in ev["attn"])
+            rel = (torch.linalg.vector_norm(out_native.float() - o.float()) / torch.linalg.vector_norm(o.float())).item()
+            res[be] = {"ms_per_step": ms, "steps_per_s": 1e3 / ms, "step_tflops_per_s": flops / ms / 1e9,
+                       "linear_ms": lin_ms, "block_gemm_tflops": lin_fl / 1e9 / max(lin_big_ms, 1e-9),
+                       "attn_ms": att_ms, "attn_tflops": att_fl / 1e9 / max(att_ms, 1e-9),
+                       "native_rel_l2_vs_library": rel, "timed": f"{warmup} warm-up + {steps} steps, CUDA events"}
+            del lm, o
+            torch.cuda.empty_cache()
+        except Exception as exc:   # noqa: BLE001 — a baseline leg must not take the bench line down
+            res[be] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+    ok = [b for b in backends if "ms_per_step" in res.get(b, {})]
+    if ok:
+        best = min(ok, key=lambda b: res[b]["ms_per_step"])
+        res["best"] = best
+        res["ms_per_step"] = res[best]["ms_per_step"]
+        res["gemm_tflops"] = res[best]["block_gemm_tflops"]
+        res["attn_tflops"] = res[best]["attn_tflops"]
+    res["what"] = ("reference forward restated with library calls only (cuBLAS nn.Linear, cuDNN Conv3d, fp32 per-token "
+                   "time MLP, complex128 RoPE, flash-attn 2 varlen / SDPA) under torch.autocast(bf16); same weights, "
+                   "inputs and B200 as the native line")
+    return res
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -267,6 +402,19 @@ def run_native(args):
     ms_e2e = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
     clk = clocks.stop() if clocks else None
 
+    # ---------------- parity (checker, outside every timed region): every rank runs the step once more, rank 0 compares
+    parity = None
+    if not args.no_parity:
+        out_p = call(resident)
+        barrier()
+        if rank == 0:
+            parity = {"checksum_sha256_16": output_checksum(out_p), "shape": list(out_p.shape)}
+            try:
+                parity.update(parity_check(torch, model, cfg, resident, out_p))
+            except Exception as exc:   # noqa: BLE001 — report, do not lose the timing line
+                parity["error"] = f"{type(exc).__name__}: {str(exc)[:200]}"
+        barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -284,8 +432,7 @@ def run_native(args):
         "metric": METRIC, "value": 1e3 / ms_value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (seeded N(0,1) latents/controls, random-init weights)",
-        "config": {"workload": WORKLOAD, "layout": layout, "l2": "working set (10 GB weights + >1 GB activations per "
-                   "step) exceeds the 126 MB L2; no flush needed", "timesteps": "per-token, 2 distinct values"},
+        "config": bench_config(world, layout),
         "latent_tokens_per_s": L0 * 1e3 / ms_value,
         "step_tflops": flops / 1e12, "step_frac_of_bf16_sustained": flops / (ms_value * 1e-3) / 1e12 / (world * sustained),
         "hoisted": {"ms_per_step": ms_hoisted, "value": 1e3 / ms_hoisted,
@@ -303,8 +450,19 @@ def run_native(args):
                           "share_of_step": att[1] / args.steps / ms_value},
         "clocks": clk,
     }
+    if parity is not None:
+        line["parity"] = parity
+    if not args.no_library_baseline and world == 1:
+        lb = library_baseline(torch, model, cfg, resident, out if parity is None else out_p)
+        line["library_baseline"] = lb
+        if "ms_per_step" in lb:
+            line["speedup_vs_library"] = lb["ms_per_step"] / ms_value
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_sample(cfg, threads=None)
+        try:
+            line["cpu_baseline"]["config1_forward"] = cpu_config1_forward(torch, model, cfg)
+        except Exception as exc:   # noqa: BLE001
+            line["cpu_baseline"]["config1_forward"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -356,28 +514,77 @@ def cpu_sample(cfg, threads=None, reps=1):
                       f"step extrapolated x60 = {step_s:.1f} s"}
 
 
+def cpu_config1_forward(torch, model, cfg):
+    """BASELINE.md §3's mandatory CPU number, MEASURED not extrapolated: the complete 30-layer forward (CFG batch 2,
+    per-token timesteps) at BASELINE config 1 — 17 frames 256x448, 560 + 112 tokens — through the fp32 oracle on all
+    host cores, with the bench model's own weights (copied to the host as fp32)."""
+    from oracle import flexam_oracle as O
+    global GRID
+    saved = GRID
+    GRID = (5, 16, 28)
+    try:
+        host = make_host_inputs(torch, cfg)
+        flops = step_flops(cfg)
+    finally:
+        GRID = saved
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    sd = {k: v.detach().to("cpu", torch.float32) for k, v in model.state_dict().items()}
+    ocfg = dict(cfg, in_dim_cnn=cfg["in_dim_cnn_block"], out_dim_cnn=cfg["out_dim_cnn_block"])
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        out = O.forward(sd, ocfg, host["x"].float(), host["t"], [c.float() for c in host["context"]], host["seq_len"],
+                        host["y"].float(), host["full_ref"].float(), host["additional_control"].float(), host["density"],
+                        policy="fp32")
+    dt = time.perf_counter() - t0
+    return {"seconds_per_step": dt, "steps_per_s": 1.0 / dt, "latent_tokens_per_s": host["seq_len"] / dt,
+            "tflops_per_s": flops / dt / 1e12, "cores": n, "finite": bool(torch.isfinite(out).all().item()),
+            "what": "full 30-layer fp32 oracle forward at BASELINE config 1 (17 frames 256x448, CFG batch 2), one run, "
+                    "measured"}
+
+
+def bench_config(world, layout=None):
+    """The `config` object of the JSON line — the same for the native and the reference arm at a given N."""
+    if layout is None:
+        layout = "single"
+        if world > 1:
+            from flexam_b200.dist import make_layout
+            layout = make_layout(world, 0).describe()
+    return {"workload": WORKLOAD, "layout": layout, "l2": "working set (10 GB weights + >1 GB activations per step) "
+            "exceeds the 126 MB L2; no flush needed", "timesteps": "per-token, 2 distinct values"}
+
+
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path is Python/torch and does not travel to the
-    GPU box, so this times the oracle port on the host cores (all threads), per step a bounded sample (see cpu_sample)."""
+    """Reference arm: the reference's own implementation of the path is Python/torch on the host CPU and its sources
+    do not travel to the GPU box, so this times the oracle port (oracle/flexam_oracle.py, pinned against the real
+    module) on all host cores. Exactly --warmup + --steps samples are run; each "step" is a bounded sample of the
+    workload (cpu_sample: one of the 30 blocks for one of the 2 CFG samples at the full 11,648 tokens, x60). Under
+    torchrun only rank 0 works."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     cfg = real_cfg()
     vals = []
-    for i in range(args.warmup + args.steps):
-        r = cpu_sample(cfg)
-        if i >= args.warmup:
-            vals.append(r)
-        if i >= 1 and (i + 1 - args.warmup) >= 2:   # keep the whole run within a few minutes
+    t_start = time.perf_counter()
+    warm_done = 0
+    for i in range(args.warmup):
+        cpu_sample(cfg)
+        warm_done += 1
+        per = (time.perf_counter() - t_start) / warm_done
+        if per * (warm_done + 1 + args.steps) > 270.0:   # slow host: spend the remaining budget on the timed steps
             break
-    v = sum(x["value"] for x in vals) / len(vals)
+    for _ in range(args.steps):
+        vals.append(cpu_sample(cfg))
+    ms = sum(1e3 / x["value"] for x in vals) / len(vals)
+    v = 1e3 / ms
     cb = dict(vals[-1], value=v)
+    cb["sample"] += f"; mean of {len(vals)} timed samples after {warm_done} warm-up"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-        "steps": len(vals), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 / v, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU port of the reference forward (oracle), bounded sample per step"},
-        "cpu_baseline": cb,
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": warm_done, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded N(0,1) latents/controls, "
+        "random-init weights)", "config": bench_config(world), "cpu_baseline": cb,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -388,6 +595,8 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison + checksum of the step output")
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip the torch library-path leg (N = 1 only)")
     ap.add_argument("--quick", action="store_true", help="resident region only (for ncu runs)")
     ap.add_argument("--workload", default="config2", choices=["config2", "long"],
                     help="config2 = the metric's workload (default); long = BASELINE config 5, 193 frames 704x1280 "

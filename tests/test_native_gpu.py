@@ -327,6 +327,34 @@ def test_forward_matches_bf16_policy_oracle(dev):
     assert rel < 5e-3
 
 
+@pytest.mark.parametrize("cfg_name", ["real2", "real"])
+def test_benchmarked_shape_matches_bf16_oracle(dev, cfg_name):
+    """The configuration the BENCH number is quoted on (BASELINE config 2): latent grid 25x32x56 = 11,200 + 448 tokens,
+    CFG batch 2, per-token timesteps — M = 23,296 rows through the CTA-pair GEMMs with every epilogue, 46 query tiles x
+    24 heads x 2 in the attention kernel — against the bf16-policy oracle executed in torch fp32 math on the GPU
+    (wan_transformer3d_FlexAM.py:817-1123). 2 layers at real width, then the full 30-layer model."""
+    from oracle import flexam_oracle as O
+    from oracle import synth
+    model, cfg = _native_model(cfg_name, dev)
+    tt, ctx, seq_len = _inputs(cfg, (25, 32, 56), True, dev)
+    assert seq_len == 11200
+    out = model(x=tt["x"].bfloat16(), t=tt["t"], context=[c.bfloat16() for c in ctx], seq_len=seq_len,
+                y=tt["y"].bfloat16(), full_ref=tt["full_ref"].bfloat16(),
+                additional_control=tt["additional_control"].bfloat16(), density=tt["density"])
+    torch.cuda.synchronize()
+    assert out.shape == (2, 48, 25, 32, 56) and torch.isfinite(out.float()).all()
+
+    class Lazy(dict):                       # fp32 copies on access: one layer's weights alive at a time
+        def __getitem__(self, k):
+            return dict.__getitem__(self, k).float()
+    sd = Lazy({k: v.detach() for k, v in model.state_dict().items()})
+    want = O.forward(sd, cfg, tt["x"], tt["t"], ctx, seq_len, tt["y"], tt["full_ref"], tt["additional_control"],
+                     tt["density"], policy="bf16")
+    rel = _rel(out, want)
+    print(f"config-2 shape, {cfg['num_layers']} layers: native vs bf16-policy oracle rel-L2 {rel:.3e}")
+    assert rel < BF16_GATE
+
+
 def test_forward_is_deterministic_and_cache_consistent(dev):
     model, cfg = _native_model("tiny", dev)
     tt, ctx, seq_len = _inputs(cfg, (3, 8, 12), True, dev)

@@ -225,3 +225,36 @@ def test_installed_reference_module_with_its_own_teacache_and_cfg_skip(monkeypat
     out = loop.run(g["timesteps"], g["sigmas"])
     assert decisions == [bool(d) for d in g["decisions"]]
     assert _rel(out, torch.from_numpy(g["out"])) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------------
+# oracle/library_step.py — the reference's library (cuBLAS / cuDNN / flash-attn) path restated as torch modules; it is
+# bench.py's `library_baseline` leg on the B200. Here its module tree is pinned in fp32 on CPU.
+# ------------------------------------------------------------------------------------------------------
+def _library_model(cfg):
+    from oracle.library_step import LibraryStep
+    m = LibraryStep(dict(cfg, in_dim_ref_conv=cfg["out_dim"]), backend="sdpa").eval()
+    missing, unexpected = m.load_state_dict(O.to_torch_sd(synth.state_dict(cfg)), strict=True)
+    assert not missing and not unexpected
+    return m
+
+
+@pytest.mark.parametrize("name", ["tiny_tok", "tiny_sample"])
+def test_library_step_matches_reference_golden(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    F, H, W, per_tok = (int(v) for v in g["meta"])
+    cfg = synth.CONFIGS[str(g["config"])]
+    inp = synth.inputs(cfg, F, H, W, per_token_t=bool(per_tok))
+    tt = {k: torch.from_numpy(inp[k]) for k in ("x", "y", "additional_control", "full_ref", "t", "density")}
+    out = _library_model(cfg)(tt["x"], tt["t"], [torch.from_numpy(c) for c in inp["context"]], inp["seq_len"], tt["y"],
+                              tt["full_ref"], tt["additional_control"], tt["density"])
+    assert _rel(out, torch.from_numpy(g["out"])) < 2e-5
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="reference tree not mounted")
+def test_library_step_has_the_reference_state_dict():
+    cfg = synth.CONFIGS["tiny"]
+    ref = ref_import.build_reference_model(cfg)
+    mine = _library_model(cfg)
+    assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == \
+           {k: tuple(v.shape) for k, v in mine.state_dict().items()}
