@@ -1,7 +1,13 @@
 // Library-level C-ABI entry points and the host helpers the kernel translation units share.
 #include <stdarg.h>
 #include <stdlib.h>
+#include <ctype.h>
 #include <string.h>
+
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
 
 #include "host_common.h"
 
@@ -25,9 +31,52 @@ bool pdl_enabled() {
   return v == 1;
 }
 
+bool ensure_dyn_smem(const void* func, int bytes, const char* what) {
+  static std::mutex mu;
+  static std::vector<std::tuple<const void*, int, int>> done;  // (function, device, bytes granted)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  for (auto& e : done) {
+    if (std::get<0>(e) == func && std::get<1>(e) == dev) {
+      if (std::get<2>(e) >= bytes) return true;
+      cudaError_t err = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (err != cudaSuccess) {
+        set_error("%s: cudaFuncSetAttribute(%d B smem, device %d): %s", what, bytes, dev, cudaGetErrorString(err));
+        return false;
+      }
+      std::get<2>(e) = bytes;
+      return true;
+    }
+  }
+  cudaError_t err = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (err != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(%d B smem, device %d): %s", what, bytes, dev, cudaGetErrorString(err));
+    return false;
+  }
+  done.emplace_back(func, dev, bytes);
+  return true;
+}
+
+// name -> value table of the developer knobs; the environment variable FX_<NAME> seeds a knob at its first read.
+static std::mutex g_tune_mu;
+static std::vector<std::pair<std::string, int>> g_tune;
+
+int tune_get(const char* name) {
+  std::lock_guard<std::mutex> lock(g_tune_mu);
+  for (auto& kv : g_tune)
+    if (kv.first == name) return kv.second;
+  std::string env = std::string("FX_") + name;
+  for (auto& c : env) c = static_cast<char>(toupper(c));
+  const char* v = getenv(env.c_str());
+  const int val = (v && v[0]) ? atoi(v) : -1;
+  g_tune.emplace_back(name, val);
+  return val;
+}
+
 int num_sms() {
-  static int cached_dev = -1;
-  static int cached = 0;
+  static thread_local int cached_dev = -1;
+  static thread_local int cached = 0;
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev != cached_dev) {
@@ -81,6 +130,21 @@ bool make_tmap(CUtensorMap* out, bool is_f32, const void* base, int rank, const 
 }
 
 }  // namespace fx
+
+extern "C" int fx_tune(const char* name, int value) {
+  if (name == nullptr || name[0] == 0) {
+    fx::set_error("fx_tune: empty name");
+    return FX_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lock(fx::g_tune_mu);
+  for (auto& kv : fx::g_tune)
+    if (kv.first == name) {
+      kv.second = value;
+      return FX_OK;
+    }
+  fx::g_tune.emplace_back(name, value);
+  return FX_OK;
+}
 
 extern "C" int fx_abi_version(void) { return FX_ABI_VERSION; }
 extern "C" const char* fx_last_error(void) { return fx::g_err; }

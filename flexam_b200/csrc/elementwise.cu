@@ -196,6 +196,16 @@ struct RmsParams {
   __nv_bfloat16* dst[8];
 };
 
+// bf16x2 product rounded once to bf16 (mul.rn.bf16x2). For bf16 operands this equals bf16(float(a) * float(b)): the
+// fp32 product of two 8-bit significands is exact, so both forms round the exact product once — the reference's
+// `x * r.to(x.dtype)` and `(...) * weight` roundings (:186-189) at one instruction per pair instead of unpack, FMUL,
+// and a quarter-rate F2F conversion per element.
+__device__ __forceinline__ uint32_t bf16x2_mul(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+
 template <int NV, int WPR>  // NV = 16-byte vectors (8 bf16) per lane = D / (256 * WPR)
 __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const __grid_constant__ RmsParams p) {
   pdl_launch_dependents();
@@ -212,62 +222,70 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const __grid_constant
   uint4 v[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) v[i] = valid ? xr[i * 32 + lane] : make_uint4(0, 0, 0, 0);
+
+  // While the row is in flight: the rotation of this lane. Every vector a lane owns sits at the same position inside
+  // its 128-wide head ((c0 + i*32 + lane) & 15 == lane & 15: c0 and 32 are multiples of 16), so the lane needs only
+  // the four (cos, sin) pairs pair0 .. pair0+3 of its token: four table reads per row instead of four per vector.
+  const bool normed = which < p.norm_tensors;
+  const int b = row / p.rows_per_batch;
+  const int tl = row - b * p.rows_per_batch;  // token inside this rank's slice of sample b
+  bool rotate = false;
+  float2 cs[4];
+  if (p.freqs != nullptr && normed && valid) {
+    const int t = p.tok_offset + tl;
+    if (t < p.gf * p.gh * p.gw) {
+      rotate = true;
+      const int pf = t / (p.gh * p.gw);
+      const int rem = t - pf * (p.gh * p.gw);
+      const int ph = rem / p.gw;
+      const int pw = rem - ph * p.gw;
+      const int pair0 = (lane & 15) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pj = pair0 + j;
+        const int pos = pj < 22 ? pf : (pj < 43 ? ph : pw);
+        cs[j] = __ldg(p.freqs + pos * 64 + pj);
+      }
+    }
+  }
+  const uint4* wr = reinterpret_cast<const uint4*>(which == 0 ? p.w : p.w2) + c0;
+  uint4 wv[NV];
+  if (normed) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) wv[i] = __ldg(wr + i * 32 + lane);
+  }
+
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float a = bf16_lo(u[j]), b = bf16_hi(u[j]);
-      ss += a * a + b * b;
+      const float a = bf16_lo(u[j]), bb = bf16_hi(u[j]);
+      ss += a * a + bb * bb;
     }
   }
   // r is rounded to bf16 before the multiply, as `.to(x.dtype)` does at :189
-  const float r = bf16_round(
-      rsqrtf(row_reduce<WPR>(ss, red, row_in_block, warp_in_row, lane) / static_cast<float>(p.D) + p.eps));
+  const float rf = rsqrtf(row_reduce<WPR>(ss, red, row_in_block, warp_in_row, lane) / static_cast<float>(p.D) + p.eps);
+  const uint32_t r2 = pack_bf16x2(rf, rf);
   if (!valid) return;
 
-  const bool normed = which < p.norm_tensors;
-  int pf = 0, ph = 0, pw = 0;
-  bool rotate = false;
-  const int b = row / p.rows_per_batch;
-  const int tl = row - b * p.rows_per_batch;  // token inside this rank's slice of sample b
-  if (p.freqs != nullptr && normed) {
-    const int t = p.tok_offset + tl;
-    if (t < p.gf * p.gh * p.gw) {
-      rotate = true;
-      pf = t / (p.gh * p.gw);
-      const int rem = t - pf * (p.gh * p.gw);
-      ph = rem / p.gw;
-      pw = rem - ph * p.gw;
-    }
-  }
-  const uint4* wr = reinterpret_cast<const uint4*>(which == 0 ? p.w : p.w2) + c0;
   const long long drow = (static_cast<long long>(b) * p.ntensors + which) * p.dst_rows + p.dst_row0 + tl;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = i * 32 + lane;  // vector index inside this warp's span
     uint4 ov = v[i];
     if (normed) {
-      const uint4 wv = __ldg(wr + c);
       const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-      const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+      const uint32_t ww[4] = {wv[i].x, wv[i].y, wv[i].z, wv[i].w};
       uint32_t o[4];
-      const int pair0 = ((c0 + c) & 15) * 4;  // first complex pair of this vector inside its 128-wide head
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float a = bf16_round(bf16_round(bf16_lo(u[j]) * r) * bf16_lo(ww[j]));
-        float bb = bf16_round(bf16_round(bf16_hi(u[j]) * r) * bf16_hi(ww[j]));
+        o[j] = bf16x2_mul(bf16x2_mul(u[j], r2), ww[j]);   // bf16(bf16(x * r) * w), both halves
         if (rotate) {
-          const int pj = pair0 + j;
-          const int pos = pj < 22 ? pf : (pj < 43 ? ph : pw);
-          const float2 cs = __ldg(p.freqs + pos * 64 + pj);
-          const float re = a * cs.x - bb * cs.y;
-          const float im = a * cs.y + bb * cs.x;
-          a = re;
-          bb = im;
+          const float a = bf16_lo(o[j]), bb = bf16_hi(o[j]);
+          o[j] = pack_bf16x2(a * cs[j].x - bb * cs[j].y, a * cs[j].y + bb * cs[j].x);
         }
-        o[j] = pack_bf16x2(a, bb);
       }
       ov = make_uint4(o[0], o[1], o[2], o[3]);
     }
@@ -505,6 +523,51 @@ extern "C" int fx_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void*
   cast_bf16_f32_kernel<<<ew_grid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
   FX_CHECK_LAUNCH("fx_cast_bf16_to_f32");
+  return FX_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Sampled fingerprint of a set of weight tensors: detects edits made behind autograd's back (`weight.data += ...`,
+// the reference's merge_lora / unmerge_lora, FlexAM/utils/lora_utils.py:481-485, :595-599) to tensors the engine keeps
+// COPIES of (packed q|k|v, cross k|v, fp32 modulation rows) or derived results of (cached cross-attention K/V).
+// out[t] = sum over every `stride`-th 16-byte word w of tensor t of mix(w, index) (64-bit integer add: order-free,
+// deterministic). A dense edit (LoRA delta = B @ A touches every element) changes every sample.
+// -------------------------------------------------------------------------------------------------
+namespace fx {
+__global__ void fingerprint_kernel(const void* const* ptrs, const long long* nbytes, int n, int stride,
+                                   unsigned long long* out) {
+  const int t = blockIdx.y;
+  if (t >= n) return;
+  const uint4* p = reinterpret_cast<const uint4*>(ptrs[t]);
+  const long long nvec = nbytes[t] / 16;
+  unsigned long long acc = 0;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * stride; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * stride) {
+    const uint4 v = __ldg(p + i);
+    unsigned long long h = (static_cast<unsigned long long>(v.x ^ v.z) << 32) | (v.y ^ v.w);
+    h ^= static_cast<unsigned long long>(i) * 0x9E3779B97F4A7C15ull;
+    h = (h ^ (h >> 31)) * 0xBF58476D1CE4E5B9ull;
+    acc += h ^ (h >> 29);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc != 0) atomicAdd(out + t, acc);
+}
+}  // namespace fx
+
+extern "C" int fx_fingerprint(const void* const* ptrs, const int64_t* nbytes, int n, int stride, uint64_t* out,
+                              void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(ptrs && nbytes && out && n > 0 && stride > 0, "fx_fingerprint: bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(uint64_t) * n, s);
+  if (e != cudaSuccess) {
+    set_error("fx_fingerprint: cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return FX_ERR_CUDA;
+  }
+  fingerprint_kernel<<<dim3(8, n), 256, 0, s>>>(ptrs, reinterpret_cast<const long long*>(nbytes), n, stride,
+                                                 reinterpret_cast<unsigned long long*>(out));
+  FX_CHECK_LAUNCH("fx_fingerprint");
   return FX_OK;
 }
 

@@ -889,15 +889,7 @@ static int fmha_launch(const void* q, int64_t q_stride_b, int64_t q_stride_l, co
       {fmha2_fwd_kernel<0>, nullptr, fmha2_fwd_kernel<2>, fmha2_fwd_kernel<3>, fmha2_fwd_kernel<4>}};
   const int fam = pipe >= 2 ? 1 : 0;
   const Kern kern = kerns[fam][poly];
-  static bool configured[2][5] = {};
-  if (!configured[fam][poly]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmhaSmem);
-    if (e != cudaSuccess) {
-      set_error("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
-      return FX_ERR_CUDA;
-    }
-    configured[fam][poly] = true;
-  }
+  if (!ensure_dyn_smem(reinterpret_cast<const void*>(kern), kFmhaSmem, name)) return FX_ERR_CUDA;
   FmhaParams p{};
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.o_stride_b = o_stride_b;

@@ -307,15 +307,8 @@ extern "C" int fx_linear_f32(const float* in, int64_t ldi, const void* w, int64_
   FX_CHECK_ARG(act_in == 0 || act_in == 1, "fx_linear_f32: unknown act_in %d", act_in);
   const int smem = kLinRows * K * static_cast<int>(sizeof(float));
   FX_CHECK_ARG(smem <= 200 * 1024, "fx_linear_f32: K=%d too large for the smem staging buffer", K);
-  static int configured_smem = 0;
-  if (smem > 48 * 1024 && smem > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(linear_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_error("fx_linear_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return FX_ERR_CUDA;
-    }
-    configured_smem = smem;
-  }
+  if (smem > 48 * 1024 && !ensure_dyn_smem(reinterpret_cast<const void*>(linear_f32_kernel), smem, "fx_linear_f32"))
+    return FX_ERR_CUDA;
   dim3 grid((N + kLinWarps - 1) / kLinWarps, (M + kLinRows - 1) / kLinRows);
   FX_CHECK_ARG(grid.y <= 65535, "fx_linear_f32: M=%d too large", M);
   linear_f32_kernel<<<grid, kLinWarps * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -359,5 +352,70 @@ extern "C" int fx_groupnorm_silu(const void* x, int64_t P, int C, int G, float e
       reinterpret_cast<const __nv_bfloat16*>(x), P, C, G, reinterpret_cast<const __nv_bfloat16*>(gamma),
       reinterpret_cast<const __nv_bfloat16*>(beta), stats, resid, y_f32, reinterpret_cast<__nv_bfloat16*>(y_bf16));
   FX_CHECK_LAUNCH("fx_groupnorm_silu(apply)");
+  return FX_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// On-device de-duplication of the per-token timesteps (replaces a host-synchronising torch.unique): the pipeline's
+// per-token t is mask * t (pipeline :891-898), i.e. a handful of distinct values in `full_edit` and up to one per token
+// with fractional trilinear masks (:686-690). One block: distinct values are appended in order of first appearance
+// (deterministic), at most `cap`; count = cap + 1 reports "more than cap" (the caller then takes the per-token path).
+// -------------------------------------------------------------------------------------------------
+namespace fx {
+constexpr int kDedupThreads = 1024;
+constexpr int kDedupCap = 64;
+
+__global__ void __launch_bounds__(kDedupThreads)
+dedup_f32_kernel(const float* t, int n, int cap, float* uniq, int* inv, int* count) {
+  __shared__ float vals[kDedupCap];
+  __shared__ int s_cnt, s_best;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  while (true) {
+    const int cnt = s_cnt;
+    if (threadIdx.x == 0) s_best = n;
+    __syncthreads();
+    int cand = n;  // first element owned by this thread whose value is not in the list yet
+    for (int i = threadIdx.x; i < n && cand == n; i += kDedupThreads) {
+      const float v = t[i];
+      bool found = false;
+      for (int j = 0; j < cnt; ++j) found |= (vals[j] == v);
+      if (!found) cand = i;
+    }
+    if (cand < n) atomicMin(&s_best, cand);
+    __syncthreads();
+    const int best = s_best;
+    if (best == n) break;              // every value is in the list
+    if (cnt == cap) {                  // a (cap+1)-th distinct value exists
+      if (threadIdx.x == 0) s_cnt = cap + 1;
+      __syncthreads();
+      break;
+    }
+    if (threadIdx.x == 0) {
+      vals[cnt] = t[best];
+      s_cnt = cnt + 1;
+    }
+    __syncthreads();
+  }
+  const int cnt = s_cnt;
+  const int listed = cnt > cap ? cap : cnt;
+  if (threadIdx.x == 0) *count = cnt;
+  for (int j = threadIdx.x; j < cap; j += kDedupThreads) uniq[j] = vals[j < listed ? j : (listed > 0 ? listed - 1 : 0)];
+  for (int i = threadIdx.x; i < n; i += kDedupThreads) {
+    const float v = t[i];
+    int idx = 0;
+    for (int j = 0; j < listed; ++j)
+      if (vals[j] == v) idx = j;
+    inv[i] = idx;
+  }
+}
+}  // namespace fx
+
+extern "C" int fx_dedup_f32(const float* t, int n, int cap, float* uniq, int32_t* inv, int32_t* count, void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(t && uniq && inv && count && n > 0, "fx_dedup_f32: bad arguments");
+  FX_CHECK_ARG(cap >= 1 && cap <= kDedupCap, "fx_dedup_f32: cap %d outside [1, %d]", cap, kDedupCap);
+  dedup_f32_kernel<<<1, kDedupThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t, n, cap, uniq, inv, count);
+  FX_CHECK_LAUNCH("fx_dedup_f32");
   return FX_OK;
 }

@@ -49,6 +49,8 @@ struct GemmParams {
   int num_m_tiles, num_n_tiles, group_m;
   int n_span;  // n-tiles per outer slab of the rasterisation (num_n_tiles = one slab)
   int a_hint, b_hint;  // L2 eviction priority of the A / B panel loads (CTA-pair kernel): 0 normal, 1 first, 2 last
+  int b_k_wrap;        // > 0: the weight's K extent; A is [M, planes * b_k_wrap] (bf16 planes of an fp32 matrix side by
+                       // side) and the weight column of k-block kb is (kb * 64) % b_k_wrap — one accumulation over all planes
 };
 
 // Tile order: the N range is cut into slabs of n_span tile columns (outer loop); inside a slab, groups of group_m tile
@@ -220,8 +222,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          const int kcol_b = p.b_k_wrap > 0 ? (kb * kBK) % p.b_k_wrap : kb * kBK;
           tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m_tile * kBM);
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBK, n_tile * BN);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kcol_b, n_tile * BN);
         }
         if (++stage == kStages) {
           stage = 0;
@@ -417,8 +420,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           uint8_t* sb = sa + Cfg::kABytes;
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
           const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          const int kcol_b = p.b_k_wrap > 0 ? (kb * kBK) % p.b_k_wrap : kb * kBK;
           tma_load_2d_2sm_hint(sa, &tmap_a, leader_full, kb * kBK, a_row, pol_a);
-          tma_load_2d_2sm_hint(sb, &tmap_b, leader_full, kb * kBK, b_row, pol_b);
+          tma_load_2d_2sm_hint(sb, &tmap_b, leader_full, kcol_b, b_row, pol_b);
         }
         if (++stage == kStages) {
           stage = 0;
@@ -532,16 +536,8 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   using Cfg = Gemm2Cfg<EPI>;
   static_assert(Cfg::kStages >= 4, "pipeline too shallow");
   static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
-  static bool configured = false;
   auto kern = gemm2_bf16_kernel<EPI>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) {
-      set_error("fx_gemm_bf16(2cta): cudaFuncSetAttribute(%d B smem): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
-      return FX_ERR_CUDA;
-    }
-    configured = true;
-  }
+  if (!ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::kSmemBytes, "fx_gemm_bf16(2cta)")) return FX_ERR_CUDA;
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int pairs = num_sms() / 2;
   const int grid = 2 * (total < pairs ? total : pairs);
@@ -579,11 +575,7 @@ static bool use_pair_kernel(int M, int N, int bn) {
 // once; a wide one (ffn.0 / qkv: W = 88 / 57 MB does not stay in L2 next to the streams) wants g = 12-16 so that W is
 // swept few times; with a small weight matrix the choice does not matter. FX_GEMM_GROUP_M overrides (experiments).
 static int pair_group_m(int N, int K) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* env = getenv("FX_GEMM_GROUP_M");
-    forced = env ? atoi(env) : 0;
-  }
+  const int forced = tune_get("gemm_group_m");
   if (forced > 0) return forced;
   if (K >= 2 * N) return 1;
   if (2LL * N * K <= (32LL << 20)) return 4;
@@ -596,16 +588,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   using Cfg = GemmCfg<BN, EPI>;
   static_assert(Cfg::kStages >= 3, "pipeline too shallow");
   static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
-  static bool configured = false;  // per (BN, EPI) instantiation; attribute is per-function, set once per process
   auto kern = gemm_bf16_kernel<BN, EPI>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) {
-      set_error("fx_gemm_bf16: cudaFuncSetAttribute(%d B smem): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
-      return FX_ERR_CUDA;
-    }
-    configured = true;
-  }
+  if (!ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::kSmemBytes, "fx_gemm_bf16")) return FX_ERR_CUDA;
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
   launch_kernel(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, tout, p);
@@ -629,14 +613,30 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
 
 }  // namespace fx
 
+namespace fx {
+// K = reduction length seen by the kernel (A's width). kw = the weight's K extent: == K normally; K = planes * kw for
+// the plane-concatenated form used by fx_linear_f32_tc (GemmParams::b_k_wrap).
+static int gemm_impl(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* out,
+                     int64_t ldo, int M, int N, int K, int kw, int epilogue, const float* gate_mod,
+                     const float* gate_e, int64_t gate_e_stride, const int32_t* row_idx, void* stream);
+}
+
 extern "C" int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* out,
                             int64_t ldo, int M, int N, int K, int epilogue, const float* gate_mod,
                             const float* gate_e, int64_t gate_e_stride, const int32_t* row_idx, void* stream) {
+  return fx::gemm_impl(a, lda, w, ldw, bias, out, ldo, M, N, K, K, epilogue, gate_mod, gate_e, gate_e_stride, row_idx,
+                       stream);
+}
+
+int fx::gemm_impl(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* out,
+                         int64_t ldo, int M, int N, int K, int kw, int epilogue, const float* gate_mod,
+                         const float* gate_e, int64_t gate_e_stride, const int32_t* row_idx, void* stream) {
   using namespace fx;
   FX_CHECK_ARG(a && w && out, "fx_gemm_bf16: null pointer");
   FX_CHECK_ARG(M > 0 && N > 0 && K > 0, "fx_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   FX_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "fx_gemm_bf16: K (%d) and N (%d) must be multiples of 8", K, N);
-  FX_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, "fx_gemm_bf16: bad lda/ldw");
+  FX_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= kw, "fx_gemm_bf16: bad lda/ldw");
+  FX_CHECK_ARG(kw == K || (kw > 0 && kw % kBK == 0 && K % kw == 0), "fx_gemm_bf16: bad plane wrap %d for K=%d", kw, K);
   FX_CHECK_ARG(ldo >= N && ldo % 8 == 0, "fx_gemm_bf16: bad ldo");
   FX_CHECK_ARG((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) |
                 reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
@@ -664,6 +664,7 @@ extern "C" int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t l
   p.num_n_tiles = (N + bn - 1) / bn;
   p.group_m = 16;
   p.n_span = p.num_n_tiles;
+  p.b_k_wrap = kw == K ? 0 : kw;
 
   CUtensorMap ta, tb, tout;
   {
@@ -673,14 +674,14 @@ extern "C" int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t l
     if (!make_tmap_bf16(&ta, a, 2, dims, strides, box)) return FX_ERR_CUDA;
   }
   {
-    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t dims[2] = {static_cast<uint64_t>(kw), static_cast<uint64_t>(N)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
     const uint32_t box[2] = {kBK, static_cast<uint32_t>(bn)};
     if (!make_tmap_bf16(&tb, w, 2, dims, strides, box)) return FX_ERR_CUDA;
   }
   CUtensorMap tb128 = tb;
   if (use_pair_kernel(M, N, bn)) {  // each CTA of a pair stages a 128-row half of the 256-wide B panel
-    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t dims[2] = {static_cast<uint64_t>(kw), static_cast<uint64_t>(N)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
     const uint32_t box[2] = {kBK, 128};
     if (!make_tmap_bf16(&tb128, w, 2, dims, strides, box)) return FX_ERR_CUDA;
@@ -697,11 +698,7 @@ extern "C" int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t l
   if (use_pair_kernel(M, N, bn)) {
     p.num_m_tiles = (M + 255) / 256;
     p.group_m = pair_group_m(N, K);
-    static int forced_span = -1;  // FX_GEMM_N_SPAN: experiments with the slab width of the rasterisation
-    if (forced_span < 0) {
-      const char* env = getenv("FX_GEMM_N_SPAN");
-      forced_span = env ? atoi(env) : 0;
-    }
+    const int forced_span = tune_get("gemm_n_span");  // FX_GEMM_N_SPAN / fx_tune: slab width of the rasterisation
     if (forced_span > 0 && forced_span < p.num_n_tiles) p.n_span = forced_span;
     // L2 eviction priorities of the operand loads, FX_GEMM_L2HINT=<a><b> (digits 0 normal, 1 evict_first, 2 evict_last)
     static int hint = -1;
@@ -720,4 +717,55 @@ extern "C" int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t l
     case 128: return dispatch_epi<128>(epilogue, ta, tb, tout, p, s);
     default: return dispatch_epi<64>(epilogue, ta, tb, tout, p, s);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32 linear on the tensor cores for the per-token embedding MLPs (time_embedding / time_projection :630-632 when
+// the timesteps are per token and mostly distinct — fg/bg edit masks, pipeline :686-690 — so de-duplication does not
+// help; the reference runs 1.56 TFLOP of SGEMM per sample there, :928-944). The fp32 input (optionally through SiLU)
+// is split exactly into `planes` bf16 planes (hi [+ mid [+ lo]]) written side by side as one [M, planes*K] matrix, and
+// ONE tcgen05 GEMM accumulates all planes against the bf16 weight (k-blocks wrap around the weight's K). planes = 2
+// keeps 16 significant bits of every input (relative error <= 2^-17), 3 is exact up to the accumulator.
+// ---------------------------------------------------------------------------------------------------------
+namespace fx {
+__global__ void split_planes_kernel(const float* in, long long ldi, int M, int K, int planes, int act_in,
+                                    __nv_bfloat16* out) {
+  const long long total = static_cast<long long>(M) * K;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total; i += stride) {
+    const long long m = i / K;
+    const int k = static_cast<int>(i - m * K);
+    float a = in[m * ldi + k];
+    if (act_in == 1) a = a / (1.f + expf(-a));  // SiLU
+    __nv_bfloat16* row = out + m * (static_cast<long long>(planes) * K) + k;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(a);
+    row[0] = hi;
+    if (planes > 1) {
+      const float r1 = a - __bfloat162float(hi);
+      const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+      row[K] = mid;
+      if (planes > 2) row[2 * K] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    }
+  }
+}
+}  // namespace fx
+
+extern "C" int fx_linear_f32_tc(const float* in, int64_t ldi, const void* w, int64_t ldw, const void* bias, float* out,
+                                int64_t ldo, int M, int N, int K, int act_in, int planes, void* planes_ws,
+                                void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(in && w && out && planes_ws, "fx_linear_f32_tc: null pointer");
+  FX_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % kBK == 0 && N % 8 == 0, "fx_linear_f32_tc: bad shape M=%d N=%d K=%d", M, N,
+               K);
+  FX_CHECK_ARG(planes >= 1 && planes <= 3 && (act_in == 0 || act_in == 1), "fx_linear_f32_tc: planes %d / act_in %d",
+               planes, act_in);
+  const long long total = static_cast<long long>(M) * K;
+  long long g = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  split_planes_kernel<<<static_cast<int>(g < cap ? g : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      in, ldi, M, K, planes, act_in, reinterpret_cast<__nv_bfloat16*>(planes_ws));
+  FX_CHECK_LAUNCH("fx_linear_f32_tc(split)");
+  return gemm_impl(planes_ws, static_cast<int64_t>(planes) * K, w, ldw, bias, out, ldo, M, N, planes * K, K,
+                   FX_EPI_F32_EXACT, nullptr, nullptr, 0, nullptr, stream);
 }

@@ -13,6 +13,13 @@ namespace fx {
 void set_error(const char* fmt, ...);
 int num_sms();  // SM count of the current device (cached per device)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a function: set once per (function, device
+// ordinal of the calling thread's current device), remembered under a mutex. Returns false (error text set) on failure.
+bool ensure_dyn_smem(const void* func, int bytes, const char* what);
+
+// Developer knobs (fx_tune / the FX_* environment variables read at first use): -1 = not set.
+int tune_get(const char* name);
+
 // bf16 tensor map with SWIZZLE_128B and a 64-element (128 B) innermost box.
 // dims/strides are innermost-first; strides in BYTES for dims 1..rank-1.
 bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

@@ -213,6 +213,14 @@ class Parallel:
             out.copy_(torch.cat(parts, 0))
         return out
 
+    def fetch_from_last_cfg_rank(self, local: torch.Tensor) -> torch.Tensor:
+        """Replace ``local`` by the same-shaped tensor of the LAST rank of this rank's CFG group (the cond branch):
+        TeaCache residuals when cfg_skip turns CFG-branch parallelism off mid-run (NativeEngine._teacache_residual)."""
+        src = self.layout.cfg_ranks(self.layout.sp_rank)[-1]
+        buf = local.clone()
+        dist.broadcast(buf, src=src, group=self.cfg_group)
+        return buf
+
     def gather_cfg(self, local: torch.Tensor) -> torch.Tensor:
         """[b, ...] -> [cfg_size*b, ...] ordered by cfg_rank (uncond first, as the sampler built the batch)."""
         Cg = self.layout.cfg_size

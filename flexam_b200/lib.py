@@ -35,6 +35,8 @@ SIGNATURES = {
     "fx_unpatchify": [_vp, _i64, _vp, _i, _i, _i, _i, _vp],
     "fx_sinusoid": [_vp, _vp, _i, _i, _vp],
     "fx_linear_f32": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
+    "fx_linear_f32_tc": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp],
+    "fx_dedup_f32": [_vp, _i, _i, _vp, _vp, _vp, _vp],
     "fx_nchw_to_nhwc": [_vp, _vp, _i64, _i, _i, _i64, _vp],
     "fx_im2col3x3": [_vp, _vp, _i, _i, _i, _i, _vp],
     "fx_groupnorm_silu": [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -42,6 +44,8 @@ SIGNATURES = {
     "fx_swap01_bf16": [_vp, _i64, _vp, _i, _i, _i, _vp],
     "fx_add_f32": [_vp, _vp, _i64, _vp],
     "fx_sub_f32": [_vp, _vp, _vp, _i64, _vp],
+    "fx_fingerprint": [_vp, _vp, _i, _i, _vp, _vp],
+    "fx_tune": [C.c_char_p, _i],
     "fx_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "fx_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
     # fp32 verification mode (flexam_b200/precise.py)

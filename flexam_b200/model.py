@@ -13,6 +13,7 @@ rows) happens once per weight version and is re-done if a parameter is edited in
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Dict, List, Optional, Sequence
 
@@ -124,6 +125,13 @@ class NativeEngine:
         self._versions = None
         self.launches = 0              # kernels launched by the last forward (bench.py reports it)
         self.timing = None             # list -> per-launch CUDA events for the GEMM / attention families
+        # Per-call checks that need ONE device->host read (weight fingerprint, content of the step-invariant inputs,
+        # number of distinct timesteps). A host that vouches for all three (DenoiseLoop after its first step) sets
+        # `trusted` and passes `t_dedup`: the forward then enqueues without any host synchronisation.
+        self.trusted = False
+        self.max_table_timesteps = 64  # more distinct per-token timesteps than this: per-token modulation path
+        self.mlp_planes = 2            # bf16 planes of the fp32 input in the tensor-core time MLP (per-token path)
+        self.host_reads = 0            # device->host reads of the last forward (tests / bench)
         self._pack()
 
     # -- weights -------------------------------------------------------------------------------------------
@@ -165,6 +173,11 @@ class NativeEngine:
         self.head_dmod = P["head.modulation_density"][0, 0].to(f32).contiguous()
         self._versions = self._pvers()
         self._static_key = None
+        # sampled fingerprint of every parameter as packed: `param.data += ...` edits (merge_lora) bump no version counter
+        self._fp_table = ops.fingerprint_table(list(P.values()))
+        self._fp_ref = ops.fingerprint(self._fp_table, self.FP_STRIDE) if self._fp_table is not None else None
+
+    FP_STRIDE = 64   # every 64th 16-byte word: ~160 MB read for the 5 B-parameter model, a dense edit hits every sample
 
     def refresh_if_modified(self):
         if self._pvers() != self._versions:
@@ -177,6 +190,12 @@ class NativeEngine:
         FlexAM/utils/lora_utils.py:481-485, :595-599): hosts call ``flexam_b200.model.refresh(module)`` after those."""
         if params is not None:
             self.params = params
+            dev = next(iter(params.values())).device
+            if dev != self.device:      # engine created before module.to(device): follow the parameters
+                self.device = dev
+                self.freqs = self.freqs.to(dev)
+                self._ws.clear()
+                self._static, self._static_key = {}, None
         self._pack()
 
     def _storage_ids(self):
@@ -217,6 +236,8 @@ class NativeEngine:
     def _embed_mlp(self, pe: str, pp: str, values: torch.Tensor):
         """fp32 sinusoid -> Linear -> SiLU -> Linear (= e) -> SiLU -> Linear (= e0) on `values` [n]. (:928-955)"""
         P = self.params
+        if values.numel() > 16:     # the weight-streaming kernel re-reads the weights every 4 rows: tensor cores instead
+            return self._embed_mlp_tokens(values, pe, pp)
         emb = ops.sinusoid(values, self.cfg["freq_dim"])
         h = ops.linear_f32(emb, P[pe + ".0.weight"], P[pe + ".0.bias"], 0)
         e = ops.linear_f32(h, P[pe + ".2.weight"], P[pe + ".2.bias"], 1)
@@ -286,38 +307,45 @@ class NativeEngine:
     def _ident(ts) -> tuple:
         return tuple((t.data_ptr(), t._version, tuple(t.shape), t.stride(), t.dtype) for t in ts)
 
-    @staticmethod
-    def _same_content(a_list, b_list) -> bool:
-        return bool(torch.stack([(a == b).all() for a, b in zip(a_list, b_list)]).all().item())   # one D2H read
-
-    def _static_hit(self, srcs) -> bool:
-        """True when every step-invariant input is unchanged since the cached results were computed.
-
-        Fast path, no device work: the very same storage at the same version. This is sound only because the engine
-        keeps a reference to the tensors it saw (``refs``), so the caching allocator cannot hand their addresses to
-        other data in the meantime. Otherwise the contents are compared on the device against private copies (one
-        small D2H read): a fresh tensor with the same values - the sampler's per-step ``torch.cat`` - still hits."""
+    def _static_probe(self, srcs):
+        """State of the step-invariant cache for these inputs: "hit" (the very same storages at the same version —
+        sound only because the engine keeps references to the tensors it saw, so the caching allocator cannot recycle
+        their addresses), "miss", or a 0-dim device tensor that is 1 when the CONTENTS equal the private copies (a
+        fresh tensor with the same values, the sampler's per-step ``torch.cat``, still hits; read by _read_facts)."""
         key = self._static_key
         if key is None:
-            return False
+            return "miss"
         ident, refs, copies = key
         if ident == self._ident(srcs):
-            return True
-        if len(copies) != len(srcs) or any(a.shape != b.shape for a, b in zip(copies, srcs)):
-            return False
-        if not self._same_content(copies, srcs):
-            return False
-        self._static_key = (self._ident(srcs), list(srcs), copies)    # same values at a new address: follow them
-        return True
+            return "hit"
+        if self.trusted or len(copies) != len(srcs) or any(a.shape != b.shape for a, b in zip(copies, srcs)):
+            return "miss"
+        return torch.stack([(a == b).all() for a, b in zip(copies, srcs)]).all()
+
+    def _read_facts(self, facts: dict) -> dict:
+        """ONE device->host copy for every data-dependent fact of this call (0-dim device tensors -> Python ints)."""
+        dev_items = [(k, v) for k, v in facts.items() if torch.is_tensor(v)]
+        out = {k: v for k, v in facts.items() if not torch.is_tensor(v)}
+        if dev_items:
+            vals = torch.stack([v.reshape(()).to(torch.int64) for _, v in dev_items]).tolist()
+            self.host_reads += 1
+            out.update({k: int(x) for (k, _), x in zip(dev_items, vals)})
+        return out
 
     # -- the denoising step ----------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, x, t, context, seq_len, y, full_ref, additional_control, density,
-                block_hook=None, teacache=None, cond_flag=True) -> torch.Tensor:
-        """Returns the stacked prediction [B, out_dim, F, H, W] in bf16 (forward :817-1123)."""
+                block_hook=None, teacache=None, cond_flag=True, t_dedup=None, teacache_decision=None) -> torch.Tensor:
+        """Returns the stacked prediction [B, out_dim, F, H, W] in bf16 (forward :817-1123).
+
+        ``t_dedup=(uniq [U] f32, inv [B, L0] int32)``: the caller already knows the distinct per-token timesteps (the
+        sampling loop: t = mask * t_step with a constant mask); ``teacache_decision``: the caller precomputed the
+        TeaCache decision of this step (it depends on the timestep embedding only). With both, and ``trusted`` set,
+        the call enqueues without a single host synchronisation (DenoiseLoop, CUDA-graph capturable)."""
         cfg, D, dev = self.cfg, self.D, self.device
         self.refresh_if_modified()
         self.launches = 0
+        self.host_reads = 0
         if y is None or full_ref is None or additional_control is None or density is None:
             raise FlexamNativeError("the FlexAM path needs y, full_ref, additional_control and density")
         C = cfg["out_dim"]
@@ -331,12 +359,16 @@ class NativeEngine:
 
         # ---- partitioning (flexam_b200/dist.py): CFG rows, then a token slice per sequence-parallel rank ------
         par = self.par
-        cfg_split = par is not None and par.layout.cfg_size > 1 and x.shape[0] % par.layout.cfg_size == 0
+        B_all = x.shape[0]
+        cfg_split = par is not None and par.layout.cfg_size > 1 and B_all % par.layout.cfg_size == 0
+        row_lo = 0
         if cfg_split:
-            nb = x.shape[0] // par.layout.cfg_size
-            lo = par.layout.cfg_rank * nb
-            x, y, add, full_ref, t, density = (u[lo:lo + nb] for u in (x, y, add, full_ref, t, density))
-            context = context[lo:lo + nb]
+            nb = B_all // par.layout.cfg_size
+            row_lo = par.layout.cfg_rank * nb
+            x, y, add, full_ref, t, density = (u[row_lo:row_lo + nb] for u in (x, y, add, full_ref, t, density))
+            context = context[row_lo:row_lo + nb]
+            if t_dedup is not None:
+                t_dedup = (t_dedup[0], t_dedup[1][row_lo:row_lo + nb])
         P = par.layout.sp_size if par is not None else 1
         sp_rank = par.layout.sp_rank if par is not None else 0
 
@@ -347,19 +379,53 @@ class NativeEngine:
         L = L0 + R
         if seq_len != L0:
             raise FlexamNativeError(f"seq_len {seq_len} != tokens on the grid {L0} (padding is handled by the SP layer)")
+        if max(F + 1, Hp, Wp) > self.freqs.shape[0]:
+            raise FlexamNativeError(f"latent grid ({F + 1},{Hp},{Wp}) exceeds the {self.freqs.shape[0]}-position RoPE table")
         grid = (F + 1, Hp, Wp)
         Lp = -(-L // P)            # tokens per SP rank; the tail of the last rank may be padding (:919-920)
         L_pad = Lp * P
         tok0 = sp_rank * Lp
         M = B * Lp
 
-        # ---- step-invariant work: control fuser, context embedding, cross-attention K/V ----------------------
-        # Cached across calls only when the inputs they derive from are unchanged, judged by CONTENT against private
-        # copies (a fresh tensor per step with the same values, as the sampler's per-step torch.cat produces, hits;
-        # a different clip that the caching allocator happens to place at the same address misses). One tiny D2H
-        # read per step, next to the one torch.unique below already needs.
+        # ---- data-dependent facts of this call, gathered with ONE device->host read ---------------------------
+        # (a) weights edited behind the version counters (merge_lora's `weight.data += ...`): sampled fingerprint;
+        # (b) step-invariant inputs unchanged (by content) -> reuse control fuser / context / cross K/V;
+        # (c) number of distinct per-token timesteps -> modulation-table path or per-token path.
+        facts = {}
         srcs = [y, add] + list(context)
-        if not (self.cache_static and self._static_hit(srcs)):
+        if not self.trusted and self._fp_table is not None:
+            facts["weights_same"] = (ops.fingerprint(self._fp_table, self.FP_STRIDE) == self._fp_ref).all()
+            self.launches += 1
+        facts["static"] = self._static_probe(srcs) if self.cache_static else "miss"
+        per_token = t.dim() == 2
+        if per_token:
+            if t.shape[1] < L:   # ref tokens are PREPENDED and take the last token's timestep (:900-904)
+                t = torch.cat([t[:, -1:].expand(B, L - t.shape[1]), t], dim=1)
+            t = t.contiguous()
+            if t_dedup is not None:
+                uniq, inv0 = t_dedup
+                uniq = uniq.to(dev, f32).contiguous()
+                inv0 = inv0.to(dev, i32)
+                if inv0.shape[1] < L:
+                    inv0 = torch.cat([inv0[:, -1:].expand(B, L - inv0.shape[1]), inv0], dim=1)
+                inv = inv0.contiguous().view(-1)
+                facts["n_uniq"] = int(uniq.numel())
+            else:
+                cap = self.max_table_timesteps
+                uniq = self._buf("t_uniq", (cap,), f32)
+                inv = self._buf("t_inv", (B * L,), i32)
+                cnt = self._buf("t_count", (1,), i32)
+                ops.dedup_f32(t.view(-1), cap, uniq, inv, cnt)
+                self.launches += 1
+                facts["n_uniq"] = cnt[0]
+        facts = self._read_facts(facts)
+        if not facts.get("weights_same", 1):
+            self._pack()                   # re-derive the packed copies, drop everything cached from the old weights
+            facts["static"] = "miss"
+        static_hit = facts["static"] == "hit" or facts["static"] == 1
+
+        # ---- step-invariant work: control fuser, context embedding, cross-attention K/V ----------------------
+        if not static_hit:
             st = {}
             st["cnn"] = [self._cnn_fuser(y[b, :C], add[b]) for b in range(B)]
             st["ctx"] = self._context(context)
@@ -367,6 +433,8 @@ class NativeEngine:
             self._static = st
             self._static_key = ((self._ident(srcs), list(srcs), [u.clone() for u in srcs])
                                 if self.cache_static else None)
+        elif facts["static"] == 1:         # same values at a new address: follow them
+            self._static_key = (self._ident(srcs), list(srcs), self._static_key[2])
         st = self._static
 
         # ---- patch + ref embedding straight into the fp32 residual stream (:885-899) --------------------------
@@ -386,21 +454,36 @@ class NativeEngine:
         if P > 1:   # keep this rank's token slice (torch.chunk(x, P, dim=1)[rank], :971-975)
             xs.view(B, Lp, D).copy_(x_full.view(B, L_pad, D)[:, tok0:tok0 + Lp])
 
-        # ---- timestep / density embeddings on the distinct timesteps (:900-955) ------------------------------
-        if t.dim() == 2:
-            if t.shape[1] < L:   # ref tokens are PREPENDED and take the last token's timestep (:900-904)
-                t = torch.cat([t[:, -1:].expand(B, L - t.shape[1]), t], dim=1)
-            uniq, inv = torch.unique(t.reshape(-1), return_inverse=True)
-            idx_full = inv.to(i32).view(B, L)
-        else:
-            uniq = t.contiguous()
-            idx_full = torch.arange(B, device=dev, dtype=i32).view(B, 1).expand(B, L)
-        last_idx = idx_full[:, -1].long()
-        if L_pad != L:           # padding rows reuse the last token's timestep (:931-935)
-            idx_full = torch.cat([idx_full, idx_full[:, -1:].expand(B, L_pad - L)], dim=1)
-        row_idx = idx_full[:, tok0:tok0 + Lp].contiguous().view(-1)
-        e, e0 = self._embed_mlp("time_embedding", "time_projection", uniq.contiguous())          # [U,D], [U,6D]
+        # ---- timestep / density embeddings (:900-955) --------------------------------------------------------
+        # table mode: the fp32 MLPs run on the DISTINCT timesteps and the block LayerNorms read rows combined once per
+        #             (timestep, sample); token mode (many distinct per-token values): the MLPs run per token of this
+        #             rank's slice on the tensor cores and LayerNorm / gates read the per-token e0 (:444-446).
+        token_mode = per_token and facts["n_uniq"] > self.max_table_timesteps
         de, de0 = self._embed_mlp("density_embedding", "density_projection", density.contiguous())
+        de0v = de0.view(B, 2, D)
+        if token_mode:
+            t_pad = t if L_pad == L else torch.cat([t, t[:, -1:].expand(B, L_pad - L)], dim=1)   # :931-935
+            t_loc = t_pad[:, tok0:tok0 + Lp].contiguous().view(-1)
+            e, e0 = self._embed_mlp_tokens(t_loc)                                   # [M, D], [M, 6D]
+            row_idx = self._arange(M)
+            e_last, e0_last = self._embed_mlp("time_embedding", "time_projection", t[:, -1].contiguous())
+            mod_inp = e0_last.view(B, 6, D)
+        else:
+            if per_token:
+                U = facts["n_uniq"]
+                uniq = uniq[:U]
+                idx_full = inv.view(B, L)
+            else:
+                uniq = t.contiguous()
+                U = uniq.shape[0]
+                idx_full = torch.arange(B, device=dev, dtype=i32).view(B, 1).expand(B, L)
+            last_idx = idx_full[:, -1].long()
+            if L_pad != L:           # padding rows reuse the last token's timestep (:931-935)
+                idx_full = torch.cat([idx_full, idx_full[:, -1:].expand(B, L_pad - L)], dim=1)
+            row_idx = idx_full[:, tok0:tok0 + Lp].contiguous().view(-1)
+            e, e0 = self._embed_mlp("time_embedding", "time_projection", uniq.contiguous())      # [U,D], [U,6D]
+            mod_inp = None
+        e0v = e0.view(-1, 6, D)
 
         # ---- 30 x WanAttentionBlock (:422-472) ---------------------------------------------------------------
         h = self._buf("h", (M, D), bf16)
@@ -418,33 +501,42 @@ class NativeEngine:
         qkv5 = qkv.view(B, Lp, 3, self.H, 128)
         attn4 = attn.view(B, Lp, self.H, 128)
         cq4 = cq.view(B, Lp, self.H, 128)
-        e0v = e0.view(-1, 6, D)
-        de0v = de0.view(B, 2, D)
-        # the block LayerNorms read modulation rows combined once per (distinct timestep, sample): row u*B + b
-        U = e0v.shape[0]
-        row_idx2 = (row_idx.view(B, Lp) * B + torch.arange(B, device=dev, dtype=i32).view(B, 1)).view(-1)
-        modtab = self._buf("modtab", (2, U * B, 2, D), f32)
+        if not token_mode:
+            # the block LayerNorms read modulation rows combined once per (distinct timestep, sample): row u*B + b
+            row_idx2 = (row_idx.view(B, Lp) * B + torch.arange(B, device=dev, dtype=i32).view(B, 1)).view(-1)
+            modtab = self._buf("modtab", (2, U * B, 2, D), f32)
 
         # ---- TeaCache (:977-1051): skip the block stack and re-apply the previous residual when the modulated
         #      timestep embedding moved little. The decision uses the GLOBAL last token so all SP ranks agree.
         run_blocks = True
         ori = None
         if teacache is not None:
-            # this package's TeaCache has decide()/step_done(); the reference's own class (an installed module whose
-            # pipeline called the reference's enable_teacache) has the same state and is driven through the functions
-            run_blocks = (teacache.decide(e0v[last_idx], cond_flag) if hasattr(teacache, "decide")
-                          else _tc.decide(teacache, e0v[last_idx], cond_flag))
+            if teacache_decision is not None:            # precomputed by the sampling loop (depends on t only)
+                run_blocks = bool(teacache_decision)
+                if cond_flag:
+                    teacache.should_calc = run_blocks
+            else:
+                # this package's TeaCache has decide()/step_done(); the reference's own class (an installed module whose
+                # pipeline called the reference's enable_teacache) has the same state and is driven through the functions
+                inp = mod_inp if mod_inp is not None else e0v[last_idx]
+                run_blocks = (teacache.decide(inp, cond_flag) if hasattr(teacache, "decide")
+                              else _tc.decide(teacache, inp, cond_flag))
+                self.host_reads += 1 if cond_flag else 0
             if not run_blocks:
-                prev = teacache.previous_residual_cond if cond_flag else teacache.previous_residual_uncond
-                ops.add_(xs, prev[-M:].contiguous())
+                prev = self._teacache_residual(teacache, cond_flag, B, M, cfg_split)
+                ops.add_(xs, prev)
                 self.launches += 1
             else:
                 ori = xs.clone()
         for i, w in enumerate(self.blk if run_blocks else ()):
             mod, dmod = w["mod"], w["dmod"]
-            ops.modulation_tables(mod, dmod, e0v, de0v, modtab)
             # self-attention
-            ops.ln_scale_shift(xs, h, self.eps, modtab[0, :, 0], modtab[0, :, 1], 2 * D, row_idx2)
+            if token_mode:
+                ops.ln_modulate(xs, h, self.eps, mod[0], mod[1], e0v[:, 0], e0v[:, 1], 6 * D, row_idx, dmod[0],
+                                de0v[:, 0], 2 * D, Lp)
+            else:
+                ops.modulation_tables(mod, dmod, e0v, de0v, modtab)
+                ops.ln_scale_shift(xs, h, self.eps, modtab[0, :, 0], modtab[0, :, 1], 2 * D, row_idx2)
             self._gemm(h, w["wqkv"], w["bqkv"], qkv, FX_EPI_BF16)
             if fused_sp:    # Ulysses with the exchange fused into the norm/rope and attention kernels (peer stores)
                 par.attention_fused(qkv, attn_sym, w["nq"], w["nk"], self.eps, self.freqs, grid, L, scale, ops,
@@ -465,10 +557,14 @@ class NativeEngine:
             self._fmha(cq4, kv5[:, :, 0], kv5[:, :, 1], attn4, scale)
             self._gemm(attn, w["cwo"], w["cbo"], xs, FX_EPI_RESID_F32)
             # ffn
-            ops.ln_scale_shift(xs, h, self.eps, modtab[1, :, 0], modtab[1, :, 1], 2 * D, row_idx2)
+            if token_mode:
+                ops.ln_modulate(xs, h, self.eps, mod[3], mod[4], e0v[:, 3], e0v[:, 4], 6 * D, row_idx, dmod[1],
+                                de0v[:, 1], 2 * D, Lp)
+            else:
+                ops.ln_scale_shift(xs, h, self.eps, modtab[1, :, 0], modtab[1, :, 1], 2 * D, row_idx2)
             self._gemm(h, w["w1"], w["b1"], ffn, FX_EPI_GELU_BF16)
             self._gemm(ffn, w["w2"], w["b2"], xs, FX_EPI_RESID_F32, gate_mod=mod[5], gate_e=e0v[:, 5], row_idx=row_idx)
-            self.launches += 6
+            self.launches += 5 if token_mode else 6
             if block_hook is not None:
                 block_hook(i, xs)
         if teacache is not None and run_blocks:
@@ -479,6 +575,8 @@ class NativeEngine:
                 teacache.previous_residual_cond = res
             else:
                 teacache.previous_residual_uncond = res
+            # which rows of the caller's batch this residual covers (cfg-parallel ranks hold one branch each)
+            teacache._fx_rows = (row_lo, row_lo + B, B_all if cfg_split else B)
 
         # ---- head (:493-507, uses e not e0) + unpatchify (:1106-1149) -----------------------------------------
         ops.ln_modulate(xs, h, self.eps, self.head_mod[0], self.head_mod[1], e, e, D, row_idx, self.head_dmod, de, D, Lp)
@@ -494,6 +592,52 @@ class NativeEngine:
         if teacache is not None:
             teacache.step_done(cond_flag) if hasattr(teacache, "step_done") else _tc.step_done(teacache, cond_flag)
         return out
+
+    def _teacache_residual(self, teacache, cond_flag: bool, B: int, M: int, cfg_split: bool) -> torch.Tensor:
+        """The residual the reference adds on a skipped step: ``previous_residual[-x.size(0):]`` (:1003-1006), i.e. the
+        LAST B rows of the batch that was stored. Under CFG-branch parallelism every rank stored only its own branch
+        (cfg_rank 0 = uncond); when the batch later shrinks to the cond half (cfg_skip) the split is off and every rank
+        needs the COND rows, which live on the last cfg rank: fetched once from that peer (all ranks take this path
+        together, the decision depends on the timestep only), then kept locally."""
+        prev = teacache.previous_residual_cond if cond_flag else teacache.previous_residual_uncond
+        lo, hi, total = getattr(teacache, "_fx_rows", (0, prev.shape[0] // max(M // B, 1), prev.shape[0] // max(M // B, 1)))
+        stored_split = total > hi - lo
+        if stored_split and not cfg_split:
+            par = self.par
+            if par is None or B > hi - lo:
+                raise FlexamNativeError("TeaCache: cached residual was stored under a CFG-parallel layout that does not "
+                                        "cover the rows needed now; disable TeaCache or keep the layout fixed")
+            prev = par.fetch_from_last_cfg_rank(prev.contiguous())
+            if cond_flag:
+                teacache.previous_residual_cond = prev
+            else:
+                teacache.previous_residual_uncond = prev
+            teacache._fx_rows = (total - (hi - lo), total, hi - lo)     # now a local, unsplit record of the last rows
+        return prev[-M:].contiguous()
+
+    def _arange(self, n: int) -> torch.Tensor:
+        t = self._ws.get(("arange", n))
+        if t is None:
+            t = torch.arange(n, device=self.device, dtype=i32)
+            self._ws[("arange", n)] = t
+        return t
+
+    def _embed_mlp_tokens(self, t_rows: torch.Tensor, pe: str = "time_embedding", pp: str = "time_projection"):
+        """time_embedding / time_projection (:928-944) for MANY rows (per-token timesteps that do not de-duplicate):
+        fp32 inputs split into bf16 planes, contractions on tcgen05 (fx_linear_f32_tc). t_rows: [M] f32 ->
+        e [M, D], e0 [M, 6D] fp32."""
+        P, D, Mr = self.params, self.D, t_rows.numel()
+        emb = ops.sinusoid(t_rows, self.cfg["freq_dim"])
+        ws = self._buf("mlp_planes", (Mr * self.mlp_planes * max(D, self.cfg["freq_dim"]),), bf16)
+        h1 = ops.linear_f32_tc(emb, P[pe + ".0.weight"], P[pe + ".0.bias"], 0, self.mlp_planes,
+                               self._buf("mlp_h1", (Mr, D), f32), ws)
+        e = ops.linear_f32_tc(h1, P[pe + ".2.weight"], P[pe + ".2.bias"], 1, self.mlp_planes,
+                              self._buf("mlp_e", (Mr, D), f32), ws)
+        w3 = P[pp + ".1.weight"]
+        e0 = ops.linear_f32_tc(e, w3, P[pp + ".1.bias"], 1, self.mlp_planes,
+                               self._buf("mlp_e0", (Mr, w3.shape[0]), f32), ws)
+        self.launches += 7
+        return e, e0
 
     def _swap01(self, src, out):
         self.launches += 1
@@ -625,7 +769,47 @@ class Wan2_2Transformer3DModel_FlexAM(nn.Module):
                 print(key, "Size don't match, skip")
         missing, unexpected = model.load_state_dict(kept, strict=False)
         print(f"### missing keys: {len(missing)}; \n### unexpected keys: {len(unexpected)};")
+        if missing:     # the reference constructor ran init_weights() (:1151-1188); torch.empty storage is not a value
+            model.init_missing_(missing)
+            print("### initialised like the reference's init_weights (not in the checkpoint): " + ", ".join(missing))
         return model.to(torch_dtype)
+
+    @torch.no_grad()
+    def init_missing_(self, keys) -> None:
+        """Values the reference gives parameters that no checkpoint tensor overwrote (init_weights :1151-1188 and the
+        module constructors): Linear weights Xavier-uniform with zero bias, text / time embedding weights N(0, 0.02),
+        density MLPs and ``head.head.weight`` ZERO (a base Wan2.2 checkpoint therefore loads as a no-op for the FlexAM
+        additions), modulation rows N(0,1)/sqrt(dim) (:419-420, :490-491), norm weights 1 / biases 0, convolutions with
+        torch's default (Kaiming-uniform) initialisation."""
+        own = dict(self.named_parameters())
+        D = self.config["dim"]
+        for k in keys:
+            p = own[k]
+            leaf = k.rsplit(".", 1)[-1]
+            if k.startswith(("density_embedding", "density_projection")) or k == "head.head.weight":
+                p.zero_()
+            elif "modulation" in leaf:
+                p.copy_(torch.randn(p.shape) / D ** 0.5)
+            elif "norm" in k and leaf == "weight" or (k.startswith("cnn_conv") and ".1.weight" in k):
+                p.fill_(1.0)
+            elif leaf == "bias" and ("conv" not in k or ".1.bias" in k):
+                p.zero_()
+            elif k.startswith(("text_embedding", "time_embedding")) and leaf == "weight":
+                p.copy_(torch.randn(p.shape) * 0.02)
+            elif p.dim() == 2:                                   # nn.Linear
+                w = torch.empty(p.shape)
+                nn.init.xavier_uniform_(w)
+                p.copy_(w)
+            elif leaf == "weight":                               # patch_embedding / ref_conv / cnn convolutions
+                w = torch.empty(p.shape)
+                if k == "patch_embedding.weight":
+                    nn.init.xavier_uniform_(w.flatten(1))
+                else:
+                    nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+                p.copy_(w)
+            else:                                                # conv bias: U(-1/sqrt(fan_in), 1/sqrt(fan_in))
+                fan_in = own[k[:-4] + "weight"][0].numel()
+                p.copy_((torch.rand(p.shape) * 2 - 1) / math.sqrt(fan_in))
 
     # -- feature toggles with the reference's names (:730-815) -----------------------------------------------
     def enable_cfg_skip(self, cfg_skip_ratio, num_steps):
@@ -688,14 +872,21 @@ def native_forward(self, x, t, context, seq_len, clip_fea=None, y=None, y_camera
         h = bs // 2
         x, t, context, y, full_ref, additional_control, density = (
             x[h:], t[h:], context[h:], y[h:], full_ref[h:], additional_control[h:], density[h:])
+    loop_kw = dict(getattr(self, "_fx_loop_kwargs", None) or {})    # DenoiseLoop: known timestep structure / decisions
+    if skip and loop_kw.get("t_dedup") is not None:
+        loop_kw["t_dedup"] = (loop_kw["t_dedup"][0], loop_kw["t_dedup"][1][bs // 2:])
     eng = self.engine() if hasattr(self, "engine") else self._flexam_engine
     # parameters whose storage was replaced since the engine saw them (module.to(...), `param.data = ...`): adopt them
     if eng._storage_ids() != tuple(p.data_ptr() for p in self.parameters()):
         eng.refresh({k: v.detach() for k, v in self.named_parameters()})
     _sync_rope_table(self, eng)          # the module's `freqs` attribute is the source of truth (enable_riflex() etc.)
-    with ops.stream_scope():
+    # the kernels launch on the calling thread's CURRENT device and on torch's current stream of that device: make the
+    # module's device current for the whole call (a module on cuda:1 called while cuda:0 is current)
+    guard = torch.cuda.device(eng.device) if eng.device.type == "cuda" else contextlib.nullcontext()
+    with guard, ops.stream_scope():
         out = eng.forward(x, t, context, seq_len, y, full_ref, additional_control, density,
-                          teacache=getattr(self, "teacache", None), cond_flag=cond_flag)
+                          teacache=getattr(self, "teacache", None), cond_flag=cond_flag,
+                          **loop_kw)
     if skip:
         out = torch.cat([out, out], dim=0)
     return out

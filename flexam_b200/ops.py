@@ -243,6 +243,72 @@ def linear_f32(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], a
     return out
 
 
+def linear_f32_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act_in: int = 0, planes: int = 2,
+                  out: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 linear for many rows on the tensor cores (see fx_linear_f32_tc). ws: bf16 workspace >= M*planes*K."""
+    _req(x, f32, "linear_f32_tc.x"), _req(w, bf16, "linear_f32_tc.w")
+    if bias is not None:
+        _req(bias, bf16, "linear_f32_tc.bias")
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=f32, device=x.device)
+    _req(out, f32, "linear_f32_tc.out")
+    if ws is None:
+        ws = torch.empty((M, planes * K), dtype=bf16, device=x.device)
+    _req(ws, bf16, "linear_f32_tc.ws")
+    if ws.numel() < M * planes * K or not ws.is_contiguous() or out.shape != (M, N):
+        raise _l.FlexamNativeError("linear_f32_tc: workspace too small / not contiguous, or out shape mismatch")
+    st = _l.load().fx_linear_f32_tc(_p(x), x.stride(0), _p(w), w.stride(0), _p(bias), _p(out), out.stride(0), M, N, K,
+                                    act_in, planes, _p(ws), _stream())
+    _l.check(st, "fx_linear_f32_tc")
+    return out
+
+
+def dedup_f32(t: torch.Tensor, cap: int, uniq: torch.Tensor, inv: torch.Tensor, count: torch.Tensor) -> None:
+    """Distinct values of the flat fp32 tensor t (first-appearance order, at most cap) without a host sync."""
+    _req(t, f32, "dedup_f32.t"), _req(uniq, f32, "dedup_f32.uniq"), _req(inv, i32, "dedup_f32.inv")
+    _req(count, i32, "dedup_f32.count")
+    if not t.is_contiguous() or uniq.numel() < cap or inv.numel() < t.numel():
+        raise _l.FlexamNativeError("dedup_f32: contiguous t and uniq[cap], inv[n] required")
+    _l.check(_l.load().fx_dedup_f32(_p(t), t.numel(), cap, _p(uniq), _p(inv), _p(count), _stream()), "fx_dedup_f32")
+
+
+class FingerprintTable:
+    """Device arrays (addresses, byte sizes) of a fixed list of tensors; keeps the tensors alive."""
+
+    def __init__(self, tensors):
+        self.tensors = list(tensors)
+        for t in self.tensors:
+            if not t.is_cuda or not t.is_contiguous() or t.data_ptr() % 16 != 0:
+                raise _l.FlexamNativeError("fingerprint_table: contiguous, 16-byte aligned CUDA tensors required")
+        dev = self.tensors[0].device
+        self.ptrs = torch.tensor([t.data_ptr() for t in self.tensors], dtype=torch.int64, device=dev)
+        self.nbytes = torch.tensor([t.numel() * t.element_size() for t in self.tensors], dtype=torch.int64, device=dev)
+
+
+def fingerprint_table(tensors) -> Optional[FingerprintTable]:
+    """None for CPU tensors: an engine may be built before ``module.to('cuda')`` (the reference pipelines do); nothing
+    native can run on them, and the table is rebuilt when the parameters arrive on the device."""
+    tensors = list(tensors)
+    if not tensors or not tensors[0].is_cuda:
+        return None
+    return FingerprintTable(tensors)
+
+
+def fingerprint(table: FingerprintTable, stride: int) -> torch.Tensor:
+    """int64 [n]: sampled hash-sum of every tensor of the table (see fx_fingerprint); a fresh tensor per call."""
+    n = table.ptrs.numel()
+    out = torch.empty((n,), dtype=torch.int64, device=table.ptrs.device)
+    _l.check(_l.load().fx_fingerprint(_p(table.ptrs), _p(table.nbytes), n, stride, _p(out), _stream()), "fx_fingerprint")
+    return out
+
+
+def tune(name: str, value: int) -> None:
+    """Developer knob by name (see fx_tune)."""
+    _l.check(_l.load().fx_tune(name.encode(), int(value)), "fx_tune")
+
+
 def nchw_to_nhwc(src: torch.Tensor, dst: torch.Tensor, c0: int) -> torch.Tensor:
     """src: bf16 [C, P] contiguous view; dst: bf16 [P, ld] receives columns [c0, c0+C)."""
     _req(src, bf16, "nchw_to_nhwc.src"), _req(dst, bf16, "nchw_to_nhwc.dst")

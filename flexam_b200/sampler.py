@@ -45,13 +45,20 @@ def flow_match_euler_schedule(num_inference_steps: int, shift: float = 5.0,
 class DenoiseLoop:
     """Device-resident state of one sampling run: fp32 master latents, the pinned first-frame latents, the latent
     mask and the step-invariant control tensors (batch-of-2 copies built once, so the transformer's static cache —
-    CNN control fuser, text embedding, cross K/V — hits on every step after the first)."""
+    CNN control fuser, text embedding, cross K/V — hits on every step after the first).
+
+    After the first step the loop enqueues WITHOUT host synchronisation: the per-token timesteps are ``mask * t`` with
+    a constant mask, so their distinct values and inverse index are known up front (``t_dedup``); the TeaCache decisions
+    depend on the timestep embedding only and are computed for all steps before the loop (one read-back,
+    ``teacache_schedule``); the engine is told that weights and control inputs cannot change inside the loop
+    (``trusted``). ``graph=True`` additionally captures the transformer call of each (batch size, run / skip) variant
+    in a CUDA graph at its second occurrence and replays it afterwards (single-GPU engines only)."""
 
     def __init__(self, transformer, latents: torch.Tensor, mask: torch.Tensor, masked_video_latents: torch.Tensor,
                  mask_latents: torch.Tensor, control_video_latents: torch.Tensor,
                  additional_control_latents: torch.Tensor, ref_image_latents: torch.Tensor,
                  negative_prompt_embeds: Sequence[torch.Tensor], prompt_embeds: Sequence[torch.Tensor],
-                 density: float, guidance_scale: float = 6.0):
+                 density: float, guidance_scale: float = 6.0, graph: bool = False):
         if latents.dim() != 5 or latents.shape[0] != 1:
             raise FlexamNativeError("DenoiseLoop: latents must be [1, C, F, H, W] (one video per loop, CFG batch 2)")
         self.tf = transformer
@@ -83,14 +90,114 @@ class DenoiseLoop:
         self.density = torch.full((2,), float(density), dtype=f32, device=dev)
         self.x_in = torch.empty((2,) + tuple(latents.shape[1:]), dtype=bf16, device=dev)
         self.launches = 0
+        self.host_reads = 0          # device->host reads made by the transformer calls of the last run()
+        # distinct mask factors and their inverse index: ONE read-back per loop instead of a torch.unique per step
+        vals, inv = torch.unique(self.tok_mask.float(), return_inverse=True)
+        self.mask_vals = vals.to(bf16)                                        # [U]
+        self.mask_inv = inv.to(torch.int32).view(1, -1).expand(2, -1).contiguous()   # [2, L0]
+        self.ts = torch.empty((2, self.seq_len), dtype=f32, device=dev)       # per-token timesteps of the current step
+        self.uniq = torch.empty((self.mask_vals.numel(),), dtype=f32, device=dev)
+        self.use_graph = bool(graph)
+        self._graphs = {}            # (batch, run_blocks) -> [occurrences, CUDAGraph | None, static output]
+        self.graph_replays = 0
+        self.decisions: List[bool] = []   # per step: did the block stack run (False = TeaCache re-applied the residual)
 
-    def step(self, i: int, t: float, sigma: float, sigma_next: float) -> None:
+    def _engine(self):
+        return self.tf.engine() if hasattr(self.tf, "engine") else self.tf._flexam_engine
+
+    def teacache_schedule(self, timesteps: Sequence[float]) -> Optional[List[bool]]:
+        """TeaCache decisions (:978-1000) of every step of the loop, before the loop: the decision input is the
+        timestep embedding ``e0`` of the LAST token, a function of ``mask[-1] * t_i`` and the weights only. One batched
+        pass of the fp32 time MLP over all steps and ONE read-back of the n-1 relative-L1 distances; the accumulate /
+        rescale / threshold recurrence then runs on the host exactly as the reference does."""
+        tc = getattr(self.tf, "teacache", None)
+        if tc is None:
+            return None
+        eng = self._engine()
+        n = len(timesteps)
+        t_last = torch.stack([(self.tok_mask[-1:] * float(t)).float() for t in timesteps]).view(-1)     # bf16 products
+        e0 = torch.cat([eng._embed_mlp("time_embedding", "time_projection", t_last[i:i + 16].contiguous())[1]
+                        for i in range(0, n, 16)])                                       # [n, 6D], fp32 kernel path
+        prev0 = tc.previous_modulated_input
+        if prev0 is not None and tc.cnt >= tc.num_skip_start_steps:
+            e0p = torch.cat([prev0.reshape(-1, e0.shape[1])[:1].to(e0), e0])
+        else:
+            e0p = torch.cat([e0[:1], e0])
+        d = ((e0p[1:] - e0p[:-1]).abs().mean(dim=1) / e0p[:-1].abs().mean(dim=1)).tolist()          # the one read-back
+        self.host_reads += 1
+        acc, cnt, out = float(tc.accumulated_rel_l1_distance), int(tc.cnt), []
+        for i in range(n):
+            if cnt < tc.num_skip_start_steps:
+                should, acc = True, 0.0
+            else:
+                acc += float(tc.rescale_func(d[i]))
+                if acc < tc.rel_l1_thresh:
+                    should = False
+                else:
+                    should, acc = True, 0.0
+            out.append(should)
+            cnt += 1
+            if cnt == tc.num_steps:        # the forward resets the cache there (:1119-1122)
+                acc, cnt = 0.0, 0
+        self._tc_final = (acc, e0[-1:].clone())
+        return out
+
+    def _call(self, decision: Optional[bool]):
+        eng = self._engine()
+        kw = {"t_dedup": (self.uniq, self.mask_inv)}
+        if decision is not None:
+            kw["teacache_decision"] = decision
+        self.tf._fx_loop_kwargs = kw
+        try:
+            return self.tf(x=self.x_in, context=self.context, t=self.ts, density=self.density, seq_len=self.seq_len,
+                           y=self.y, full_ref=self.full_ref, additional_control=self.add)
+        finally:
+            self.tf._fx_loop_kwargs = {}
+            self.host_reads += eng.host_reads
+
+    def _skipping_cfg(self, i: int) -> bool:
+        r = getattr(self.tf, "cfg_skip_ratio", None)
+        n = getattr(self.tf, "num_inference_steps", None)
+        return r is not None and n is not None and i >= n * (1 - r)
+
+    def step(self, i: int, t: float, sigma: float, sigma_next: float, decision: Optional[bool] = None) -> None:
         self.tf.current_steps = i                                            # :847 (cfg_skip reads it)
         self.x_in[0].copy_(self.lat[0])                                      # :852 torch.cat([latents] * 2), bf16
         self.x_in[1].copy_(self.lat[0])
-        ts = (self.tok_mask * float(t)).float().unsqueeze(0).expand(2, -1)   # :892-899 (seq_len == grid tokens)
-        pred = self.tf(x=self.x_in, context=self.context, t=ts, density=self.density, seq_len=self.seq_len,
-                       y=self.y, full_ref=self.full_ref, additional_control=self.add)
+        self.uniq.copy_((self.mask_vals * float(t)).float())                 # :892-899 distinct values of mask * t
+        self.ts.copy_((self.tok_mask * float(t)).float().unsqueeze(0).expand(2, -1))
+        eng = self._engine()
+        graphable = (self.use_graph and eng.par is None and eng.trusted and
+                     (decision is not None or getattr(self.tf, "teacache", None) is None))
+        if not graphable:
+            pred = self._call(decision)
+        else:
+            key = (1 if self._skipping_cfg(i) else 2, decision)
+            slot = self._graphs.setdefault(key, [0, None, None])
+            slot[0] += 1
+            if slot[0] == 1:                 # first occurrence: eager (allocates the engine's workspaces)
+                pred = self._call(decision)
+            else:
+                tc = getattr(self.tf, "teacache", None)
+                if slot[1] is None:          # second occurrence: capture (records, does not execute) ...
+                    state = (tc.cnt, tc.should_calc) if tc is not None else None
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        slot[2] = self._call(decision)
+                    slot[1] = g
+                    if tc is not None:       # the captured call ran the host bookkeeping once; the replay below is the step
+                        tc.cnt, tc.should_calc = state
+                slot[1].replay()             # ... then replay
+                self.graph_replays += 1
+                if tc is not None:           # host bookkeeping the captured forward would have done (:1119-1122)
+                    tc.should_calc = bool(decision)
+                    tc.cnt += 1
+                    if tc.cnt == tc.num_steps:
+                        tc.reset()
+                pred = slot[2]
+        tc_obj = getattr(self.tf, "teacache", None)
+        self.decisions.append(bool(decision) if decision is not None else
+                              (bool(tc_obj.should_calc) if tc_obj is not None else True))
         # :926-934 in one launch: v = vu + s (vc - vu); lat += (sigma' - sigma) v; lat = (1-m) pinned + m lat
         ops.cfg_euler_step(pred[0], pred[1], self.guidance, float(sigma_next) - float(sigma), self.lat,
                            self.mask_full, self.pinned if self.repin else None)
@@ -101,8 +208,22 @@ class DenoiseLoop:
         if len(sigmas) != len(timesteps) + 1:
             raise FlexamNativeError("DenoiseLoop.run: need one more sigma than timesteps (terminal sigma)")
         self.tf.num_inference_steps = len(timesteps)                         # :845
-        for i, t in enumerate(timesteps):
-            self.step(i, float(t), float(sigmas[i]), float(sigmas[i + 1]))
-            if callback is not None:
-                callback(i, self.lat)
+        self.host_reads = 0
+        self.decisions = []
+        eng = self._engine()
+        decisions = self.teacache_schedule(timesteps)
+        was_trusted = eng.trusted
+        try:
+            for i, t in enumerate(timesteps):
+                if i == 1:   # step 0 ran every per-call check (weights, control inputs); they cannot change inside the loop
+                    eng.trusted = True
+                self.step(i, float(t), float(sigmas[i]), float(sigmas[i + 1]),
+                          None if decisions is None else decisions[i])
+                if callback is not None:
+                    callback(i, self.lat)
+        finally:
+            eng.trusted = was_trusted
+        tc = getattr(self.tf, "teacache", None)
+        if tc is not None and decisions is not None and tc.cnt != 0:   # loop ended mid-schedule: leave a consistent state
+            tc.accumulated_rel_l1_distance, tc.previous_modulated_input = self._tc_final
         return self.lat.to(bf16)

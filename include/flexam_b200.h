@@ -134,6 +134,17 @@ int fx_unpatchify(const void* head, int64_t ldh, void* out, int C, int F, int H,
  *                  act_in: 0 none, 1 SiLU.  K % 8 == 0.
  */
 int fx_sinusoid(const float* t, float* out, int n, int dim, void* stream);
+/* fx_linear_f32_tc: the same fp32 linear for MANY rows (per-token timesteps that do not de-duplicate: fg/bg edit
+ *   masks, pipeline_wan2_2_fun_control_FlexAM.py:686-690, 891-898; the reference runs 1.56 TFLOP of SGEMM per sample
+ *   there, :928-944) on tcgen05: act_in(in) is split exactly into `planes` (1..3) bf16 planes hi [+ mid [+ lo]] written
+ *   side by side into planes_ws (bf16 [M, planes*K]) and ONE GEMM accumulates all planes against the bf16 weight.
+ *   planes = 2 keeps 16 significant bits of the input (relative error <= 2^-17). K % 64 == 0, N % 8 == 0.
+ * fx_dedup_f32: distinct values of t[n] in order of first appearance, at most cap (<= 64): uniq f32 [cap] (unused
+ *   tail = last value), inv int32 [n] (index into uniq), count int32 [1] = number found, cap + 1 = "more than cap"
+ *   (inv is then meaningless). Stream-ordered, no host synchronisation: replaces torch.unique on the step's path. */
+int fx_linear_f32_tc(const float* in, int64_t ldi, const void* w, int64_t ldw, const void* bias, float* out,
+                     int64_t ldo, int M, int N, int K, int act_in, int planes, void* planes_ws, void* stream);
+int fx_dedup_f32(const float* t, int n, int cap, float* uniq, int32_t* inv, int32_t* count, void* stream);
 int fx_linear_f32(const float* in, int64_t ldi, const void* w, int64_t ldw, const void* bias, float* out,
                   int64_t ldo, int M, int N, int K, int act_in, void* stream);
 
@@ -221,6 +232,17 @@ int fx_groupnorm_silu_f32(const float* x, int64_t P, int C, int G, float eps, co
 /* TeaCache residual bookkeeping on the fp32 token stream (:1003-1051): dst += src, out = a - b. */
 int fx_add_f32(float* dst, const float* src, int64_t n, void* stream);
 int fx_sub_f32(float* out, const float* a, const float* b, int64_t n, void* stream);
+
+/* Sampled fingerprint of n weight tensors (DEVICE arrays ptrs[n], nbytes[n]; every tensor 16-byte aligned): out[t] =
+ * order-free 64-bit hash-sum over every `stride`-th 16-byte word of tensor t. The host keeps the values taken when it
+ * packed / cached anything derived from those weights and compares later: edits that bypass torch's version counters
+ * (`weight.data += delta`, the reference's merge_lora / unmerge_lora, FlexAM/utils/lora_utils.py:481-485, :595-599)
+ * are dense, so any sample catches them. out: uint64 [n] (zeroed inside, stream-ordered). */
+int fx_fingerprint(const void* const* ptrs, const int64_t* nbytes, int n, int stride, uint64_t* out, void* stream);
+
+/* Developer knobs by name (the FX_<NAME> environment variables seed the same table at first use): "gemm_group_m",
+ * "gemm_n_span" (rasterisation of the CTA-pair GEMM; 0 / -1 = built-in choice). Not a compute-path switch. */
+int fx_tune(const char* name, int value);
 
 /* Small utility kernels used by the host glue. */
 int fx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);

@@ -29,8 +29,11 @@ CASES = {
     # BASELINE config 1 itself: the full 30-layer, 5.0 B-parameter model at 17 frames 256x448 (fp32 on CPU: ~6 min of
     # weight hashing + 20 s forward, ~45 GB of RAM). Not part of the default list: `make_golden.py real_tok`.
     "real_tok": ("real", (5, 16, 28), True),
+    # fg/bg-edit regime: fractional (trilinear) latent mask => (almost) every token has its own timestep
+    "tiny_frac": ("tiny", (3, 8, 12), "frac"),
+    "real2_frac": ("real2", (5, 16, 28), "frac"),
 }
-DEFAULT = ("tiny_tok", "tiny_sample", "real2_tok", "tiny_loop", "rope_tables")
+DEFAULT = ("tiny_tok", "tiny_sample", "real2_tok", "tiny_frac", "real2_frac", "tiny_loop", "rope_tables")
 
 
 def run_case(name: str):
@@ -61,7 +64,7 @@ def run_case(name: str):
         x0_rows=taps["x0"][0, rows].numpy(), after_self0_rows=taps["b0.after_self"][rows].numpy(),
         after_cross0_rows=taps["b0.after_cross"][rows].numpy(), x_final_rows=taps["x_final"][rows].numpy(),
         cnn_out_slice=taps["cnn_out"][0, :, 0].numpy(), ctx_rows=taps["ctx"][0, ::64].numpy(),
-        meta=np.array([F, H, W, int(per_tok)], dtype=np.int64), config=np.array(cfg_name))
+        meta=np.array([F, H, W, 2 if per_tok == "frac" else int(per_tok)], dtype=np.int64), config=np.array(cfg_name))
 
 
 # the sampling-loop fixture: 6 Euler steps (shift 5, guidance 6, density 10 = `full_edit`) around the REAL reference

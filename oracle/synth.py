@@ -159,7 +159,16 @@ def inputs(cfg: dict, F: int, H: int, W: int, B: int = 2, per_token_t: bool = Tr
     full_ref = tensor(f"{tag}/full_ref", (B, C, H, W))
     context = [tensor(f"{tag}/context{i}", (prompt_lens[i % len(prompt_lens)], cfg["text_dim"])) for i in range(B)]
     L0 = F * (H // 2) * (W // 2)
-    if per_token_t:
+    if per_token_t == "frac":
+        # fg/bg-edit regime (pipeline :686-690, :891-898): the latent mask is a TRILINEAR resize of the pixel mask kept
+        # in bf16, so boundary tokens carry fractional factors and the per-token timesteps `mask * t` take many distinct
+        # values. Synthetic stand-in: a smooth ramp in [0, 1] over (f, h, w), rounded to bf16, times t (bf16 product).
+        f, h, w = np.meshgrid(np.arange(F), np.arange(H // 2), np.arange(W // 2), indexing="ij")
+        ramp = (0.15 * f / max(F - 1, 1) + 0.55 * h / max(H // 2 - 1, 1) + 0.30 * w / max(W // 2 - 1, 1)).astype(np.float32)
+        ramp = np.clip(1.25 * ramp - 0.1, 0.0, 1.0)
+        t_tok = to_bf16_f32(to_bf16_f32(ramp.reshape(-1)) * np.float32(t_value))
+        t = np.broadcast_to(t_tok, (B, L0)).copy()
+    elif per_token_t:
         t_tok = (mask[:, ::2, ::2].reshape(-1) * np.float32(t_value)).astype(np.float32)
         t = np.broadcast_to(t_tok, (B, L0)).copy()
     else:

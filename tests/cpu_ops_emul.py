@@ -281,7 +281,60 @@ def groupnorm_silu_f32(x, groups, eps, gamma, beta, resid, y, stats):
     return y
 
 
-NAMES = ("gemm", "ln_modulate", "modulation_tables", "ln_scale_shift", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
+def linear_f32_tc(x, w, bias, act_in=0, planes=2, out=None, ws=None):
+    if act_in == 1:
+        x = F.silu(x)
+    hi = x.to(bf16).float()
+    kept = hi
+    if planes > 1:
+        mid = (x - hi).to(bf16).float()
+        kept = hi + mid
+        if planes > 2:
+            kept = kept + (x - hi - mid).to(bf16).float()
+    y = (kept.double() @ w.double().t()).float()
+    if bias is not None:
+        y = y + bias.float()
+    if out is None:
+        return y
+    return out.copy_(y)
+
+
+def dedup_f32(t, cap, uniq, inv, count):
+    vals = []
+    for v in t.tolist():
+        if v not in vals:
+            vals.append(v)
+            if len(vals) > cap:
+                break
+    n = len(vals)
+    count[0] = n
+    listed = vals[:cap]
+    uniq[:cap] = torch.tensor(listed + [listed[-1]] * (cap - len(listed)), dtype=f32)
+    if n <= cap:
+        lut = {v: j for j, v in enumerate(listed)}
+        inv[: t.numel()] = torch.tensor([lut[v] for v in t.tolist()], dtype=torch.int32)
+
+
+class _FpTable:
+    def __init__(self, tensors):
+        self.tensors = list(tensors)
+
+
+def fingerprint_table(tensors):
+    return _FpTable(tensors)
+
+
+def fingerprint(table, stride):
+    # every element (stronger than the sampled kernel): int64 sum of the raw 16-bit / 32-bit patterns
+    out = []
+    for t in table.tensors:
+        v = t.detach().contiguous().view(-1)
+        raw = v.view(torch.int16) if v.element_size() == 2 else v.view(torch.int32)
+        out.append((raw.to(torch.int64) * (torch.arange(raw.numel()) % 8191 + 1)).sum())
+    return torch.stack(out)
+
+
+NAMES = ("linear_f32_tc", "dedup_f32", "fingerprint_table", "fingerprint", "gemm", "ln_modulate", "modulation_tables", "ln_scale_shift", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
                  "linear_f32", "nchw_to_nhwc", "im2col3x3", "groupnorm_silu", "swap01", "cfg_euler_step", "add_", "sub", "split3", "join3",
                  "ln_f32", "rmsnorm_rope_f32", "gelu_f32_", "gated_residual_f32_", "attention_f32",
                  "groupnorm_silu_f32")

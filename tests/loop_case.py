@@ -35,26 +35,18 @@ def run_oracle_loop(g, policy="fp32", dtype=torch.float32, device="cpu"):
     return out, otc.decisions
 
 
-def run_native_loop(model, g, device):
+def run_native_loop(model, g, device, graph=False):
     """flexam_b200.sampler.DenoiseLoop around the (native or kernel-emulated) mirror module."""
     from flexam_b200.sampler import DenoiseLoop
     cfg = synth.CONFIGS[LOOP["config"]]
     tc = LOOP["teacache"]
     model.enable_teacache(tc["coefficients"], LOOP["steps"], tc["rel_l1_thresh"], tc["num_skip_start_steps"], offload=False)
     model.enable_cfg_skip(LOOP["cfg_skip_ratio"], LOOP["steps"])
-    decisions = []
-    orig = model.teacache.decide
-
-    def spy(mod_inp, cond_flag):
-        r = orig(mod_inp, cond_flag)
-        decisions.append(bool(r))
-        return r
-    model.teacache.decide = spy
     lt = make_golden.loop_tensors(cfg, *LOOP["grid"])
     lt = {k: ([u.to(device) for u in v] if isinstance(v, list) else v.to(device)) for k, v in lt.items()}
     loop = DenoiseLoop(model, lt["latents"], lt["mask"], lt["masked_video_latents"], lt["mask_latents"],
                        lt["control_video_latents"], lt["additional_control"], lt["ref_image_latents"],
                        lt["negative_prompt_embeds"], lt["prompt_embeds"], density=LOOP["density"],
-                       guidance_scale=LOOP["guidance"])
+                       guidance_scale=LOOP["guidance"], graph=graph)
     out = loop.run(g["timesteps"], g["sigmas"])
-    return out, decisions, loop
+    return out, list(loop.decisions), loop

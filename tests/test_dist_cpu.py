@@ -112,3 +112,77 @@ def test_ulysses_sequence_parallel_matches_single_process(tmp_path):
 def test_ulysses_with_ragged_token_count(tmp_path):
     # (F+1)*Hp*Wp = 3*3*5 = 45 tokens over 2 ranks -> 23 + 22 (+1 padding row that must be masked as a key)
     _run_case(tmp_path, (2, 6, 10), cfg_size=1)
+
+
+# ------------------------------------------------------------------------------------------------------
+# TeaCache + cfg_skip under CFG-branch parallelism: while the batch is split every rank caches the residual of its own
+# branch (cfg_rank 0 = uncond); once cfg_skip halves the batch the split is off and a skipped step must add the COND
+# residual on every rank (the reference takes previous_residual[-x.size(0):], wan_transformer3d_FlexAM.py:1003-1006).
+# ------------------------------------------------------------------------------------------------------
+def _loop_out(world, rank, cfg_skip_ratio):
+    import loop_case
+    from flexam_b200 import dist as fdist
+    from test_host_logic import build
+    from oracle import synth
+    saved = loop_case.LOOP["cfg_skip_ratio"]
+    loop_case.LOOP["cfg_skip_ratio"] = cfg_skip_ratio
+    try:
+        m, _ = build(synth.CONFIGS["tiny"])
+        if world > 1:
+            fdist.setup(m, world, rank, cfg_size=2)
+        g = loop_case.golden(os.path.join(HERE, "golden"))
+        out, decisions, _ = loop_case.run_native_loop(m, g, "cpu")
+    finally:
+        loop_case.LOOP["cfg_skip_ratio"] = saved
+    return out, decisions
+
+
+def _loop_worker(rank, world, port, ratio, ref_path, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    torch.set_num_threads(2)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _patch_ops()
+        out, decisions = _loop_out(world, rank, ratio)
+        ref = torch.load(ref_path)
+        err = (torch.linalg.vector_norm(out.float() - ref.float()) / torch.linalg.vector_norm(ref.float())).item()
+        q.put((rank, decisions, err))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_teacache_with_cfg_skip_under_cfg_parallel(tmp_path):
+    """cfg_skip from step 3 of 6 with TeaCache decisions [T, F, T, F, T, F]: step 2 caches residuals under the CFG
+    split, step 3 is a SKIPPED step on the halved batch — cfg_rank 0 must fetch the cond residual from its peer."""
+    sys.path.insert(0, HERE)
+    from flexam_b200 import ops
+    ratio = 0.5
+    saved = {n: getattr(ops, n) for n in dir(ops) if callable(getattr(ops, n)) and not n.startswith("_")}
+    try:
+        _patch_ops()
+        ref, ref_decisions = _loop_out(1, 0, ratio)
+    finally:
+        for n, f in saved.items():
+            setattr(ops, n, f)
+    assert ref_decisions == [True, False, True, False, True, False]
+    ref_path = str(tmp_path / "ref_loop.pt")
+    torch.save(ref, ref_path)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_loop_worker, args=(r, 2, port, ratio, ref_path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=10) for _ in range(2))
+    for rank, decisions, err in res:
+        assert decisions == ref_decisions
+        # six bf16 steps: the emulated matmuls of a split batch block differently, flips accumulate to ~5e-3; a rank
+        # that re-applies the wrong branch's residual lands at 1.5e-2 (measured with the fetch disabled)
+        assert err < 8e-3, f"rank {rank}: CFG-parallel loop differs from the single-process loop ({err:.2e})"
+    assert res[0][2] == res[1][2], "the two CFG ranks disagree with each other"

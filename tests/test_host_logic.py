@@ -50,6 +50,30 @@ def test_engine_host_logic_matches_oracle(monkeypatch, per_tok):
     assert m.engine().launches > 0
 
 
+@pytest.mark.parametrize("table_cap", [64, 128])
+def test_many_distinct_timesteps(monkeypatch, golden_dir, table_cap):
+    """fg/bg-edit regime (fractional trilinear latent mask, pipeline :686-690, :891-898): 66 distinct per-token
+    timesteps on this grid. Above the table capacity the engine runs the time MLP per token on the tensor cores and
+    LayerNorm / gates read the per-token e0 (:444-446); below it the modulation tables hold one row per distinct value.
+    Both must reproduce the REAL reference's output (tests/golden/tiny_frac.npz)."""
+    import os
+    cpu_ops_emul.install(monkeypatch)
+    cfg = synth.CONFIGS["tiny"]
+    g = np.load(os.path.join(golden_dir, "tiny_frac.npz"))
+    m, np_sd = build(cfg)
+    eng = m.engine()
+    if table_cap > 64:      # the dedup kernel lists at most 64 values; the emulation has no such limit
+        eng.max_table_timesteps = table_cap
+    inp = synth.inputs(cfg, 3, 8, 12, per_token_t="frac")
+    assert len(np.unique(inp["t"])) == 66
+    out, tt, ctx = call(m, inp)
+    assert rel(out, torch.from_numpy(g["out"])) < 1e-2
+    want = O.forward(O.to_torch_sd(np_sd), cfg, tt["x"], tt["t"], ctx, inp["seq_len"], tt["y"], tt["full_ref"],
+                     tt["additional_control"], tt["density"], policy="bf16")
+    assert rel(out, want) < 4e-3
+    assert eng.host_reads == 1
+
+
 def test_cfg_skip_wrapper_halves_and_duplicates(monkeypatch):
     cpu_ops_emul.install(monkeypatch)
     cfg = synth.CONFIGS["tiny"]
@@ -114,6 +138,9 @@ def test_sampling_loop_host_logic_matches_reference_golden(monkeypatch, golden_d
     out, decisions, loop = loop_case.run_native_loop(m, g, "cpu")
     assert decisions == [bool(d) for d in g["decisions"]]
     assert out.dtype == torch.bfloat16 and loop.launches == 6
+    # device->host reads of the whole 6-step loop: the TeaCache schedule (all decisions at once) and step 0's per-call
+    # checks; steps 1..5 enqueue without host synchronisation (the reference loop syncs >= 3 times per step)
+    assert loop.host_reads == 2
     r = rel(out, torch.from_numpy(g["out"]))
     print(f"emulated native loop vs reference loop golden: rel-L2 {r:.3e}")
     assert r < 1e-2
@@ -193,14 +220,15 @@ def test_static_cache_identity_fast_path(monkeypatch):
               additional_control=torch.from_numpy(inp["additional_control"]).bfloat16(),
               density=torch.from_numpy(inp["density"]))
     eng = m.engine()
-    fuser_calls, compares = [], []
-    real_fuser, real_same = eng._cnn_fuser, eng._same_content
+    fuser_calls, probes = [], []
+    real_fuser, real_probe = eng._cnn_fuser, eng._static_probe
     monkeypatch.setattr(eng, "_cnn_fuser", lambda *a, **k: (fuser_calls.append(1), real_fuser(*a, **k))[1])
     out1 = m(**kw)
     n = len(fuser_calls)
-    monkeypatch.setattr(eng, "_same_content", lambda *a, **k: (compares.append(1), real_same(*a, **k))[1])
+    monkeypatch.setattr(eng, "_static_probe", lambda *a, **k: (probes.append(real_probe(*a, **k)), probes[-1])[1])
     out2 = m(**kw)
-    assert len(fuser_calls) == n and not compares and torch.equal(out1, out2)
+    assert len(fuser_calls) == n and probes == ["hit"] and torch.equal(out1, out2)
+    assert eng.host_reads == 1          # the single read of the call: weight fingerprint + number of distinct timesteps
     kw["additional_control"].mul_(0.5)                       # in place: same address, new version
     out3 = m(**kw)
     assert len(fuser_calls) == 2 * n and not torch.equal(out1, out3)
@@ -237,14 +265,26 @@ def test_from_pretrained_follows_the_reference_contract(tmp_path):
     for k in ("blocks.1.ffn.2.weight", "cnn_conv3.0.bias", "time_projection.1.weight"):
         assert torch.equal(got[k], sd[k].bfloat16()), k
     assert "dict_mapping" in extra                                       # the caller's dict is not consumed
+    # parameters the checkpoint does not carry get the reference's init_weights values, never torch.empty garbage: the
+    # FlexAM additions of a base checkpoint (density MLPs, head.head.weight would be zero) — here head.modulation
+    assert torch.isfinite(got["head.modulation"].float()).all() and got["head.modulation"].float().abs().max() < 1.0
+    base = {k: v for k, v in ckpt.items() if not k.startswith("density_") and k != "head.modulation"}
+    save_file({k: v.contiguous() for k, v in base.items()}, str(root / "model-00001-of-00002.safetensors"))
+    (root / "model-00002-of-00002.safetensors").unlink()
+    m2 = Wan2_2Transformer3DModel_FlexAM.from_pretrained(str(tmp_path / "ckpt"), subfolder="transformer",
+                                                         transformer_additional_kwargs=extra)
+    for k, v in m2.state_dict().items():
+        if k.startswith("density_"):
+            assert v.float().abs().max().item() == 0, k            # zero-initialised like the reference (:1172-1185)
     with pytest.raises(RuntimeError, match="config.json does not exist"):
         Wan2_2Transformer3DModel_FlexAM.from_pretrained(str(tmp_path / "ckpt"), subfolder="nope")
 
 
 def test_weight_edits_are_picked_up(monkeypatch):
-    """In-place torch ops on a parameter (version counter), replaced storages (`param.data = ...`, module.to()) and -
-    after refresh() - edits through `param.data` (the reference's LoRA merge, lora_utils.py:481-485) all reach the
-    packed q|k|v copy the kernels read; the result equals a freshly built model with the same weights."""
+    """In-place torch ops on a parameter (version counter), replaced storages (`param.data = ...`, module.to()) and
+    edits through `param.data` (the reference's LoRA merge, lora_utils.py:481-485; invisible to the counters, caught by
+    the per-call weight fingerprint) all reach the packed q|k|v copy the kernels read and the cached cross-attention
+    K/V; the result equals a freshly built model with the same weights."""
     import flexam_b200.model as fx
     cpu_ops_emul.install(monkeypatch)
     cfg = synth.CONFIGS["tiny"]
@@ -268,7 +308,19 @@ def test_weight_edits_are_picked_up(monkeypatch):
     p.data = (p.data.float() - delta.float()).bfloat16()       # new storage: automatic
     got2, _, _ = call(m, inp)
     assert torch.equal(got2, fresh(p.data))
-    p.data += delta                                             # invisible to autograd: needs refresh()
-    fx.refresh(m)
+    p.data += delta                                             # invisible to autograd: the fingerprint catches it
     got3, _, _ = call(m, inp)
     assert torch.equal(got3, fresh(p.data)) and not torch.equal(got3, got2)
+    # a weight that feeds the CACHED cross-attention K/V (step-invariant cache): merge + unmerge through .data
+    key2 = "blocks.0.cross_attn.v.weight"
+    p2 = dict(m.named_parameters())[key2]
+    d2 = torch.from_numpy(synth.tensor("lora/delta2", tuple(p2.shape), 0.05)).bfloat16()
+    same_inputs = {k: torch.from_numpy(v) if hasattr(v, "dtype") else v for k, v in inp.items() if k != "context"}
+    p2.data += d2
+    got4, _, _ = call(m, inp)
+    f, _ = build(cfg)
+    dict(f.named_parameters())[key].data.copy_(p.data)
+    dict(f.named_parameters())[key2].data.copy_(p2.data)
+    assert torch.equal(got4, call(f, inp)[0]) and not torch.equal(got4, got3)
+    fx.refresh(m)                                               # explicit form still works
+    assert torch.equal(call(m, inp)[0], got4)

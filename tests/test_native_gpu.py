@@ -243,8 +243,9 @@ def _native_model(cfg_name, dev):
 
 
 def _inputs(cfg, grid, per_tok, dev):
+    """per_tok: False per-sample timesteps, True per-token (two values), 2 / "frac" per-token fractional (fg/bg edit)."""
     from oracle import synth
-    inp = synth.inputs(cfg, *grid, per_token_t=per_tok)
+    inp = synth.inputs(cfg, *grid, per_token_t="frac" if per_tok in (2, "frac") else bool(per_tok))
     tt = {k: torch.from_numpy(inp[k]).to(dev) for k in ("x", "y", "additional_control", "full_ref", "t", "density")}
     ctx = [torch.from_numpy(c).to(dev) for c in inp["context"]]
     return tt, ctx, inp["seq_len"]
@@ -292,13 +293,15 @@ def test_full_depth_forward_matches_reference_golden(dev, golden_dir):
     assert rel < 2 * BF16_GATE and rel < 2 * ref_gap + 5e-3   # and no further from fp32 than that path itself is
 
 
-@pytest.mark.parametrize("name", ["tiny_tok", "tiny_sample", "real2_tok"])
+@pytest.mark.parametrize("name", ["tiny_tok", "tiny_sample", "real2_tok", "tiny_frac", "real2_frac"])
 def test_forward_matches_reference_golden(dev, golden_dir, name):
-    """Native bf16 step vs the REAL reference's fp32 CPU output (tests/golden, made by oracle/make_golden.py)."""
+    """Native bf16 step vs the REAL reference's fp32 CPU output (tests/golden, made by oracle/make_golden.py). The
+    `_frac` fixtures are the fg/bg-edit regime: (almost) every token has its own timestep, so the time MLP runs per
+    token on the tensor cores and the LayerNorms / gates read the per-token e0."""
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     F, H, W, per_tok = (int(v) for v in g["meta"])
     model, cfg = _native_model(str(g["config"]), dev)
-    tt, ctx, seq_len = _inputs(cfg, (F, H, W), bool(per_tok), dev)
+    tt, ctx, seq_len = _inputs(cfg, (F, H, W), per_tok, dev)
     taps = {}
     out = model(x=tt["x"].bfloat16(), t=tt["t"], context=[c.bfloat16() for c in ctx], seq_len=seq_len,
                 y=tt["y"].bfloat16(), full_ref=tt["full_ref"].bfloat16(),

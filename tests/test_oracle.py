@@ -25,12 +25,18 @@ def _rel(a, b):
     return (torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(b)).item()
 
 
-@pytest.mark.parametrize("name", ["tiny_tok", "tiny_sample"])
+def _tmode(meta_flag):
+    """meta[3] of a fixture: 0 per-sample timesteps, 1 per-token (two values), 2 per-token fractional (fg/bg edit)."""
+    return "frac" if int(meta_flag) == 2 else bool(meta_flag)
+
+
+@pytest.mark.parametrize("name", ["tiny_tok", "tiny_sample", "tiny_frac"])
 def test_oracle_matches_reference_golden(name, golden_dir):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     F, H, W, per_tok = (int(v) for v in g["meta"])
+    per_tok = _tmode(per_tok)
     taps = {}
-    out = _run_oracle(str(g["config"]), (F, H, W), bool(per_tok), taps=taps)
+    out = _run_oracle(str(g["config"]), (F, H, W), per_tok, taps=taps)
     assert _rel(out, torch.from_numpy(g["out"])) < 2e-5
     rows = slice(0, None, max(1, taps["x0"].shape[1] // 16))
     assert _rel(taps["x_final"][rows], torch.from_numpy(g["x_final_rows"])) < 2e-5
@@ -239,12 +245,12 @@ def _library_model(cfg):
     return m
 
 
-@pytest.mark.parametrize("name", ["tiny_tok", "tiny_sample"])
+@pytest.mark.parametrize("name", ["tiny_tok", "tiny_sample", "tiny_frac"])
 def test_library_step_matches_reference_golden(name, golden_dir):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     F, H, W, per_tok = (int(v) for v in g["meta"])
     cfg = synth.CONFIGS[str(g["config"])]
-    inp = synth.inputs(cfg, F, H, W, per_token_t=bool(per_tok))
+    inp = synth.inputs(cfg, F, H, W, per_token_t=_tmode(per_tok))
     tt = {k: torch.from_numpy(inp[k]) for k in ("x", "y", "additional_control", "full_ref", "t", "density")}
     out = _library_model(cfg)(tt["x"], tt["t"], [torch.from_numpy(c) for c in inp["context"]], inp["seq_len"], tt["y"],
                               tt["full_ref"], tt["additional_control"], tt["density"])
