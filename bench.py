@@ -291,6 +291,60 @@ def library_baseline(torch, model, cfg, d, out_native, steps=10, warmup=3):
     return res
 
 
+class Itemiser:
+    """CUDA events around EVERY launch of the step (all flexam_b200.ops entry points, the cross-rank barriers and the
+    NCCL gathers): where the device time of a step goes, per kernel family, including the idle gaps in front of each
+    launch (an event pair measures from the end of the previous work on the stream to the end of this launch).
+    Diagnostic: the events serialise the stream, so programmatic dependent launch cannot overlap kernels here."""
+
+    def __init__(self, torch, eng):
+        from flexam_b200 import ops
+        self.torch, self.ops, self.eng = torch, ops, eng
+        self.rec = []
+        self.saved = []
+
+    def _wrap(self, owner, name, label):
+        fn = getattr(owner, name)
+        torch, rec = self.torch, self.rec
+
+        def timed(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            rec.append((label, e0, e1))
+            return r
+        self.saved.append((owner, name, fn))
+        setattr(owner, name, timed)
+
+    def __enter__(self):
+        import types
+        for name in dir(self.ops):
+            fn = getattr(self.ops, name)
+            if isinstance(fn, types.FunctionType) and not name.startswith("_") and fn.__module__ == self.ops.__name__ \
+                    and name not in ("stream_scope", "fingerprint_table", "tune"):
+                self._wrap(self.ops, name, name)
+        par = self.eng.par
+        if par is not None:
+            for name, label in (("_barrier", "sp_barrier"), ("gather_tokens", "nccl_gather_sp"),
+                                ("gather_cfg", "nccl_gather_cfg")):
+                self._wrap(par, name, label)
+        return self
+
+    def __exit__(self, *exc):
+        for owner, name, fn in reversed(self.saved):
+            setattr(owner, name, fn)
+
+    def table(self, steps):
+        agg = {}
+        for label, a, b in self.rec:
+            t = agg.setdefault(label, [0, 0.0])
+            t[0] += 1
+            t[1] += a.elapsed_time(b)
+        return {k: {"launches_per_step": v[0] / steps, "ms_per_step": v[1] / steps}
+                for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -366,11 +420,29 @@ def run_native(args):
         f = fam.setdefault(kind, [0.0, 0.0, 0])
         f[0] += flops; f[1] += a.elapsed_time(b); f[2] += 1
 
+    itemised = None
+    if args.itemise:
+        with Itemiser(torch, eng) as it:
+            call(resident)
+            barrier()
+            it.rec.clear()
+            ev0.record()
+            for _ in range(3):
+                call(resident)
+            ev1.record()
+            barrier()
+            itemised = {"ms_per_step_with_events": ev0.elapsed_time(ev1) / 3, "rank": rank, "kernels": it.table(3)}
+            itemised["sum_ms"] = sum(v["ms_per_step"] for v in itemised["kernels"].values())
+        if world > 1:   # every rank's table, gathered on rank 0
+            allt = [None] * world
+            dist.all_gather_object(allt, itemised)
+            itemised = allt
+
     if args.quick:   # profiling runs (ncu) only need the resident region
         if rank == 0:
             print(json.dumps({"quick": True, "workload": WORKLOAD, "n_gpus": world, "ms_per_step": ms_value,
                               "step_tflops": step_flops(cfg) / 1e12, "gpu_launches": launches,
-                              "host_enqueue_ms_per_step": host_enqueue_ms}))
+                              "host_enqueue_ms_per_step": host_enqueue_ms, "itemised": itemised}))
         if clocks:
             clocks.stop()
         return
@@ -450,6 +522,8 @@ def run_native(args):
                           "share_of_step": att[1] / args.steps / ms_value},
         "clocks": clk,
     }
+    if itemised is not None:
+        line["itemised"] = itemised
     if parity is not None:
         line["parity"] = parity
     if not args.no_library_baseline and world == 1:
@@ -464,6 +538,85 @@ def run_native(args):
         except Exception as exc:   # noqa: BLE001
             line["cpu_baseline"]["config1_forward"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_loop(args):
+    """BASELINE config 4: the full sampling loop (`full_edit`: first latent frame pinned, density 10 => the model sees
+    0.1, guidance 6, flow-match Euler with shift 5) at 97 frames 512x896 through flexam_b200.sampler.DenoiseLoop — per
+    step one transformer call (CFG batch 2) + one fused CFG/Euler/re-pin launch, step-invariant control work hoisted
+    as in the real sampler. A stress/parity case, not the bench line: prints its own JSON line."""
+    import torch
+    import torch.distributed as dist
+    from flexam_b200 import lib
+    from flexam_b200.model import Wan2_2Transformer3DModel_FlexAM
+    from flexam_b200.sampler import DenoiseLoop, flow_match_euler_schedule
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib.check(lib.load().fx_check_device(local), "fx_check_device")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = real_cfg()
+    model = Wan2_2Transformer3DModel_FlexAM(**cfg, device=dev)
+    init_weights(torch, model)
+    layout = "single"
+    if world > 1:
+        from flexam_b200 import dist as fdist
+        layout = fdist.setup(model, world, rank)
+    F, H, W = GRID
+    g = torch.Generator().manual_seed(4321)
+    C = cfg["out_dim"]
+    lat = torch.randn(1, C, F, H, W, generator=g)
+    mask = torch.ones(1, 1, F, H, W)
+    mask[:, :, 0] = 0
+    masked_video = torch.randn(1, C, F, H, W, generator=g)
+    mask_lat = (1 - mask).expand(1, 4, F, H, W).contiguous()
+    control = torch.randn(1, C, F, H, W, generator=g)
+    add = torch.randn(1, cfg["in_dim_cnn_block"] - C, F, H, W, generator=g)
+    ref = torch.randn(1, C, H, W, generator=g)
+    neg = [torch.randn(PROMPT_LENS[0], cfg["text_dim"], generator=g)]
+    pos = [torch.randn(PROMPT_LENS[1], cfg["text_dim"], generator=g)]
+    to = lambda u: u.to(dev)  # noqa: E731
+    n = args.loop_steps
+    ts, sig = flow_match_euler_schedule(n, 5.0)
+
+    def one_loop():
+        loop = DenoiseLoop(model, to(lat), to(mask), to(masked_video), to(mask_lat), to(control), to(add), to(ref),
+                           [to(u) for u in neg], [to(u) for u in pos], density=0.1, guidance_scale=6.0,
+                           graph=args.graph and world == 1)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        out = loop.run(ts, sig)
+        e1.record()
+        host_s = time.perf_counter() - t0       # host time to ENQUEUE the loop (it never waits for the device)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        return out, e0.elapsed_time(e1), host_s, loop
+    one_loop()                                   # warm-up loop (allocations, caches of the first video)
+    out, ms, host_s, loop = one_loop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    if rank == 0:
+        print(json.dumps({
+            "workload": f"BASELINE config 4: {n}-step full_edit sampling loop, 97 frames 512x896, CFG 6, shift 5, density "
+                        "10 (model input 0.1), synthetic control latents", "n_gpus": world, "layout": layout,
+            "loop_seconds": ms / 1e3, "ms_per_step": ms / n, "steps_per_s": n * 1e3 / ms,
+            "host_enqueue_seconds": host_s, "device_to_host_reads_per_loop": loop.host_reads,
+            "cuda_graph_replays": loop.graph_replays, "launches_outside_transformer": loop.launches,
+            "parity": {"checksum_sha256_16": output_checksum(out), "finite": bool(torch.isfinite(out.float()).all().item()),
+                       "note": "final latents; equal across N iff bit-identical"}}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -598,7 +751,11 @@ if __name__ == "__main__":
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison + checksum of the step output")
     ap.add_argument("--no-library-baseline", action="store_true", help="skip the torch library-path leg (N = 1 only)")
     ap.add_argument("--quick", action="store_true", help="resident region only (for ncu runs)")
-    ap.add_argument("--workload", default="config2", choices=["config2", "long"],
+    ap.add_argument("--itemise", action="store_true", help="add a per-kernel-family device-time table (CUDA events "
+                    "around every launch, 3 extra steps outside the timed regions)")
+    ap.add_argument("--loop-steps", type=int, default=50, help="sampling steps of --workload loop50")
+    ap.add_argument("--graph", action="store_true", help="loop50: replay the transformer call from CUDA graphs (N = 1)")
+    ap.add_argument("--workload", default="config2", choices=["config2", "long", "loop50"],
                     help="config2 = the metric's workload (default); long = BASELINE config 5, 193 frames 704x1280 "
                          "(43,120 tokens + 880 ref): a parity/stress case, not the bench line")
     a = ap.parse_args()
@@ -608,5 +765,7 @@ if __name__ == "__main__":
                     "CFG batch 2 (long-clip stress case, BASELINE config 5)")
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "loop50":
+        run_loop(a)
     else:
         run_native(a)

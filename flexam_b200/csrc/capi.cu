@@ -22,15 +22,6 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* env = getenv("FX_PDL");
-    v = (env && env[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
 bool ensure_dyn_smem(const void* func, int bytes, const char* what) {
   static std::mutex mu;
   static std::vector<std::tuple<const void*, int, int>> done;  // (function, device, bytes granted)
@@ -72,6 +63,13 @@ int tune_get(const char* name) {
   const int val = (v && v[0]) ? atoi(v) : -1;
   g_tune.emplace_back(name, val);
   return val;
+}
+
+bool pdl_enabled() {
+  // Programmatic dependent launch is ON by default (round 2: -2 % on the per-rank block chain at 8 GPUs, GPU suite green
+  // with it; FX_PDL=0 / fx_tune("pdl", 0) turns it off). Read per launch so that fx_tune takes effect immediately.
+  const int v = tune_get("pdl");
+  return v != 0;
 }
 
 int num_sms() {

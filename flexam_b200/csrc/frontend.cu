@@ -245,6 +245,62 @@ __global__ void groupnorm_apply_kernel(const __nv_bfloat16* x, long long P, int 
   }
 }
 
+// GroupNorm statistics in two deterministic stages, so that frames can live on different ranks (the control fuser is
+// sharded by frames across a sequence-parallel group) and still give bit-identical statistics on every layout:
+// (1) per (frame, group) partial sum / sum of squares in fp64, one block each — also 25x more blocks than one block per
+// group; (2) the partials of ALL frames are summed in frame order (locally computed or gathered from the peers).
+__global__ void __launch_bounds__(512)
+groupnorm_partial_kernel(const __nv_bfloat16* x, long long pp, int C, int G, double* partials) {
+  const int g = blockIdx.x, f = blockIdx.y;
+  const int cg = C / G;
+  const long long n = pp * cg;
+  const __nv_bfloat16* xf = x + static_cast<long long>(f) * pp * C + g * cg;
+  double s = 0.0, q = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const long long pix = i / cg;
+    const int ci = static_cast<int>(i - pix * cg);
+    const float v = __bfloat162float(xf[pix * C + ci]);
+    s += v;
+    q += static_cast<double>(v) * v;
+  }
+  __shared__ double sh_s[16], sh_q[16];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    sh_s[warp] = s;
+    sh_q[warp] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int w = 0; w < 16; ++w) {
+      ts += sh_s[w];
+      tq += sh_q[w];
+    }
+    double* o = partials + (static_cast<long long>(f) * G + g) * 2;
+    o[0] = ts;
+    o[1] = tq;
+  }
+}
+
+__global__ void groupnorm_finalize_kernel(const double* partials, int Ft, int G, double n, float eps, float* stats) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  double s = 0.0, q = 0.0;
+  for (int f = 0; f < Ft; ++f) {
+    s += partials[(static_cast<long long>(f) * G + g) * 2];
+    q += partials[(static_cast<long long>(f) * G + g) * 2 + 1];
+  }
+  const double mean = s / n;
+  const double var = q / n - mean * mean;
+  stats[2 * g] = static_cast<float>(mean);
+  stats[2 * g + 1] = static_cast<float>(1.0 / sqrt((var > 0.0 ? var : 0.0) + static_cast<double>(eps)));
+}
+
 static int ew_grid2(long long n) {
   long long g = (n + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -352,6 +408,36 @@ extern "C" int fx_groupnorm_silu(const void* x, int64_t P, int C, int G, float e
       reinterpret_cast<const __nv_bfloat16*>(x), P, C, G, reinterpret_cast<const __nv_bfloat16*>(gamma),
       reinterpret_cast<const __nv_bfloat16*>(beta), stats, resid, y_f32, reinterpret_cast<__nv_bfloat16*>(y_bf16));
   FX_CHECK_LAUNCH("fx_groupnorm_silu(apply)");
+  return FX_OK;
+}
+
+extern "C" int fx_groupnorm_partials(const void* x, int F, int64_t pp, int C, int G, double* partials, void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(x && partials, "fx_groupnorm_partials: null pointer");
+  FX_CHECK_ARG(F > 0 && F <= 65535 && pp > 0 && C > 0 && G > 0 && C % G == 0,
+               "fx_groupnorm_partials: bad shape F=%d pp=%lld C=%d G=%d", F, (long long)pp, C, G);
+  groupnorm_partial_kernel<<<dim3(G, F), 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), pp, C, G, partials);
+  FX_CHECK_LAUNCH("fx_groupnorm_partials");
+  return FX_OK;
+}
+
+extern "C" int fx_groupnorm_silu_partials(const void* x, int64_t P, int C, int G, float eps, const void* gamma,
+                                          const void* beta, const double* partials, int Ft, int64_t pp,
+                                          const float* resid, float* y_f32, void* y_bf16, float* stats, void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(x && gamma && beta && partials && stats && (y_f32 || y_bf16), "fx_groupnorm_silu_partials: null pointer");
+  FX_CHECK_ARG(P > 0 && C > 0 && G > 0 && C % G == 0 && Ft > 0 && pp > 0,
+               "fx_groupnorm_silu_partials: bad shape P=%lld C=%d G=%d Ft=%d pp=%lld", (long long)P, C, G, Ft,
+               (long long)pp);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const double n = static_cast<double>(Ft) * static_cast<double>(pp) * (C / G);
+  groupnorm_finalize_kernel<<<(G + 31) / 32, 32, 0, s>>>(partials, Ft, G, n, eps, stats);
+  FX_CHECK_LAUNCH("fx_groupnorm_silu_partials(finalize)");
+  groupnorm_apply_kernel<<<ew_grid2(P * C), 256, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), P, C, G, reinterpret_cast<const __nv_bfloat16*>(gamma),
+      reinterpret_cast<const __nv_bfloat16*>(beta), stats, resid, y_f32, reinterpret_cast<__nv_bfloat16*>(y_bf16));
+  FX_CHECK_LAUNCH("fx_groupnorm_silu_partials(apply)");
   return FX_OK;
 }
 

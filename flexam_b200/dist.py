@@ -75,7 +75,8 @@ class Layout:
 def make_layout(world: int, rank: int, cfg_size: Optional[int] = None, num_heads: int = 24) -> Layout:
     """CFG-parallel first (no per-layer traffic), then Ulysses over what is left."""
     if cfg_size is None:
-        cfg_size = 2 if world % 2 == 0 else 1
+        env = os.environ.get("FLEXAM_CFG_SIZE")       # e.g. 1: sequence parallelism only (SP8 with batched CFG)
+        cfg_size = int(env) if env else (2 if world % 2 == 0 else 1)
     if world % cfg_size != 0:
         raise ValueError(f"world size {world} not divisible by cfg_size {cfg_size}")
     sp = world // cfg_size
@@ -158,7 +159,7 @@ class Parallel:
         full = self.symm_buffer("full", (B, 3, P * Lp, Hl * 128), qkv.dtype, qkv.device)
         ops.qkv_norm_rope_scatter(qkv, D, w_q, w_k, eps, freqs, grid, lay.sp_rank * Lp, Lp, full.ptrs, Hl, P * Lp,
                                   lay.sp_rank * Lp)
-        full.handle.barrier(0)            # every rank's heads have landed before anyone attends over them
+        self._barrier(full)               # every rank's heads have landed before anyone attends over them
         f5 = full.tensor.view(B, 3, P * Lp, Hl, 128)
         esz = attn.tensor.element_size()
         head0 = lay.sp_rank * Hl * 128 * esz
@@ -167,7 +168,11 @@ class Parallel:
             ops.fmha_scatter(*args)
         else:
             timed("fmha", 4.0 * B * Hl * (P * Lp) * L * 128, ops.fmha_scatter, *args)
-        full.handle.barrier(0)            # every rank's rows have landed before the o projection reads them
+        self._barrier(full)               # every rank's rows have landed before the o projection reads them
+
+    def _barrier(self, buf: "SymmBuffer") -> None:
+        """Stream-ordered barrier over the SP group (symmetric-memory signal pads; a kernel, not a host wait)."""
+        buf.handle.barrier(0)
 
     def _buf(self, name, shape, like):
         key = (name, tuple(shape), like.dtype)

@@ -40,6 +40,8 @@ SIGNATURES = {
     "fx_nchw_to_nhwc": [_vp, _vp, _i64, _i, _i, _i64, _vp],
     "fx_im2col3x3": [_vp, _vp, _i, _i, _i, _i, _vp],
     "fx_groupnorm_silu": [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "fx_groupnorm_partials": [_vp, _i, _i64, _i, _i, _vp, _vp],
+    "fx_groupnorm_silu_partials": [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp],
     "fx_cfg_euler_step": [_vp, _vp, _f, _f, _vp, _vp, _vp, _i64, _vp],
     "fx_swap01_bf16": [_vp, _i64, _vp, _i, _i, _i, _vp],
     "fx_add_f32": [_vp, _vp, _i64, _vp],

@@ -246,36 +246,65 @@ class NativeEngine:
         return e, e0
 
     def _cnn_fuser(self, y_ctrl0: torch.Tensor, add: torch.Tensor) -> torch.Tensor:
-        """cnn_conv1..5 (:868-880) for one sample; inputs [48,F,H,W] and [240,F,H,W] bf16 -> channel-last [P, 48]."""
+        """cnn_conv1..5 (:868-880) for one sample; inputs [48,F,H,W] and [240,F,H,W] bf16 -> channel-last [P, 48].
+
+        The convolutions are per frame (kernel (1,3,3)), so across a sequence-parallel group every rank runs them on
+        its own block of frames; only the GroupNorm statistics span the sample: per-(frame, group) fp64 partials are
+        all-gathered and summed in frame order on every rank, the same order a single GPU uses, so the result is
+        bit-identical on every layout. One more all-gather returns the 48-channel output to all ranks."""
         P = self.params
         C0, F, H, W = y_ctrl0.shape
         C1 = add.shape[0]
-        npix = F * H * W
-        act = self._buf("cnn_in", (npix, C0 + C1), bf16)
-        ops.nchw_to_nhwc(y_ctrl0.reshape(C0, npix), act, 0)
-        ops.nchw_to_nhwc(add.reshape(C1, npix), act, C0)
-        self.launches += 2
+        pp = H * W
+        par = self.par
+        nsp = par.layout.sp_size if par is not None else 1
+        Fc = -(-F // nsp)                                     # frames per rank; the last rank(s) may hold fewer or none
+        f0 = min((par.layout.sp_rank if par is not None else 0) * Fc, F)
+        Fl = min(f0 + Fc, F) - f0
+        npix = Fl * pp
+        out_pad = self._buf("cnn_out_pad", (Fc * pp, self.w_cnn5.shape[0]), bf16)
+        if nsp > 1 and Fl < Fc:
+            out_pad.zero_()
+        act = None
+        if Fl > 0:
+            act = self._buf("cnn_in", (npix, C0 + C1), bf16)
+            src0 = y_ctrl0 if nsp == 1 else y_ctrl0[:, f0:f0 + Fl].contiguous()
+            src1 = add if nsp == 1 else add[:, f0:f0 + Fl].contiguous()
+            ops.nchw_to_nhwc(src0.reshape(C0, npix), act, 0)
+            ops.nchw_to_nhwc(src1.reshape(C1, npix), act, C0)
+            self.launches += 2
         stats = self._buf("cnn_stats", (64,), f32)
         resid = None
         for j, (groups, keep) in enumerate([(24, True), (24, False), (12, True), (12, False)]):
-            cin = act.shape[1]
             wj = self.w_cnn[j]
             cout = wj.shape[0]
-            rows = self._buf("cnn_rows", (npix, 9 * cin), bf16)
-            ops.im2col3x3(act, F, H, W, rows)
-            conv = self._buf(f"cnn_conv{j}", (npix, cout), bf16)
-            self._gemm(rows, wj, P[f"cnn_conv{j + 1}.0.bias"], conv, FX_EPI_BF16)
-            nxt = self._buf(f"cnn_act{j}", (npix, cout), bf16)
-            keep_f32 = self._buf(f"cnn_f32_{j}", (npix, cout), f32) if keep else None
-            # x2 = S(GN(conv2(x1))) + x1 and x4 = S(GN(conv4(x3))) + x3 take the previous stage's fp32 output
-            ops.groupnorm_silu(conv, groups, 1e-5, P[f"cnn_conv{j + 1}.1.weight"], P[f"cnn_conv{j + 1}.1.bias"],
-                               None if keep else resid, keep_f32, nxt, stats)
-            self.launches += 3
-            resid = keep_f32
-            act = nxt
-        out = torch.empty((npix, self.w_cnn5.shape[0]), dtype=bf16, device=self.device)
-        self._gemm(act, self.w_cnn5, P["cnn_conv5.bias"], out, FX_EPI_BF16)
-        return out
+            part = self._buf(f"cnn_part{j}", (Fc, groups, 2), torch.float64)
+            if Fl < Fc:
+                part.zero_()
+            if Fl > 0:
+                cin = act.shape[1]
+                rows = self._buf("cnn_rows", (npix, 9 * cin), bf16)
+                ops.im2col3x3(act, Fl, H, W, rows)
+                conv = self._buf(f"cnn_conv{j}", (npix, cout), bf16)
+                self._gemm(rows, wj, P[f"cnn_conv{j + 1}.0.bias"], conv, FX_EPI_BF16)
+                ops.groupnorm_partials(conv, Fl, groups, part[:Fl])
+                self.launches += 2
+            allp = part if nsp == 1 else par.gather_tokens(part)[:F].contiguous()     # [F, groups, 2], frame order
+            if Fl > 0:
+                nxt = self._buf(f"cnn_act{j}", (npix, cout), bf16)
+                keep_f32 = self._buf(f"cnn_f32_{j}", (npix, cout), f32) if keep else None
+                # x2 = S(GN(conv2(x1))) + x1 and x4 = S(GN(conv4(x3))) + x3 take the previous stage's fp32 output
+                ops.groupnorm_silu_partials(conv, groups, 1e-5, P[f"cnn_conv{j + 1}.1.weight"],
+                                            P[f"cnn_conv{j + 1}.1.bias"], allp, pp, None if keep else resid, keep_f32,
+                                            nxt, stats)
+                self.launches += 2
+                resid = keep_f32
+                act = nxt
+        if Fl > 0:
+            self._gemm(act, self.w_cnn5, P["cnn_conv5.bias"], out_pad[:npix], FX_EPI_BF16)
+        if nsp == 1:
+            return out_pad.clone()
+        return par.gather_tokens(out_pad)[:F * pp].contiguous()
 
     def _context(self, context: List[torch.Tensor]) -> torch.Tensor:
         """zero-pad to text_len, text_embedding MLP (:958-964) -> [B*text_len, D] bf16."""
@@ -568,7 +597,9 @@ class NativeEngine:
             if block_hook is not None:
                 block_hook(i, xs)
         if teacache is not None and run_blocks:
-            res = torch.empty_like(xs)
+            # a persistent buffer per branch: a CUDA-graph replay of this call and of a later skipped step then agree on
+            # where the residual lives (the reference's `offload` to host memory is not needed with 180 GB of HBM)
+            res = self._buf("tc_res_cond" if cond_flag else "tc_res_uncond", tuple(xs.shape), f32)
             ops.sub(xs, ori, res)
             self.launches += 1
             if cond_flag:

@@ -334,6 +334,32 @@ def groupnorm_silu(x: torch.Tensor, groups: int, eps: float, gamma: torch.Tensor
     _l.check(st, "fx_groupnorm_silu")
 
 
+def groupnorm_partials(x: torch.Tensor, frames: int, groups: int, partials: torch.Tensor) -> torch.Tensor:
+    """partials f64 [frames, groups, 2] = per-(frame, group) sum / sum of squares of x bf16 [frames*pp, C]."""
+    _req(x, bf16, "groupnorm_partials.x"), _req(partials, torch.float64, "groupnorm_partials.partials")
+    P, Cc = x.shape
+    if P % frames != 0 or tuple(partials.shape) != (frames, groups, 2) or not partials.is_contiguous():
+        raise _l.FlexamNativeError("groupnorm_partials: x rows must split into frames; partials [frames, groups, 2]")
+    st = _l.load().fx_groupnorm_partials(_p(x), frames, P // frames, Cc, groups, _p(partials), _stream())
+    _l.check(st, "fx_groupnorm_partials")
+    return partials
+
+
+def groupnorm_silu_partials(x: torch.Tensor, groups: int, eps: float, gamma: torch.Tensor, beta: torch.Tensor,
+                            partials: torch.Tensor, pix_per_frame: int, resid: Optional[torch.Tensor],
+                            y_f32: Optional[torch.Tensor], y_bf16: Optional[torch.Tensor], stats: torch.Tensor) -> None:
+    """GroupNorm + SiLU (+ resid) of the local pixels x [P, C] with the statistics of ALL frames: partials f64
+    [Ft, groups, 2] in frame order (see fx_groupnorm_silu_partials)."""
+    _req(x, bf16, "groupnorm_silu_partials.x"), _req(partials, torch.float64, "groupnorm_silu_partials.partials")
+    if partials.dim() != 3 or partials.shape[1] != groups or not partials.is_contiguous():
+        raise _l.FlexamNativeError("groupnorm_silu_partials: partials must be contiguous [Ft, groups, 2]")
+    P, Cc = x.shape
+    st = _l.load().fx_groupnorm_silu_partials(_p(x), P, Cc, groups, eps, _p(gamma), _p(beta), _p(partials),
+                                              partials.shape[0], pix_per_frame, _p(resid), _p(y_f32), _p(y_bf16),
+                                              _p(stats), _stream())
+    _l.check(st, "fx_groupnorm_silu_partials")
+
+
 def cfg_euler_step(vu: torch.Tensor, vc: torch.Tensor, guidance: float, dsigma: float, lat: torch.Tensor,
                    mask: Optional[torch.Tensor], pinned: Optional[torch.Tensor]) -> torch.Tensor:
     _req(vu, bf16, "cfg_euler_step.vu"), _req(vc, bf16, "cfg_euler_step.vc"), _req(lat, f32, "cfg_euler_step.lat")

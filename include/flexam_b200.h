@@ -156,11 +156,21 @@ int fx_linear_f32(const float* in, int64_t ldi, const void* w, int64_t ldw, cons
  *   fx_groupnorm_silu: y = SiLU(GroupNorm_G(x; gamma, beta, eps)) (+ resid), stats over all pixels of the sample;
  *                    x bf16 [P, C] (conv output), y_f32 [P, C] and y_bf16 [P, C] (either may be NULL),
  *                    resid f32 [P, C] or NULL; stats: f32 workspace [2*G].
+ *   fx_groupnorm_partials / fx_groupnorm_silu_partials: the same normalisation in two deterministic stages, so the
+ *                    frames of a sample may live on different ranks (the fuser is sharded by frames across a
+ *                    sequence-parallel group) with bit-identical statistics on every layout: partials f64 [F, G, 2] =
+ *                    (sum, sum of squares) per (frame, group) of x bf16 [F*pp, C] (pp pixels per frame); the second
+ *                    call sums the partials of ALL Ft frames of the sample in frame order (gathered from the peers
+ *                    when sharded), then applies GroupNorm + SiLU (+ resid) to the P local pixels.
  */
 int fx_nchw_to_nhwc(const void* src, void* dst, int64_t ldd, int c0, int C, int64_t P, void* stream);
 int fx_im2col3x3(const void* in, void* rows, int F, int H, int W, int C, void* stream);
 int fx_groupnorm_silu(const void* x, int64_t P, int C, int G, float eps, const void* gamma, const void* beta,
                       const float* resid, float* y_f32, void* y_bf16, float* stats, void* stream);
+int fx_groupnorm_partials(const void* x, int F, int64_t pp, int C, int G, double* partials, void* stream);
+int fx_groupnorm_silu_partials(const void* x, int64_t P, int C, int G, float eps, const void* gamma, const void* beta,
+                               const double* partials, int Ft, int64_t pp, const float* resid, float* y_f32,
+                               void* y_bf16, float* stats, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Sampler glue (pipeline_wan2_2_fun_control_FlexAM.py:926-934): CFG combine + Euler flow step + first-frame

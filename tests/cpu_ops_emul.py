@@ -172,6 +172,32 @@ def groupnorm_silu(x, groups, eps, gamma, beta, resid, y_f32, y_bf16, stats):
         y_bf16.copy_(y.to(bf16))
 
 
+def groupnorm_partials(x, frames, groups, partials):
+    P, C = x.shape
+    v = x.double().view(frames, P // frames, groups, C // groups)
+    partials[..., 0] = v.sum(dim=(1, 3))
+    partials[..., 1] = (v * v).sum(dim=(1, 3))
+    return partials
+
+
+def groupnorm_silu_partials(x, groups, eps, gamma, beta, partials, pix_per_frame, resid, y_f32, y_bf16, stats):
+    P, C = x.shape
+    n = partials.shape[0] * pix_per_frame * (C // groups)
+    mean = partials[..., 0].sum(0) / n
+    var = (partials[..., 1].sum(0) / n - mean * mean).clamp(min=0)
+    rstd = 1.0 / torch.sqrt(var + eps)
+    m = mean.float().repeat_interleave(C // groups)
+    r = rstd.float().repeat_interleave(C // groups)
+    v = (x.float() - m) * r * gamma.float() + beta.float()
+    y = F.silu(v)
+    if resid is not None:
+        y = y + resid
+    if y_f32 is not None:
+        y_f32.copy_(y)
+    if y_bf16 is not None:
+        y_bf16.copy_(y.to(bf16))
+
+
 def swap01(src, out):
     out.copy_(src.transpose(0, 1))
     return out
@@ -334,7 +360,7 @@ def fingerprint(table, stride):
     return torch.stack(out)
 
 
-NAMES = ("linear_f32_tc", "dedup_f32", "fingerprint_table", "fingerprint", "gemm", "ln_modulate", "modulation_tables", "ln_scale_shift", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
+NAMES = ("groupnorm_partials", "groupnorm_silu_partials", "linear_f32_tc", "dedup_f32", "fingerprint_table", "fingerprint", "gemm", "ln_modulate", "modulation_tables", "ln_scale_shift", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
                  "linear_f32", "nchw_to_nhwc", "im2col3x3", "groupnorm_silu", "swap01", "cfg_euler_step", "add_", "sub", "split3", "join3",
                  "ln_f32", "rmsnorm_rope_f32", "gelu_f32_", "gated_residual_f32_", "attention_f32",
                  "groupnorm_silu_f32")

@@ -524,6 +524,122 @@ def test_sampling_loop_matches_reference_golden(dev, golden_dir):
     assert rel < BF16_GATE
 
 
+def test_dedup_and_tensor_core_fp32_linear(dev):
+    """fx_dedup_f32 against torch.unique (values, inverse, overflow report) and fx_linear_f32_tc (fp32 linear on bf16
+    planes, one tcgen05 accumulation) against an fp64 matmul: 2 planes keep 16 bits of the input, 3 are exact up to
+    the accumulator."""
+    from flexam_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(41)
+    vals = torch.tensor([875.0, 0.0, 437.5, 12.25, 875.0 * 0.3], device=dev)
+    t = vals[torch.randint(0, 5, (23296,), device=dev, generator=g)].contiguous()
+    uniq = torch.full((8,), float("nan"), device=dev)
+    inv = torch.full((t.numel(),), -1, device=dev, dtype=torch.int32)
+    cnt = torch.zeros(1, device=dev, dtype=torch.int32)
+    ops.dedup_f32(t, 8, uniq, inv, cnt)
+    n = int(cnt.item())
+    assert n == 5 and torch.equal(uniq[:n][inv.long()], t)
+    assert sorted(uniq[:n].tolist()) == sorted(vals.tolist())
+    first = [int((t == v).nonzero()[0]) for v in uniq[:n]]
+    assert first == sorted(first)                                   # order of first appearance: deterministic
+    ops.dedup_f32(t, 4, uniq, inv, cnt)
+    assert int(cnt.item()) == 5                                     # cap + 1: "more than cap distinct values"
+    many = torch.randn(11648, device=dev, generator=g)
+    ops.dedup_f32(many, 64, torch.empty(64, device=dev), inv, cnt)
+    assert int(cnt.item()) == 65
+
+    M, N, K = 2912, 3072, 3072
+    x = torch.randn(M, K, device=dev, generator=g) * 2
+    w = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    b = torch.randn(N, device=dev, generator=g).bfloat16()
+    want = torch.nn.functional.silu(x.double()) @ w.double().t() + b.double()
+    for planes, tol in ((1, 4e-3), (2, 2e-5), (3, 8e-6)):
+        got = ops.linear_f32_tc(x, w, b, act_in=1, planes=planes)
+        r = (torch.linalg.vector_norm(got.double() - want) / torch.linalg.vector_norm(want)).item()
+        print(f"linear_f32_tc planes={planes}: rel-L2 vs fp64 {r:.3e}")
+        assert r < tol
+    small = torch.randn(300, 256, device=dev, generator=g)          # freq_dim-wide input of the first MLP layer
+    w0 = (torch.randn(N, 256, device=dev, generator=g) / 16).bfloat16()
+    got = ops.linear_f32_tc(small, w0, None, act_in=0, planes=2)
+    assert _rel(got.double(), small.double() @ w0.double().t()) < 2e-5
+
+
+def test_weight_edits_through_data_are_detected(dev):
+    """merge_lora / unmerge_lora edit ``weight.data`` in place (lora_utils.py:481-485, :595-599): no version counter
+    moves, but the per-call sampled fingerprint does — packed q|k|v copies and the cached cross-attention K/V follow."""
+    model, cfg = _native_model("tiny", dev)
+    tt, ctx, seq_len = _inputs(cfg, (3, 8, 12), True, dev)
+    kw = dict(x=tt["x"].bfloat16(), t=tt["t"], context=[c.bfloat16() for c in ctx], seq_len=seq_len,
+              y=tt["y"].bfloat16(), full_ref=tt["full_ref"].bfloat16(),
+              additional_control=tt["additional_control"].bfloat16(), density=tt["density"])
+    base = model(**kw).clone()
+    ps = dict(model.named_parameters())
+    g = torch.Generator(device=dev).manual_seed(5)
+    deltas = {k: (torch.randn(ps[k].shape, device=dev, generator=g) * 0.05).bfloat16()
+              for k in ("blocks.1.self_attn.k.weight", "blocks.0.cross_attn.v.weight")}
+    for k, d in deltas.items():
+        ps[k].data += d
+    merged = model(**kw).clone()
+    fresh, _ = _native_model("tiny", dev)
+    fp = dict(fresh.named_parameters())
+    for k in deltas:
+        fp[k].data.copy_(ps[k].data)
+    assert torch.equal(merged, fresh(**kw)) and not torch.equal(merged, base)
+    for k, d in deltas.items():
+        ps[k].data -= d
+    assert _rel(model(**kw), base) < 2e-2       # unmerged (bf16 add/sub need not round-trip bit-exactly)
+    assert model.engine().host_reads == 1
+
+
+def test_engine_created_before_module_to_cuda(dev):
+    """The reference pipelines build on the CPU, hook the model, and only then ``pipe.to(device)``: an engine created
+    while the parameters were on the CPU must follow them to the GPU."""
+    from flexam_b200.model import Wan2_2Transformer3DModel_FlexAM
+    from oracle import synth
+    ref_model, cfg = _native_model("tiny", dev)
+    m = Wan2_2Transformer3DModel_FlexAM(
+        model_type="ti2v", patch_size=cfg["patch_size"], text_len=cfg["text_len"], in_dim=cfg["in_dim"], dim=cfg["dim"],
+        ffn_dim=cfg["ffn_dim"], freq_dim=cfg["freq_dim"], text_dim=cfg["text_dim"], out_dim=cfg["out_dim"],
+        num_heads=cfg["num_heads"], num_layers=cfg["num_layers"], eps=cfg["eps"], add_ref_conv=True,
+        in_dim_ref_conv=cfg["out_dim"], add_cnn_block=True, in_dim_cnn_block=cfg["in_dim_cnn"],
+        out_dim_cnn_block=cfg["out_dim_cnn"], device="cpu")
+    m.load_state_dict({k: v.cpu() for k, v in ref_model.state_dict().items()}, strict=True)
+    eng = m.engine()                              # created on the CPU
+    assert eng.device.type == "cpu"
+    m = m.to(dev)
+    tt, ctx, seq_len = _inputs(cfg, (3, 8, 12), True, dev)
+    kw = dict(x=tt["x"].bfloat16(), t=tt["t"], context=[c.bfloat16() for c in ctx], seq_len=seq_len,
+              y=tt["y"].bfloat16(), full_ref=tt["full_ref"].bfloat16(),
+              additional_control=tt["additional_control"].bfloat16(), density=tt["density"])
+    assert torch.equal(m(**kw), ref_model(**kw)) and m.engine().device.type == "cuda"
+
+
+def test_sampling_loop_without_host_syncs_and_with_cuda_graphs(dev, golden_dir):
+    """After step 0 DenoiseLoop enqueues without a device->host read (known timestep structure, TeaCache schedule
+    computed before the loop, trusted weights / control inputs); with graph=True the transformer call of every
+    (batch, run / skip) variant is captured at its second occurrence and replayed. Same latents bit for bit."""
+    import loop_case
+    g = loop_case.golden(golden_dir)
+    ts = np.concatenate([g["timesteps"], g["timesteps"][-1:] * 0.5, g["timesteps"][-1:] * 0.25])   # 8 steps: variants recur
+    sig = np.concatenate([ts / np.float32(1000.0), np.zeros(1, np.float32)]).astype(np.float32)
+    g8 = {"timesteps": ts, "sigmas": sig}
+    outs = []
+    for graph in (False, True):
+        model, cfg = _native_model("tiny", dev)
+        saved = dict(loop_case.LOOP)
+        loop_case.LOOP["steps"] = 8
+        try:
+            out, decisions, loop = loop_case.run_native_loop(model, g8, dev, graph=graph)
+        finally:
+            loop_case.LOOP.update(saved)
+        torch.cuda.synchronize()
+        assert loop.host_reads == 2, loop.host_reads
+        if graph:
+            assert loop.graph_replays >= 2, (loop.graph_replays, decisions)
+        outs.append((out.clone(), decisions))
+    assert outs[0][1] == outs[1][1] and not all(outs[0][1])
+    assert torch.equal(outs[0][0], outs[1][0])
+
+
 def test_missing_extension_fails_loudly(monkeypatch):
     from flexam_b200 import lib
     monkeypatch.setattr(lib, "_lib", None)
