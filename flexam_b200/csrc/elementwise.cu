@@ -207,7 +207,7 @@ __device__ __forceinline__ uint32_t bf16x2_mul(uint32_t a, uint32_t b) {
 }
 
 template <int NV, int WPR>  // NV = 16-byte vectors (8 bf16) per lane = D / (256 * WPR)
-__global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const __grid_constant__ RmsParams p) {
+__global__ void __launch_bounds__(256, NV <= 4 ? 6 : 3) rmsnorm_rope_kernel(const __grid_constant__ RmsParams p) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[8];
@@ -249,11 +249,6 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const __grid_constant
     }
   }
   const uint4* wr = reinterpret_cast<const uint4*>(which == 0 ? p.w : p.w2) + c0;
-  uint4 wv[NV];
-  if (normed) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) wv[i] = __ldg(wr + i * 32 + lane);
-  }
 
   float ss = 0.f;
 #pragma unroll
@@ -276,8 +271,9 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const __grid_constant
     const int c = i * 32 + lane;  // vector index inside this warp's span
     uint4 ov = v[i];
     if (normed) {
+      const uint4 wv = __ldg(wr + c);   // 6 KB per tensor, L1-resident; loading it here keeps the kernel at <= 40 registers
       const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-      const uint32_t ww[4] = {wv[i].x, wv[i].y, wv[i].z, wv[i].w};
+      const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
       uint32_t o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -565,7 +561,7 @@ extern "C" int fx_fingerprint(const void* const* ptrs, const int64_t* nbytes, in
     set_error("fx_fingerprint: cudaMemsetAsync: %s", cudaGetErrorString(e));
     return FX_ERR_CUDA;
   }
-  fingerprint_kernel<<<dim3(8, n), 256, 0, s>>>(ptrs, reinterpret_cast<const long long*>(nbytes), n, stride,
+  fingerprint_kernel<<<dim3(4, n), 256, 0, s>>>(ptrs, reinterpret_cast<const long long*>(nbytes), n, stride,
                                                  reinterpret_cast<unsigned long long*>(out));
   FX_CHECK_LAUNCH("fx_fingerprint");
   return FX_OK;

@@ -177,7 +177,7 @@ class NativeEngine:
         self._fp_table = ops.fingerprint_table(list(P.values()))
         self._fp_ref = ops.fingerprint(self._fp_table, self.FP_STRIDE) if self._fp_table is not None else None
 
-    FP_STRIDE = 64   # every 64th 16-byte word: ~160 MB read for the 5 B-parameter model, a dense edit hits every sample
+    FP_STRIDE = 256  # every 256th 16-byte word: ~40 MB read for the 5 B-parameter model, a dense edit hits every sample
 
     def refresh_if_modified(self):
         if self._pvers() != self._versions:

@@ -54,6 +54,28 @@ def bench_fmha():
     want = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), v)
     got = out[:1, :512, :2].float()
     print(json.dumps({"case": "fmha_self_err", "rel": ((got - want).norm() / want.norm()).item()}))
+    # the reference's library attention on the same tensors (F.scaled_dot_product_attention: cuDNN / flash backend),
+    # timed the same way: what `attention()` (attention_utils.py:174-233) dispatches to without flash-attn
+    qt, kt, vt = (v5[:, :, i].transpose(1, 2) for i in range(3))
+    try:
+        ms_lib = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt))
+        print(json.dumps({"case": "sdpa_self (library)", "ms": ms_lib, "tflops": fl / ms_lib / 1e9}))
+        # steady state (1 s back to back, no flush): what both sustain under the power cap
+        for name, fn in (("fmha_self", lambda: ops.fmha(v5[:, :, 0], v5[:, :, 1], v5[:, :, 2], out, 128 ** -0.5)),
+                         ("sdpa_self (library)", lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt))):
+            n = 400
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(20):
+                fn()
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms1 = a.elapsed_time(b) / n
+            print(json.dumps({"case": name + " sustained x400", "ms": ms1, "tflops": fl / ms1 / 1e9}))
+    except Exception as exc:  # noqa: BLE001
+        print(json.dumps({"case": "sdpa_self (library)", "error": str(exc)[:200]}))
     kv = torch.randn(B * 512, 2 * H * 128, device=dev, generator=g).bfloat16().view(B, 512, 2, H, 128)
     ms = timeit(lambda: ops.fmha(v5[:, :, 0], kv[:, :, 0], kv[:, :, 1], out, 128 ** -0.5))
     print(json.dumps({"case": "fmha_cross", "ms": ms, "tflops": 4.0 * B * H * L * 512 * 128 / ms / 1e9}))
