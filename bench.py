@@ -544,6 +544,63 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+def run_t5(args):
+    """the umT5-XXL text encoder (24 layers, dim 4096, 64 heads, 5.7 B parameters) on the pipeline's
+    2 x 512 token ids, native vs the library form (stock torch bf16 ops) on the same GPU, with parity against the
+    bf16-policy oracle. Runs once per video in the real flow; a stress/parity case, not the bench line."""
+    import torch
+    from flexam_b200 import lib
+    from flexam_b200.text_encoder import WanT5EncoderModel
+    from oracle import t5_oracle as T
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    lib.check(lib.load().fx_check_device(dev.index), "fx_check_device")
+    cfg = T.T5_CONFIGS["real"]
+    m = WanT5EncoderModel(**cfg, device=dev)
+    g = torch.Generator(device=dev).manual_seed(99)
+    for name, p in m.named_parameters():
+        if "norm" in name:
+            p.data.fill_(1.0)
+        else:
+            std = 1.0 if name.startswith("token_embedding") else (0.5 if "pos_embedding" in name else p.shape[-1] ** -0.5)
+            if name.endswith("attn.q.weight"):
+                std *= 0.35          # T5 applies no 1/sqrt(d): the reference initialises q with (dim * dim_attn)^-0.5
+            p.data.copy_((torch.randn(p.shape, device=dev, generator=g) * std).to(p.dtype))
+    ids, mask = T.inputs(cfg, L=512, lens=PROMPT_LENS)
+    ids, mask = torch.from_numpy(ids).to(dev), torch.from_numpy(mask).to(dev)
+    B, L = ids.shape
+    flops = 2.0 * B * L * cfg["num_layers"] * (4 * cfg["dim"] * cfg["dim_attn"] + 3 * cfg["dim"] * cfg["dim_ffn"]) + \
+        4.0 * B * cfg["num_heads"] * L * L * 64 * cfg["num_layers"]
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            out = fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return out, e0.elapsed_time(e1) / steps
+    out, ms = timed(lambda: m(ids, mask)[0], args.steps, args.warmup)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        lib_out, lib_ms = timed(lambda: T.forward_library(sd, cfg, ids, mask), args.steps, args.warmup)
+        want = T.forward(_LazyF32(sd), cfg, ids, mask, policy="bf16")
+    rel = lambda a, b: (torch.linalg.vector_norm(a.float() - b.float()) / torch.linalg.vector_norm(b.float())).item()  # noqa: E731
+    print(json.dumps({
+        "workload": "umT5-XXL text encoder, 2 prompts padded to 512 tokens (pipeline _get_t5_prompt_embeds), bf16",
+        "ms": ms, "tflops_per_s": flops / ms / 1e9, "algorithmic_tflop": flops / 1e12, "gpu_launches": m.engine().launches,
+        "library_baseline": {"ms": lib_ms, "tflops_per_s": flops / lib_ms / 1e9,
+                             "what": "the module's forward in stock torch bf16 ops (cuBLAS Linear, einsum attention)"},
+        "speedup_vs_library": lib_ms / ms,
+        "parity": {"rel_l2_vs_oracle": rel(out, want), "native_rel_l2_vs_library": rel(out, lib_out),
+                   "library_rel_l2_vs_oracle": rel(lib_out, want), "gate": 1e-2, "checksum_sha256_16": output_checksum(out)}}))
+
+
 def run_loop(args):
     """BASELINE config 4: the full sampling loop (`full_edit`: first latent frame pinned, density 10 => the model sees
     0.1, guidance 6, flow-match Euler with shift 5) at 97 frames 512x896 through flexam_b200.sampler.DenoiseLoop — per
@@ -759,7 +816,7 @@ if __name__ == "__main__":
                     "around every launch, 3 extra steps outside the timed regions)")
     ap.add_argument("--loop-steps", type=int, default=50, help="sampling steps of --workload loop50")
     ap.add_argument("--graph", action="store_true", help="loop50: replay the transformer call from CUDA graphs (N = 1)")
-    ap.add_argument("--workload", default="config2", choices=["config2", "long", "loop50"],
+    ap.add_argument("--workload", default="config2", choices=["config2", "long", "loop50", "t5"],
                     help="config2 = the metric's workload (default); long = BASELINE config 5, 193 frames 704x1280 "
                          "(43,120 tokens + 880 ref): a parity/stress case, not the bench line")
     a = ap.parse_args()
@@ -771,5 +828,7 @@ if __name__ == "__main__":
         run_reference(a)
     elif a.workload == "loop50":
         run_loop(a)
+    elif a.workload == "t5":
+        run_t5(a)
     else:
         run_native(a)

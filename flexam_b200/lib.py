@@ -48,6 +48,12 @@ SIGNATURES = {
     "fx_sub_f32": [_vp, _vp, _vp, _i64, _vp],
     "fx_fingerprint": [_vp, _vp, _i, _i, _vp, _vp],
     "fx_tune": [C.c_char_p, _i],
+    # umT5 text encoder (flexam_b200/text_encoder.py)
+    "fx_embedding_bf16": [_vp, _vp, _vp, _i64, _i, _i64, _vp],
+    "fx_t5_layernorm": [_vp, _vp, _vp, _i, _i, _f, _vp],
+    "fx_t5_attention": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _vp],
+    "fx_add_bf16": [_vp, _vp, _i64, _vp],
+    "fx_gated_gelu_bf16": [_vp, _vp, _vp, _i64, _vp],
     "fx_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "fx_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
     # fp32 verification mode (flexam_b200/precise.py)

@@ -484,3 +484,55 @@ def groupnorm_silu_f32(x: torch.Tensor, groups: int, eps: float, gamma: torch.Te
                                          _stream())
     _l.check(st, "fx_groupnorm_silu_f32")
     return y
+
+
+# ----------------------------------------------------------------------------------------------------------
+# umT5 text encoder operators (see include/flexam_b200.h and flexam_b200/text_encoder.py)
+# ----------------------------------------------------------------------------------------------------------
+def embedding(ids: torch.Tensor, table: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _req(table, bf16, "embedding.table"), _req(out, bf16, "embedding.out")
+    if ids.dtype != torch.int64 or not ids.is_cuda or not ids.is_contiguous() or not out.is_contiguous():
+        raise _l.FlexamNativeError("embedding: contiguous int64 CUDA ids and a contiguous out required")
+    rows, D = ids.numel(), table.shape[1]
+    _l.check(_l.load().fx_embedding_bf16(_p(ids), _p(table), _p(out), rows, D, table.shape[0], _stream()),
+             "fx_embedding_bf16")
+    return out
+
+
+def t5_layernorm(x: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    _req(x, bf16, "t5_layernorm.x"), _req(weight, bf16, "t5_layernorm.weight"), _req(out, bf16, "t5_layernorm.out")
+    if not (x.is_contiguous() and out.is_contiguous()):
+        raise _l.FlexamNativeError("t5_layernorm: contiguous tensors required")
+    M, D = x.shape
+    _l.check(_l.load().fx_t5_layernorm(_p(x), _p(weight), _p(out), M, D, eps, _stream()), "fx_t5_layernorm")
+    return out
+
+
+def t5_attention(qkv: torch.Tensor, bias_rel: torch.Tensor, mask: Optional[torch.Tensor], out: torch.Tensor, B: int,
+                 L: int, H: int) -> torch.Tensor:
+    _req(qkv, bf16, "t5_attention.qkv"), _req(bias_rel, bf16, "t5_attention.bias_rel"), _req(out, bf16, "t5_attention.out")
+    if mask is not None:
+        _req(mask, i32, "t5_attention.mask")
+    if tuple(bias_rel.shape) != (H, 2 * L - 1) or not bias_rel.is_contiguous() or qkv.shape[0] != B * L:
+        raise _l.FlexamNativeError("t5_attention: bias_rel must be contiguous [H, 2L-1]; qkv rows must be B*L")
+    st = _l.load().fx_t5_attention(_p(qkv), qkv.stride(0), _p(bias_rel), _p(mask), _p(out), out.stride(0), B, L, H,
+                                   _stream())
+    _l.check(st, "fx_t5_attention")
+    return out
+
+
+def add_bf16_(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    _req(x, bf16, "add_bf16.x"), _req(y, bf16, "add_bf16.y")
+    if not (x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()):
+        raise _l.FlexamNativeError("add_bf16: contiguous tensors of equal size required")
+    _l.check(_l.load().fx_add_bf16(_p(x), _p(y), x.numel(), _stream()), "fx_add_bf16")
+    return x
+
+
+def gated_gelu(fc1: torch.Tensor, gate: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    for n, t in (("fc1", fc1), ("gate", gate), ("out", out)):
+        _req(t, bf16, "gated_gelu." + n)
+        if not t.is_contiguous() or t.numel() != fc1.numel():
+            raise _l.FlexamNativeError("gated_gelu: contiguous tensors of equal size required")
+    _l.check(_l.load().fx_gated_gelu_bf16(_p(fc1), _p(gate), _p(out), fc1.numel(), _stream()), "fx_gated_gelu_bf16")
+    return out

@@ -254,6 +254,29 @@ int fx_fingerprint(const void* const* ptrs, const int64_t* nbytes, int n, int st
  * "gemm_n_span" (rasterisation of the CTA-pair GEMM; 0 / -1 = built-in choice). Not a compute-path switch. */
 int fx_tune(const char* name, int value);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * umT5 text encoder (FlexAM/models/wan_text_encoder.py): WanT5EncoderModel.forward :291-304 as the
+ * pipeline calls it (_get_t5_prompt_embeds: 2 x 512 token ids + the tokenizer's attention mask, bf16 weights AND
+ * activations). The q|k|v / o / gated-FFN projections are fx_gemm_bf16 calls; these are the remaining operators, each
+ * with the reference's bf16 rounding points:
+ *   fx_embedding_bf16   out bf16 [rows, D] = table bf16 [vocab, D][ids[rows]]                        (token_embedding :296)
+ *   fx_t5_layernorm     out = bf16(w * bf16(x * rsqrt(mean_fp32(x^2) + eps)))  x, out bf16 [M, D]        (T5LayerNorm :51-56)
+ *   fx_t5_attention     qkv bf16 [B*L, ld] = q | k | v (each H*64 wide); head_dim 64, L <= 512, NO 1/sqrt(d) scaling:
+ *                       s_ij = bf16(bf16(q_i.k_j) + bias_rel[h][j-i+L-1]), keys with mask[b][j] == 0 get finfo(bf16).min,
+ *                       p = bf16(softmax_fp32(s)), out[b*L+i][h*64 ..] = bf16(sum_j p_ij v_j)              (T5Attention :75-109)
+ *                       bias_rel bf16 [H][2L-1] = pos_embedding[bucket(j-i)][h] (T5RelativeEmbedding :219-253), mask int32
+ *                       [B, L] or NULL
+ *   fx_add_bf16         x = bf16(x + y), n % 8 == 0                                       (bf16 residual stream :161-162)
+ *   fx_gated_gelu_bf16  out = bf16(fc1 * GELU(gate)), GELU as the reference's chain of bf16 tensor ops :38-41, :126
+ */
+int fx_embedding_bf16(const int64_t* ids, const void* table, void* out, int64_t rows, int D, int64_t vocab,
+                      void* stream);
+int fx_t5_layernorm(const void* x, const void* weight, void* out, int M, int D, float eps, void* stream);
+int fx_t5_attention(const void* qkv, int64_t ld, const void* bias_rel, const int32_t* mask, void* out, int64_t ldo,
+                    int B, int L, int H, void* stream);
+int fx_add_bf16(void* x, const void* y, int64_t n, void* stream);
+int fx_gated_gelu_bf16(const void* fc1, const void* gate, void* out, int64_t n, void* stream);
+
 /* Small utility kernels used by the host glue. */
 int fx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int fx_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);

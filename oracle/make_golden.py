@@ -33,7 +33,8 @@ CASES = {
     "tiny_frac": ("tiny", (3, 8, 12), "frac"),
     "real2_frac": ("real2", (5, 16, 28), "frac"),
 }
-DEFAULT = ("tiny_tok", "tiny_sample", "real2_tok", "tiny_frac", "real2_frac", "tiny_loop", "rope_tables")
+DEFAULT = ("tiny_tok", "tiny_sample", "real2_tok", "tiny_frac", "real2_frac", "tiny_loop", "rope_tables", "t5_tiny",
+           "t5_real2")
 
 
 def run_case(name: str):
@@ -135,6 +136,35 @@ def run_loop(name: str = "tiny_loop"):
                         step0=trace[0].numpy().astype(np.float32))
 
 
+T5_CASES = {
+    # name: (t5 config, padded length, prompt lengths)
+    "t5_tiny": ("tiny", 64, (11, 40)),
+    "t5_real2": ("real2", 512, (37, 120)),      # real width and head layout, 2 of 24 layers, the pipeline's 512-token padding
+}
+
+
+def run_t5(name: str):
+    """The REAL umT5 encoder (FlexAM/models/wan_text_encoder.py:256-304) on synthetic weights and token ids, fp32 CPU."""
+    from oracle import t5_oracle as T
+    cfg_name, L, lens = T5_CASES[name]
+    cfg = T.T5_CONFIGS[cfg_name]
+    t0 = time.time()
+    model = ref_import.build_reference_t5(cfg).eval()
+    sd = {k: torch.from_numpy(v) for k, v in T.state_dict(cfg).items()}
+    model.load_state_dict(sd, strict=True)
+    ids, mask = T.inputs(cfg, L=L, lens=lens)
+    with torch.no_grad():
+        ref = model(torch.from_numpy(ids), torch.from_numpy(mask))[0]
+        mine = T.forward(sd, cfg, torch.from_numpy(ids), torch.from_numpy(mask))
+    rel = ((ref - mine).norm() / ref.norm()).item()
+    print(f"{name}: reference out {tuple(ref.shape)} |max| {ref.abs().max():.3f}  oracle rel-L2 {rel:.2e}  ({time.time() - t0:.1f}s)")
+    assert rel < 2e-5, "T5 oracle restatement disagrees with the reference"
+    step = 4 if L >= 256 else 1          # every 4th token row of the long fixture keeps the file small
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"),
+                        out=ref[:, ::step].numpy().astype(np.float32),
+                        meta=np.array([L, step] + list(lens), dtype=np.int64), config=np.array(cfg_name))
+
+
 def run_rope(name: str = "rope_tables"):
     """RoPE tables of the REAL reference module, default and after enable_riflex() with its default arguments
     (:774-788): a few position rows of the complex128 / complex64 tables as float64 (cos, sin)."""
@@ -156,4 +186,5 @@ def run_rope(name: str = "rope_tables"):
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     for n in (sys.argv[1:] or DEFAULT):
-        run_loop(n) if n == "tiny_loop" else run_rope(n) if n == "rope_tables" else run_case(n)
+        (run_loop(n) if n == "tiny_loop" else run_rope(n) if n == "rope_tables" else run_t5(n) if n in T5_CASES
+         else run_case(n))

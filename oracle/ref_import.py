@@ -116,3 +116,14 @@ def build_reference_model(cfg: dict):
         out_dim=cfg["out_dim"], num_heads=cfg["num_heads"], num_layers=cfg["num_layers"], qk_norm=True,
         cross_attn_norm=True, eps=cfg["eps"], add_ref_conv=True, in_dim_ref_conv=cfg["out_dim"],
         add_cnn_block=True, in_dim_cnn_block=cfg["in_dim_cnn"], out_dim_cnn_block=cfg["out_dim_cnn"])
+
+
+def build_reference_t5(cfg: dict):
+    """The REAL umT5 encoder class (FlexAM/models/wan_text_encoder.py:256-304) built as the FlexAM yaml does
+    (shared_pos False, dropout 0)."""
+    import_reference()          # installs the diffusers stubs
+    name = "FlexAM.models.wan_text_encoder"
+    mod = sys.modules.get(name) or _load(name, os.path.join(REF_ROOT, "FlexAM", "models", "wan_text_encoder.py"))
+    return mod.WanT5EncoderModel(vocab=cfg["vocab"], dim=cfg["dim"], dim_attn=cfg["dim_attn"], dim_ffn=cfg["dim_ffn"],
+                                 num_heads=cfg["num_heads"], num_layers=cfg["num_layers"],
+                                 num_buckets=cfg["num_buckets"], shared_pos=False, dropout=0.0)

@@ -360,7 +360,41 @@ def fingerprint(table, stride):
     return torch.stack(out)
 
 
-NAMES = ("groupnorm_partials", "groupnorm_silu_partials", "linear_f32_tc", "dedup_f32", "fingerprint_table", "fingerprint", "gemm", "ln_modulate", "modulation_tables", "ln_scale_shift", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
+def embedding(ids, table, out):
+    return out.copy_(table[ids.view(-1)].view(out.shape))
+
+
+def t5_layernorm(x, weight, out, eps=1e-6):
+    y = _rb(x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + eps))
+    return out.copy_((weight.float() * y).to(bf16))
+
+
+def t5_attention(qkv, bias_rel, mask, out, B, L, H):
+    A = H * 64
+    q, k, v = (qkv[:, i * A:(i + 1) * A].float().view(B, L, H, 64) for i in range(3))
+    rel = torch.arange(L).unsqueeze(0) - torch.arange(L).unsqueeze(1) + L - 1          # [i, j] -> j - i + L - 1
+    bias = bias_rel.float()[:, rel].unsqueeze(0)                                         # [1, H, L, L]
+    s = _rb(_rb(torch.einsum("binc,bjnc->bnij", q, k)) + bias)
+    if mask is not None:
+        s = s.masked_fill(mask.view(B, 1, 1, L) == 0, torch.finfo(bf16).min)
+    p = _rb(F.softmax(s, dim=-1))
+    o = torch.einsum("bnij,bjnc->binc", p, v).reshape(B * L, A)
+    out[:, :A].copy_(o.to(bf16))
+    return out
+
+
+def add_bf16_(x, y):
+    return x.copy_((x.float() + y.float()).to(bf16))
+
+
+def gated_gelu(fc1, gate, out):
+    g = gate.float()
+    inner = _rb(g + _rb(0.044715 * _rb(g * g * g)))
+    th = _rb(torch.tanh(_rb(math.sqrt(2.0 / math.pi) * inner)))
+    return out.copy_((fc1.float() * _rb(_rb(0.5 * g) * _rb(1.0 + th))).to(bf16))
+
+
+NAMES = ("embedding", "t5_layernorm", "t5_attention", "add_bf16_", "gated_gelu", "groupnorm_partials", "groupnorm_silu_partials", "linear_f32_tc", "dedup_f32", "fingerprint_table", "fingerprint", "gemm", "ln_modulate", "modulation_tables", "ln_scale_shift", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
                  "linear_f32", "nchw_to_nhwc", "im2col3x3", "groupnorm_silu", "swap01", "cfg_euler_step", "add_", "sub", "split3", "join3",
                  "ln_f32", "rmsnorm_rope_f32", "gelu_f32_", "gated_residual_f32_", "attention_f32",
                  "groupnorm_silu_f32")

@@ -642,6 +642,106 @@ def test_sampling_loop_without_host_syncs_and_with_cuda_graphs(dev, golden_dir):
     assert torch.equal(outs[0][0], outs[1][0])
 
 
+# ------------------------------------------------------------------------------------------------------
+# umT5 text encoder (FlexAM/models/wan_text_encoder.py)
+# ------------------------------------------------------------------------------------------------------
+def test_t5_operators(dev):
+    from flexam_b200 import ops
+    from flexam_b200.text_encoder import relative_position_bucket
+    g = torch.Generator(device=dev).manual_seed(51)
+    B, L, H, D = 2, 200, 4, 1024
+    A = H * 64
+    table = torch.randn(300, D, device=dev, generator=g).bfloat16()
+    ids = torch.randint(0, 300, (B, L), device=dev, generator=g)
+    x = torch.empty(B * L, D, device=dev, dtype=torch.bfloat16)
+    ops.embedding(ids, table, x)
+    assert torch.equal(x, table[ids.view(-1)])
+    w = (1 + 0.1 * torch.randn(D, device=dev, generator=g)).bfloat16()
+    h = torch.empty_like(x)
+    ops.t5_layernorm(x, w, h)
+    y = (x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-6)).bfloat16()
+    assert _rel(h, (w * y).float()) < 2e-3
+    qkv = (torch.randn(B * L, 3 * A, device=dev, generator=g) * 0.35).bfloat16()
+    pos = (torch.randn(32, H, device=dev, generator=g) * 0.5).bfloat16()
+    bucket = relative_position_bucket(L, L, 32)
+    d = torch.cat([bucket[L - 1, :L - 1], bucket[0]]).to(dev)
+    bias_rel = pos[d].t().contiguous()
+    mask = torch.ones(B, L, device=dev, dtype=torch.int32)
+    mask[0, 150:] = 0
+    mask[1, 37:] = 0
+    out = torch.full((B * L, A), float("nan"), device=dev, dtype=torch.bfloat16)
+    ops.t5_attention(qkv, bias_rel, mask, out, B, L, H)
+    q, k, v = (qkv[:, i * A:(i + 1) * A].float().view(B, L, H, 64) for i in range(3))
+    bias = pos.float()[bucket.to(dev)].permute(2, 0, 1).unsqueeze(0)                      # the reference's [1, n, L, L]
+    sc = (torch.einsum("binc,bjnc->bnij", q, k).bfloat16().float() + bias).bfloat16().float()
+    sc = sc.masked_fill(mask.view(B, 1, 1, L) == 0, torch.finfo(torch.bfloat16).min)
+    want = torch.einsum("bnij,bjnc->binc", sc.softmax(-1).bfloat16().float(), v).reshape(B * L, A)
+    assert torch.isfinite(out.float()).all() and _rel(out, want) < 4e-3
+    a, b2 = torch.randn(B * L, D, device=dev, generator=g).bfloat16(), torch.randn(B * L, D, device=dev, generator=g).bfloat16()
+    s_ = a.clone()
+    ops.add_bf16_(s_, b2)
+    assert torch.equal(s_, a + b2)
+    gg = torch.empty_like(a)
+    ops.gated_gelu(a, b2, gg)
+    gelu = 0.5 * b2 * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (b2 + 0.044715 * torch.pow(b2, 3.0))))   # bf16 op chain
+    assert _rel(gg, (a * gelu).float()) < 4e-3
+
+
+def _t5_model(cfg_name, dev):
+    from flexam_b200.text_encoder import WanT5EncoderModel
+    from oracle import t5_oracle as T
+    cfg = T.T5_CONFIGS[cfg_name]
+    m = WanT5EncoderModel(**cfg, device=dev)
+    m.load_state_dict(T.state_dict_torch(cfg, dev, torch.bfloat16), strict=True)
+    return m, cfg
+
+
+@pytest.mark.parametrize("name", ["t5_tiny", "t5_real2"])
+def test_t5_encoder_matches_reference_golden(dev, golden_dir, name):
+    """Native umT5 encoder vs the REAL module's fp32 CPU output (tests/golden, oracle/make_golden.py) and vs the
+    bf16-policy oracle (the module as the pipeline runs it: bf16 weights and activations) executed on the GPU."""
+    from oracle import t5_oracle as T
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    L, step = int(g["meta"][0]), int(g["meta"][1])
+    lens = tuple(int(v) for v in g["meta"][2:])
+    m, cfg = _t5_model(str(g["config"]), dev)
+    ids, mask = T.inputs(cfg, L=L, lens=lens)
+    ids, mask = torch.from_numpy(ids).to(dev), torch.from_numpy(mask).to(dev)
+    out = m(ids, mask)[0]
+    torch.cuda.synchronize()
+    assert out.shape == (2, L, cfg["dim"]) and out.dtype == torch.bfloat16 and torch.isfinite(out.float()).all()
+    sd = {k: v.float() for k, v in m.state_dict().items()}
+    want = T.forward(sd, cfg, ids, mask, policy="bf16")
+    rel_b, rel_g = _rel(out, want), _rel(out[:, ::step].cpu(), torch.from_numpy(g["out"]))
+    gap = _rel(want[:, ::step].cpu(), torch.from_numpy(g["out"]))
+    print(f"{name}: native vs bf16-policy oracle {rel_b:.3e}; native vs fp32 reference golden {rel_g:.3e}; "
+          f"bf16-policy oracle vs fp32 golden {gap:.3e}")
+    assert rel_b < BF16_GATE                       # north star: within 1e-2 of the reference's bf16 path
+    assert rel_g < 2 * gap + 5e-3                   # and no further from fp32 than that path itself is
+
+
+def test_t5_encoder_full_depth(dev):
+    """The umT5-XXL encoder at full size (24 layers, dim 4096, 64 heads, 256,384-token vocabulary: 5.7 B parameters) on
+    2 x 512 token ids, against the bf16-policy oracle on the GPU."""
+    from oracle import t5_oracle as T
+    m, cfg = _t5_model("real", dev)
+    assert cfg["num_layers"] == 24
+    ids, mask = T.inputs(cfg, L=512, lens=(37, 120))
+    ids, mask = torch.from_numpy(ids).to(dev), torch.from_numpy(mask).to(dev)
+    out = m(ids, mask)[0]
+    torch.cuda.synchronize()
+
+    class Lazy(dict):
+        def __getitem__(self, k):
+            return dict.__getitem__(self, k).float()
+    want = T.forward(Lazy({k: v.detach() for k, v in m.state_dict().items()}), cfg, ids, mask, policy="bf16")
+    rel = _rel(out, want)
+    # the rows the pipeline keeps (u[:v] for the real prompt lengths, _get_t5_prompt_embeds) are what matters downstream
+    kept = torch.cat([out[0, :37], out[1, :120]]), torch.cat([want[0, :37], want[1, :120]])
+    print(f"umT5-XXL (24 layers): native vs bf16-policy oracle rel-L2 {rel:.3e}; on the kept prompt rows {_rel(*kept):.3e}")
+    assert rel < BF16_GATE and _rel(*kept) < BF16_GATE
+
+
 def test_missing_extension_fails_loudly(monkeypatch):
     from flexam_b200 import lib
     monkeypatch.setattr(lib, "_lib", None)

@@ -218,10 +218,6 @@ def test_installed_reference_module_with_its_own_teacache_and_cfg_skip(monkeypat
     native.enable_teacache(tc["coefficients"], L["steps"], tc["rel_l1_thresh"], tc["num_skip_start_steps"], offload=False)
     native.enable_cfg_skip(L["cfg_skip_ratio"], L["steps"])
     assert type(native.teacache).__module__.endswith("cache_utils")      # the reference's class, not this package's
-    decisions = []
-    real_decide = fx._tc.decide
-    monkeypatch.setattr(fx._tc, "decide", lambda t, m, c: (lambda r: (decisions.append(bool(r)) if c else None, r)[1])(
-        real_decide(t, m, c)))
     from oracle import make_golden
     lt = make_golden.loop_tensors(cfg, *L["grid"])
     loop = DenoiseLoop(native, lt["latents"], lt["mask"], lt["masked_video_latents"], lt["mask_latents"],
@@ -229,8 +225,24 @@ def test_installed_reference_module_with_its_own_teacache_and_cfg_skip(monkeypat
                        lt["negative_prompt_embeds"], lt["prompt_embeds"], density=L["density"],
                        guidance_scale=L["guidance"])
     out = loop.run(g["timesteps"], g["sigmas"])
-    assert decisions == [bool(d) for d in g["decisions"]]
+    # the decisions of all steps are computed before the loop from the reference's own TeaCache object (its thresholds,
+    # its np.poly1d rescale function, its counters) and must be the ones the unmodified module took
+    assert loop.decisions == [bool(d) for d in g["decisions"]]
     assert _rel(out, torch.from_numpy(g["out"])) < 1e-2
+    # the per-call form (the reference pipeline's own loop calls forward step by step): same decisions through decide()
+    native.enable_teacache(tc["coefficients"], L["steps"], tc["rel_l1_thresh"], tc["num_skip_start_steps"], offload=False)
+    native.enable_cfg_skip(L["cfg_skip_ratio"], L["steps"])
+    decisions = []
+    real_decide = fx._tc.decide
+    monkeypatch.setattr(fx._tc, "decide", lambda t, m, c: (lambda r: (decisions.append(bool(r)) if c else None, r)[1])(
+        real_decide(t, m, c)))
+    monkeypatch.setattr(DenoiseLoop, "teacache_schedule", lambda self, ts: None)
+    loop2 = DenoiseLoop(native, lt["latents"], lt["mask"], lt["masked_video_latents"], lt["mask_latents"],
+                        lt["control_video_latents"], lt["additional_control"], lt["ref_image_latents"],
+                        lt["negative_prompt_embeds"], lt["prompt_embeds"], density=L["density"],
+                        guidance_scale=L["guidance"])
+    out2 = loop2.run(g["timesteps"], g["sigmas"])
+    assert decisions == [bool(d) for d in g["decisions"]] and torch.equal(out2, out)
 
 
 # ------------------------------------------------------------------------------------------------------
