@@ -566,7 +566,7 @@ def run_t5(args):
         else:
             std = 1.0 if name.startswith("token_embedding") else (0.5 if "pos_embedding" in name else p.shape[-1] ** -0.5)
             if name.endswith("attn.q.weight"):
-                std *= 0.35          # T5 applies no 1/sqrt(d): the reference initialises q with (dim * dim_attn)^-0.5
+                std *= 0.2           # T5 applies no 1/sqrt(d): the reference initialises q with (dim * dim_attn)^-0.5
             p.data.copy_((torch.randn(p.shape, device=dev, generator=g) * std).to(p.dtype))
     ids, mask = T.inputs(cfg, L=512, lens=PROMPT_LENS)
     ids, mask = torch.from_numpy(ids).to(dev), torch.from_numpy(mask).to(dev)

@@ -53,7 +53,7 @@ SIGNATURES = {
     "fx_t5_layernorm": [_vp, _vp, _vp, _i, _i, _f, _vp],
     "fx_t5_attention": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _vp],
     "fx_add_bf16": [_vp, _vp, _i64, _vp],
-    "fx_gated_gelu_bf16": [_vp, _vp, _vp, _i64, _vp],
+    "fx_gated_gelu_bf16": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _vp],
     "fx_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "fx_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
     # fp32 verification mode (flexam_b200/precise.py)

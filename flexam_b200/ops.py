@@ -530,9 +530,13 @@ def add_bf16_(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
 
 
 def gated_gelu(fc1: torch.Tensor, gate: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out = bf16(fc1 * GELU(gate)) on [M, N] views (row strides free: the two halves of one packed GEMM output)."""
     for n, t in (("fc1", fc1), ("gate", gate), ("out", out)):
         _req(t, bf16, "gated_gelu." + n)
-        if not t.is_contiguous() or t.numel() != fc1.numel():
-            raise _l.FlexamNativeError("gated_gelu: contiguous tensors of equal size required")
-    _l.check(_l.load().fx_gated_gelu_bf16(_p(fc1), _p(gate), _p(out), fc1.numel(), _stream()), "fx_gated_gelu_bf16")
+        if t.dim() != 2 or t.shape != fc1.shape:
+            raise _l.FlexamNativeError("gated_gelu: 2-D tensors of equal shape required")
+    M, N = fc1.shape
+    st = _l.load().fx_gated_gelu_bf16(_p(fc1), fc1.stride(0), _p(gate), gate.stride(0), _p(out), out.stride(0), M, N,
+                                      _stream())
+    _l.check(st, "fx_gated_gelu_bf16")
     return out

@@ -58,7 +58,9 @@ class T5Engine:
             self.blk.append({
                 "wqkv": torch.cat([P[p + "attn.q.weight"], P[p + "attn.k.weight"], P[p + "attn.v.weight"]], 0).contiguous(),
                 "wo": P[p + "attn.o.weight"], "n1": P[p + "norm1.weight"], "n2": P[p + "norm2.weight"],
-                "wg": P[p + "ffn.gate.0.weight"], "w1": P[p + "ffn.fc1.weight"], "w2": P[p + "ffn.fc2.weight"],
+                # gate | fc1 as ONE projection (N = 2 * dim_ffn): 4.3 waves of 256x256 tiles instead of 2 x 2.2 at M = 1024
+                "wgu": torch.cat([P[p + "ffn.gate.0.weight"], P[p + "ffn.fc1.weight"]], 0).contiguous(),
+                "w2": P[p + "ffn.fc2.weight"],
                 "pos": P[p + "pos_embedding.embedding.weight"],
             })
         self._versions = tuple(p._version for p in P.values())
@@ -101,8 +103,8 @@ class T5Engine:
         qkv = self._buf("qkv", (M, 3 * A), bf16)
         att = self._buf("att", (M, A), bf16)
         y = self._buf("y", (M, D), bf16)
-        g = self._buf("gate", (M, Fd), bf16)
-        u = self._buf("fc1", (M, Fd), bf16)
+        gu = self._buf("gate_fc1", (M, 2 * Fd), bf16)
+        u = self._buf("ffn", (M, Fd), bf16)
         for i, w in enumerate(self.blk):
             ops.t5_layernorm(x, w["n1"], h)
             ops.gemm(h, w["wqkv"], None, qkv, FX_EPI_BF16)
@@ -110,12 +112,11 @@ class T5Engine:
             ops.gemm(att, w["wo"], None, y, FX_EPI_BF16)
             ops.add_bf16_(x, y)                                      # x = x + attn(norm1(x))            :161
             ops.t5_layernorm(x, w["n2"], h)
-            ops.gemm(h, w["wg"], None, g, FX_EPI_BF16)
-            ops.gemm(h, w["w1"], None, u, FX_EPI_BF16)
-            ops.gated_gelu(u, g, u)                                  # fc1(x) * GELU(gate(x))            :126
+            ops.gemm(h, w["wgu"], None, gu, FX_EPI_BF16)
+            ops.gated_gelu(gu[:, Fd:], gu[:, :Fd], u)                # fc1(x) * GELU(gate(x))            :126
             ops.gemm(u, w["w2"], None, y, FX_EPI_BF16)
             ops.add_bf16_(x, y)                                      # x = x + ffn(norm2(x))             :162
-            self.launches += 11
+            self.launches += 10
         out = torch.empty((M, D), dtype=bf16, device=dev)
         ops.t5_layernorm(x, self.params["norm.weight"], out)
         self.launches += 2

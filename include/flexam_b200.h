@@ -267,7 +267,10 @@ int fx_tune(const char* name, int value);
  *                       bias_rel bf16 [H][2L-1] = pos_embedding[bucket(j-i)][h] (T5RelativeEmbedding :219-253), mask int32
  *                       [B, L] or NULL
  *   fx_add_bf16         x = bf16(x + y), n % 8 == 0                                       (bf16 residual stream :161-162)
- *   fx_gated_gelu_bf16  out = bf16(fc1 * GELU(gate)), GELU as the reference's chain of bf16 tensor ops :38-41, :126
+ *   fx_gated_gelu_bf16  out[M, N] = bf16(fc1 * GELU(gate)), GELU as the reference's chain of bf16 tensor ops :38-41, :126;
+ *                       row strides ld1 / ldg / ldo in elements (fc1 and gate are the two halves of ONE packed GEMM output)
+ *   fx_t5_attention runs on tcgen05: S = Q K^T for all (<= 512) keys of a 128-query tile into the 512 TMEM columns, softmax
+ *                       in TMEM, P (bf16 pairs, in place) as the A operand of O = P V
  */
 int fx_embedding_bf16(const int64_t* ids, const void* table, void* out, int64_t rows, int D, int64_t vocab,
                       void* stream);
@@ -275,7 +278,8 @@ int fx_t5_layernorm(const void* x, const void* weight, void* out, int M, int D, 
 int fx_t5_attention(const void* qkv, int64_t ld, const void* bias_rel, const int32_t* mask, void* out, int64_t ldo,
                     int B, int L, int H, void* stream);
 int fx_add_bf16(void* x, const void* y, int64_t n, void* stream);
-int fx_gated_gelu_bf16(const void* fc1, const void* gate, void* out, int64_t n, void* stream);
+int fx_gated_gelu_bf16(const void* fc1, int64_t ld1, const void* gate, int64_t ldg, void* out, int64_t ldo, int64_t M,
+                       int N, void* stream);
 
 /* Small utility kernels used by the host glue. */
 int fx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);

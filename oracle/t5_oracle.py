@@ -135,7 +135,7 @@ def param_specs(cfg: dict):
     specs = [("token_embedding.weight", (cfg["vocab"], D), 1.0, 0.0)]
     for i in range(cfg["num_layers"]):
         p = f"blocks.{i}."
-        specs += [(p + "norm1.weight", (D,), 0.1, 1.0), (p + "attn.q.weight", (A, D), 1.5 * D ** -0.5 / 8 ** 0.5, 0.0),
+        specs += [(p + "norm1.weight", (D,), 0.1, 1.0), (p + "attn.q.weight", (A, D), 0.2 * D ** -0.5, 0.0),   # no 1/sqrt(d) in T5: logits of std ~1.6
                   (p + "attn.k.weight", (A, D), D ** -0.5, 0.0), (p + "attn.v.weight", (A, D), D ** -0.5, 0.0),
                   (p + "attn.o.weight", (D, A), A ** -0.5, 0.0), (p + "norm2.weight", (D,), 0.1, 1.0),
                   (p + "ffn.gate.0.weight", (Fd, D), D ** -0.5, 0.0), (p + "ffn.fc1.weight", (Fd, D), D ** -0.5, 0.0),
