@@ -141,8 +141,19 @@ linear_f32_kernel(const float* in, long long ldi, const __nv_bfloat16* w, long l
 // -------------------------------------------------------------------------------------------------
 // CNN control fuser helpers (cnn_conv1..5 :680-711,:868-881), activations channel-last [P, C]
 // -------------------------------------------------------------------------------------------------
+// dense pixel index p = (f*H + y)*W + x -> row of the zero-padded grid [F, H+2, W+2] (interior position (y+1, x+1)):
+// the layout the implicit-GEMM convolution reads (fx_conv_gemm_bf16). pad_H == 0: dense rows.
+__device__ __forceinline__ long long padded_row(long long p, int pad_H, int pad_W) {
+  if (pad_H == 0) return p;
+  const long long hw = static_cast<long long>(pad_H) * pad_W;
+  const long long f = p / hw;
+  const int r = static_cast<int>(p - f * hw);
+  const int y = r / pad_W, x = r - y * pad_W;
+  return (f * (pad_H + 2) + y + 1) * (pad_W + 2) + x + 1;
+}
+
 __global__ void nchw_to_nhwc_kernel(const __nv_bfloat16* src, __nv_bfloat16* dst, long long ldd, int c0, int C,
-                                    long long P) {
+                                    long long P, int pad_H, int pad_W) {
   __shared__ __nv_bfloat16 tile[32][33];
   const long long p0 = static_cast<long long>(blockIdx.x) * 32;
   const int cb = blockIdx.y * 32;
@@ -155,7 +166,7 @@ __global__ void nchw_to_nhwc_kernel(const __nv_bfloat16* src, __nv_bfloat16* dst
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const long long pp = p0 + j;
     const int c = cb + threadIdx.x;
-    if (c < C && pp < P) dst[pp * ldd + c0 + c] = tile[threadIdx.x][j];
+    if (c < C && pp < P) dst[padded_row(pp, pad_H, pad_W) * ldd + c0 + c] = tile[threadIdx.x][j];
   }
 }
 
@@ -228,7 +239,8 @@ groupnorm_stats_kernel(const __nv_bfloat16* x, long long P, int C, int G, float 
 
 __global__ void groupnorm_apply_kernel(const __nv_bfloat16* x, long long P, int C, int G,
                                        const __nv_bfloat16* gamma, const __nv_bfloat16* beta, const float* stats,
-                                       const float* resid, float* y_f32, __nv_bfloat16* y_bf16) {
+                                       const float* resid, float* y_f32, __nv_bfloat16* y_bf16, int pad_H = 0,
+                                       int pad_W = 0, long long ld_bf16 = 0) {
   const long long total = P * C;
   const int cg = C / G;
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -241,7 +253,10 @@ __global__ void groupnorm_apply_kernel(const __nv_bfloat16* x, long long P, int 
     v = v / (1.f + expf(-v));  // SiLU
     if (resid != nullptr) v += resid[i];
     if (y_f32 != nullptr) y_f32[i] = v;
-    if (y_bf16 != nullptr) y_bf16[i] = __float2bfloat16_rn(v);
+    if (y_bf16 != nullptr) {
+      if (pad_H == 0) y_bf16[i] = __float2bfloat16_rn(v);
+      else y_bf16[padded_row(i / C, pad_H, pad_W) * ld_bf16 + c] = __float2bfloat16_rn(v);
+    }
   }
 }
 
@@ -379,8 +394,21 @@ extern "C" int fx_nchw_to_nhwc(const void* src, void* dst, int64_t ldd, int c0, 
   FX_CHECK_ARG(src && dst && C > 0 && P > 0 && c0 >= 0 && ldd >= c0 + C, "fx_nchw_to_nhwc: bad arguments");
   dim3 grid(static_cast<unsigned>((P + 31) / 32), (C + 31) / 32);
   nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), ldd, c0, C, P);
+      reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), ldd, c0, C, P, 0, 0);
   FX_CHECK_LAUNCH("fx_nchw_to_nhwc");
+  return FX_OK;
+}
+
+extern "C" int fx_nchw_to_nhwc_padded(const void* src, void* dst, int64_t ldd, int c0, int C, int F, int H, int W,
+                                      void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(src && dst && C > 0 && F > 0 && H > 0 && W > 0 && c0 >= 0 && ldd >= c0 + C,
+               "fx_nchw_to_nhwc_padded: bad arguments");
+  const long long P = static_cast<long long>(F) * H * W;
+  dim3 grid(static_cast<unsigned>((P + 31) / 32), (C + 31) / 32);
+  nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), ldd, c0, C, P, H, W);
+  FX_CHECK_LAUNCH("fx_nchw_to_nhwc_padded");
   return FX_OK;
 }
 
@@ -424,9 +452,12 @@ extern "C" int fx_groupnorm_partials(const void* x, int F, int64_t pp, int C, in
 
 extern "C" int fx_groupnorm_silu_partials(const void* x, int64_t P, int C, int G, float eps, const void* gamma,
                                           const void* beta, const double* partials, int Ft, int64_t pp,
-                                          const float* resid, float* y_f32, void* y_bf16, float* stats, void* stream) {
+                                          const float* resid, float* y_f32, void* y_bf16, int pad_H, int pad_W,
+                                          int64_t ld_bf16, float* stats, void* stream) {
   using namespace fx;
   FX_CHECK_ARG(x && gamma && beta && partials && stats && (y_f32 || y_bf16), "fx_groupnorm_silu_partials: null pointer");
+  FX_CHECK_ARG(pad_H == 0 || (pad_H > 0 && pad_W > 0 && ld_bf16 >= C && P % (static_cast<int64_t>(pad_H) * pad_W) == 0),
+               "fx_groupnorm_silu_partials: bad padded-output arguments");
   FX_CHECK_ARG(P > 0 && C > 0 && G > 0 && C % G == 0 && Ft > 0 && pp > 0,
                "fx_groupnorm_silu_partials: bad shape P=%lld C=%d G=%d Ft=%d pp=%lld", (long long)P, C, G, Ft,
                (long long)pp);
@@ -436,7 +467,8 @@ extern "C" int fx_groupnorm_silu_partials(const void* x, int64_t P, int C, int G
   FX_CHECK_LAUNCH("fx_groupnorm_silu_partials(finalize)");
   groupnorm_apply_kernel<<<ew_grid2(P * C), 256, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), P, C, G, reinterpret_cast<const __nv_bfloat16*>(gamma),
-      reinterpret_cast<const __nv_bfloat16*>(beta), stats, resid, y_f32, reinterpret_cast<__nv_bfloat16*>(y_bf16));
+      reinterpret_cast<const __nv_bfloat16*>(beta), stats, resid, y_f32, reinterpret_cast<__nv_bfloat16*>(y_bf16), pad_H,
+      pad_W, ld_bf16);
   FX_CHECK_LAUNCH("fx_groupnorm_silu_partials(apply)");
   return FX_OK;
 }

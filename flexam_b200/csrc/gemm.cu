@@ -49,6 +49,12 @@ struct GemmParams {
   int num_m_tiles, num_n_tiles, group_m;
   int n_span;  // n-tiles per outer slab of the rasterisation (num_n_tiles = one slab)
   int a_hint, b_hint;  // L2 eviction priority of the A / B panel loads (CTA-pair kernel): 0 normal, 1 first, 2 last
+  // Implicit-GEMM convolution (fx_conv_gemm_bf16): A is a zero-padded channel-last activation [Tin * Hp * Wp, Cin]; the
+  // K range is cut into conv_taps segments of conv_kb_per_tap k-blocks, segment `tap` reads A rows shifted by
+  // conv_off[tap] (the tap's (dt, dy, dx) as a row distance on the padded grid; rows outside the buffer are TMA zero fill);
+  // output row m is a position of the padded grid: interior positions are written to the dense [T*H*W, N] result.
+  int conv_taps, conv_kb_per_tap, conv_Hp, conv_Wp, conv_H, conv_W;
+  int conv_off[27];
   int b_k_wrap;        // > 0: the weight's K extent; A is [M, planes * b_k_wrap] (bf16 planes of an fp32 matrix side by
                        // side) and the weight column of k-block kb is (kb * 64) % b_k_wrap — one accumulation over all planes
 };
@@ -88,9 +94,22 @@ __device__ __forceinline__ void add_bias8(const GemmParams& p, int col, const ui
   }
 }
 
+// Convolution mode: padded-grid row -> dense output row, or -1 for a halo position.
+__device__ __forceinline__ long long conv_dense_row(const GemmParams& p, int row) {
+  if (p.conv_taps == 0) return row;
+  const int plane = p.conv_Hp * p.conv_Wp;
+  const int t = row / plane;
+  const int r = row - t * plane;
+  const int yp = r / p.conv_Wp;
+  const int xp = r - yp * p.conv_Wp;
+  const int y = yp - (p.conv_Hp - p.conv_H) / 2, x = xp - (p.conv_Wp - p.conv_W) / 2;
+  if (y < 0 || y >= p.conv_H || x < 0 || x >= p.conv_W) return -1;
+  return (static_cast<long long>(t) * p.conv_H + y) * p.conv_W + x;
+}
+
 // Direct-store epilogues: one 32-column slab of one output row, v[j] = accumulator bits for column col0 + j.
 template <int EPI>
-__device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int col0, uint32_t (&v)[32]) {
+__device__ __forceinline__ void epilogue_row32(const GemmParams& p, long long row, int col0, uint32_t (&v)[32]) {
   // 8-column groups; N % 8 == 0 so a group is either fully valid or fully out of range.
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -108,14 +127,14 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int
       o.y = pack_bf16x2(y[2], y[3]);
       o.z = pack_bf16x2(y[4], y[5]);
       o.w = pack_bf16x2(y[6], y[7]);
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col;
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col;
       *reinterpret_cast<uint4*>(dst) = o;
     } else if constexpr (EPI == FX_EPI_F32_EXACT) {  // verification mode: no rounding after the fp32 accumulator
-      float* dst = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
+      float* dst = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
       *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
       *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
     } else {  // FX_EPI_F32
-      float* dst = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
+      float* dst = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
       float4 o0 = make_float4(bf16_round(y[0]), bf16_round(y[1]), bf16_round(y[2]), bf16_round(y[3]));
       float4 o1 = make_float4(bf16_round(y[4]), bf16_round(y[5]), bf16_round(y[6]), bf16_round(y[7]));
       *reinterpret_cast<float4*>(dst) = o0;
@@ -223,7 +242,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int kcol_b = p.b_k_wrap > 0 ? (kb * kBK) % p.b_k_wrap : kb * kBK;
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m_tile * kBM);
+          int a_col = kb * kBK, a_row = m_tile * kBM;
+          if (p.conv_taps > 0) {
+            const int tap = kb / p.conv_kb_per_tap;
+            a_col = (kb - tap * p.conv_kb_per_tap) * kBK;
+            a_row += p.conv_off[tap];
+          }
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], a_col, a_row);
           tma_load_2d(sb, &tmap_b, &full_bar[stage], kcol_b, n_tile * BN);
         }
         if (++stage == kStages) {
@@ -288,6 +313,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if constexpr (EPI == FX_EPI_RESID_F32) {
         if (p.row_idx != nullptr && row < p.M) u = p.row_idx[row];
       }
+      const long long orow = row < p.M ? conv_dense_row(p, row) : -1;   // where this thread's row goes (-1: nowhere)
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
@@ -309,7 +335,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ++slab_sel;
           }
         } else {
-          if (row < p.M) epilogue_row32<EPI>(p, row, col0, v);
+          if (orow >= 0) epilogue_row32<EPI>(p, orow, col0, v);
         }
       }
       tc_fence_before();
@@ -421,7 +447,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
           const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
           const int kcol_b = p.b_k_wrap > 0 ? (kb * kBK) % p.b_k_wrap : kb * kBK;
-          tma_load_2d_2sm_hint(sa, &tmap_a, leader_full, kb * kBK, a_row, pol_a);
+          int a_col = kb * kBK, a_row_k = a_row;
+          if (p.conv_taps > 0) {
+            const int tap = kb / p.conv_kb_per_tap;
+            a_col = (kb - tap * p.conv_kb_per_tap) * kBK;
+            a_row_k += p.conv_off[tap];
+          }
+          tma_load_2d_2sm_hint(sa, &tmap_a, leader_full, a_col, a_row_k, pol_a);
           tma_load_2d_2sm_hint(sb, &tmap_b, leader_full, kcol_b, b_row, pol_b);
         }
         if (++stage == kStages) {
@@ -488,6 +520,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if constexpr (EPI == FX_EPI_RESID_F32) {
         if (p.row_idx != nullptr && row < p.M) u = p.row_idx[row];
       }
+      const long long orow = row < p.M ? conv_dense_row(p, row) : -1;   // where this thread's row goes (-1: nowhere)
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
@@ -507,7 +540,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
           ++slab_sel;
         } else {
-          if (row < p.M) epilogue_row32<EPI>(p, row, col0, v);
+          if (orow >= 0) epilogue_row32<EPI>(p, orow, col0, v);
         }
       }
       tc_fence_before();
@@ -614,11 +647,17 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
 }  // namespace fx
 
 namespace fx {
+struct ConvSpec {   // implicit-GEMM convolution over a zero-padded channel-last activation (see fx_conv_gemm_bf16)
+  int taps, cin, Hp, Wp, H, W;
+  long long a_rows;   // rows of the padded activation buffer (Tin * Hp * Wp)
+  int off[27];
+};
 // K = reduction length seen by the kernel (A's width). kw = the weight's K extent: == K normally; K = planes * kw for
 // the plane-concatenated form used by fx_linear_f32_tc (GemmParams::b_k_wrap).
 static int gemm_impl(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* out,
                      int64_t ldo, int M, int N, int K, int kw, int epilogue, const float* gate_mod,
-                     const float* gate_e, int64_t gate_e_stride, const int32_t* row_idx, void* stream);
+                     const float* gate_e, int64_t gate_e_stride, const int32_t* row_idx, void* stream,
+                     const ConvSpec* conv = nullptr);
 }
 
 extern "C" int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* out,
@@ -630,12 +669,13 @@ extern "C" int fx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t l
 
 int fx::gemm_impl(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* out,
                          int64_t ldo, int M, int N, int K, int kw, int epilogue, const float* gate_mod,
-                         const float* gate_e, int64_t gate_e_stride, const int32_t* row_idx, void* stream) {
+                         const float* gate_e, int64_t gate_e_stride, const int32_t* row_idx, void* stream,
+                         const ConvSpec* conv) {
   using namespace fx;
   FX_CHECK_ARG(a && w && out, "fx_gemm_bf16: null pointer");
   FX_CHECK_ARG(M > 0 && N > 0 && K > 0, "fx_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   FX_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "fx_gemm_bf16: K (%d) and N (%d) must be multiples of 8", K, N);
-  FX_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= kw, "fx_gemm_bf16: bad lda/ldw");
+  FX_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && lda >= (conv ? conv->cin : K) && ldw >= kw, "fx_gemm_bf16: bad lda/ldw");
   FX_CHECK_ARG(kw == K || (kw > 0 && kw % kBK == 0 && K % kw == 0), "fx_gemm_bf16: bad plane wrap %d for K=%d", kw, K);
   FX_CHECK_ARG(ldo >= N && ldo % 8 == 0, "fx_gemm_bf16: bad ldo");
   FX_CHECK_ARG((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) |
@@ -665,10 +705,17 @@ int fx::gemm_impl(const void* a, int64_t lda, const void* w, int64_t ldw, const 
   p.group_m = 16;
   p.n_span = p.num_n_tiles;
   p.b_k_wrap = kw == K ? 0 : kw;
+  if (conv != nullptr) {
+    p.conv_taps = conv->taps;
+    p.conv_kb_per_tap = conv->cin / kBK;
+    p.conv_Hp = conv->Hp; p.conv_Wp = conv->Wp; p.conv_H = conv->H; p.conv_W = conv->W;
+    for (int i = 0; i < conv->taps; ++i) p.conv_off[i] = conv->off[i];
+  }
 
   CUtensorMap ta, tb, tout;
   {
-    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    const uint64_t dims[2] = {static_cast<uint64_t>(conv ? conv->cin : K),
+                              static_cast<uint64_t>(conv ? conv->a_rows : M)};
     const uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
     const uint32_t box[2] = {kBK, kBM};
     if (!make_tmap_bf16(&ta, a, 2, dims, strides, box)) return FX_ERR_CUDA;
@@ -768,4 +815,42 @@ extern "C" int fx_linear_f32_tc(const float* in, int64_t ldi, const void* w, int
   FX_CHECK_LAUNCH("fx_linear_f32_tc(split)");
   return gemm_impl(planes_ws, static_cast<int64_t>(planes) * K, w, ldw, bias, out, ldo, M, N, planes * K, K,
                    FX_EPI_F32_EXACT, nullptr, nullptr, 0, nullptr, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Convolution as an implicit GEMM on the same tcgen05 kernels — no im2col buffer. The activation is channel-last and
+// zero-padded: bf16 [Tin, Hp, Wp, Cin] with Hp = H + 2, Wp = W + 2 for a 3x3 spatial kernel (Hp = H, Wp = W for 1x1) and
+// Tin = T + kt - 1 leading frames of causal history for a kt-tap time kernel. Output position m runs over the padded grid
+// [T, Hp, Wp]; tap (dt, dy, dx) reads the SAME matrix shifted by dt*Hp*Wp + (dy-1)*Wp + (dx-1) rows, so the K loop
+// walks taps x Cin with one TMA coordinate change per tap; halo positions are computed and dropped (1.5-9 % extra work),
+// interior ones are written densely as [T*H*W, Cout]. Weight: bf16 [Cout, taps*Cin], K order (dt, dy, dx, cin).
+// Used by the control fuser's 3x3 convolutions (cnn_conv1..4, wan_transformer3d_FlexAM.py:680-711).
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int fx_conv_gemm_bf16(const void* act, const void* w, const void* bias, void* out, int64_t ldo, int T,
+                                 int H, int W, int Cin, int Cout, int kt, int ks, int epilogue, void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(act && w && out, "fx_conv_gemm_bf16: null pointer");
+  FX_CHECK_ARG(T > 0 && H > 0 && W > 0 && Cin > 0 && Cin % kBK == 0 && Cout > 0 && Cout % 8 == 0,
+               "fx_conv_gemm_bf16: bad shape T=%d H=%d W=%d Cin=%d (multiple of 64) Cout=%d (multiple of 8)", T, H, W, Cin,
+               Cout);
+  FX_CHECK_ARG((kt == 1 || kt == 3) && (ks == 1 || ks == 3), "fx_conv_gemm_bf16: kernel %dx%dx%d unsupported", kt, ks, ks);
+  FX_CHECK_ARG(epilogue == FX_EPI_BF16 || epilogue == FX_EPI_GELU_BF16 || epilogue == FX_EPI_F32 ||
+                   epilogue == FX_EPI_F32_EXACT,
+               "fx_conv_gemm_bf16: epilogue %d unsupported", epilogue);
+  ConvSpec c{};
+  c.taps = kt * ks * ks;
+  c.cin = Cin;
+  c.H = H; c.W = W;
+  c.Hp = ks == 3 ? H + 2 : H;
+  c.Wp = ks == 3 ? W + 2 : W;
+  const long long plane = static_cast<long long>(c.Hp) * c.Wp;
+  c.a_rows = (T + kt - 1) * plane;
+  FX_CHECK_ARG(c.a_rows < (1LL << 31) && static_cast<long long>(T) * plane < (1LL << 31), "fx_conv_gemm_bf16: too many rows");
+  int i = 0;
+  for (int dt = 0; dt < kt; ++dt)
+    for (int dy = 0; dy < ks; ++dy)
+      for (int dx = 0; dx < ks; ++dx)
+        c.off[i++] = static_cast<int>(dt * plane + (ks == 3 ? (dy - 1) * c.Wp + (dx - 1) : 0));
+  return gemm_impl(act, Cin, w, static_cast<int64_t>(c.taps) * Cin, bias, out, ldo, static_cast<int>(T * plane), Cout,
+                   c.taps * Cin, c.taps * Cin, epilogue, nullptr, nullptr, 0, nullptr, stream, &c);
 }

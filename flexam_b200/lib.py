@@ -41,7 +41,9 @@ SIGNATURES = {
     "fx_im2col3x3": [_vp, _vp, _i, _i, _i, _i, _vp],
     "fx_groupnorm_silu": [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "fx_groupnorm_partials": [_vp, _i, _i64, _i, _i, _vp, _vp],
-    "fx_groupnorm_silu_partials": [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp],
+    "fx_groupnorm_silu_partials": [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _i, _i64, _vp, _vp],
+    "fx_conv_gemm_bf16": [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "fx_nchw_to_nhwc_padded": [_vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
     "fx_cfg_euler_step": [_vp, _vp, _f, _f, _vp, _vp, _vp, _i64, _vp],
     "fx_swap01_bf16": [_vp, _i64, _vp, _i, _i, _i, _vp],
     "fx_add_f32": [_vp, _vp, _i64, _vp],

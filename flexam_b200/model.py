@@ -169,6 +169,15 @@ class NativeEngine:
         self.w_ref = P["ref_conv.weight"].flatten(1).contiguous()
         self.w_cnn = [P[f"cnn_conv{j}.0.weight"].flatten(1).contiguous() for j in range(1, 5)]  # [Co, Ci*9] (c,kh,kw)
         self.w_cnn5 = P["cnn_conv5.weight"].flatten(1).contiguous()
+        # the same 3x3 weights for the implicit-GEMM convolution: K order (kh, kw, c) with c zero-padded to a multiple of 64
+        self.w_cnn_taps = []
+        for j in range(1, 5):
+            w = P[f"cnn_conv{j}.0.weight"][:, :, 0]                       # [Co, Ci, 3, 3]
+            co, ci = w.shape[:2]
+            cp = -(-ci // 64) * 64
+            wt = torch.zeros((co, 3, 3, cp), dtype=bf16, device=dev)
+            wt[..., :ci] = w.permute(0, 2, 3, 1)
+            self.w_cnn_taps.append(wt.view(co, 9 * cp).contiguous())
         self.head_mod = P["head.modulation"][0].to(f32).contiguous()           # [2, D]
         self.head_dmod = P["head.modulation_density"][0, 0].to(f32).contiguous()
         self._versions = self._pvers()
@@ -265,38 +274,41 @@ class NativeEngine:
         out_pad = self._buf("cnn_out_pad", (Fc * pp, self.w_cnn5.shape[0]), bf16)
         if nsp > 1 and Fl < Fc:
             out_pad.zero_()
+        # Activations of the 3x3 stages live in the zero-padded channel-last grid the implicit-GEMM convolution reads
+        # ([Fl, H+2, W+2, C rounded up to 64]); only interior positions / real channels are ever written, so the halo and
+        # the padding channels keep the zeros they were allocated with.
         act = None
         if Fl > 0:
-            act = self._buf("cnn_in", (npix, C0 + C1), bf16)
+            act = self._buf_zero("cnn_in_pad", (Fl * (H + 2) * (W + 2), -(-(C0 + C1) // 64) * 64), bf16)
             src0 = y_ctrl0 if nsp == 1 else y_ctrl0[:, f0:f0 + Fl].contiguous()
             src1 = add if nsp == 1 else add[:, f0:f0 + Fl].contiguous()
-            ops.nchw_to_nhwc(src0.reshape(C0, npix), act, 0)
-            ops.nchw_to_nhwc(src1.reshape(C1, npix), act, C0)
+            ops.nchw_to_nhwc_padded(src0.reshape(C0, npix), act, 0, Fl, H, W)
+            ops.nchw_to_nhwc_padded(src1.reshape(C1, npix), act, C0, Fl, H, W)
             self.launches += 2
         stats = self._buf("cnn_stats", (64,), f32)
         resid = None
         for j, (groups, keep) in enumerate([(24, True), (24, False), (12, True), (12, False)]):
-            wj = self.w_cnn[j]
+            wj = self.w_cnn_taps[j]
             cout = wj.shape[0]
             part = self._buf(f"cnn_part{j}", (Fc, groups, 2), torch.float64)
             if Fl < Fc:
                 part.zero_()
             if Fl > 0:
-                cin = act.shape[1]
-                rows = self._buf("cnn_rows", (npix, 9 * cin), bf16)
-                ops.im2col3x3(act, Fl, H, W, rows)
                 conv = self._buf(f"cnn_conv{j}", (npix, cout), bf16)
-                self._gemm(rows, wj, P[f"cnn_conv{j + 1}.0.bias"], conv, FX_EPI_BF16)
+                self._timed("gemm", 2.0 * npix * cout * wj.shape[1], ops.conv_gemm, act, wj,
+                            P[f"cnn_conv{j + 1}.0.bias"], conv, Fl, H, W, 1, 3, FX_EPI_BF16)
                 ops.groupnorm_partials(conv, Fl, groups, part[:Fl])
-                self.launches += 2
+                self.launches += 1
             allp = part if nsp == 1 else par.gather_tokens(part)[:F].contiguous()     # [F, groups, 2], frame order
             if Fl > 0:
-                nxt = self._buf(f"cnn_act{j}", (npix, cout), bf16)
+                last = j == 3        # x4 feeds the 1x1 convolution: dense rows
+                nxt = (self._buf(f"cnn_act{j}", (npix, cout), bf16) if last else
+                       self._buf_zero(f"cnn_act{j}_pad", (Fl * (H + 2) * (W + 2), -(-cout // 64) * 64), bf16))
                 keep_f32 = self._buf(f"cnn_f32_{j}", (npix, cout), f32) if keep else None
                 # x2 = S(GN(conv2(x1))) + x1 and x4 = S(GN(conv4(x3))) + x3 take the previous stage's fp32 output
                 ops.groupnorm_silu_partials(conv, groups, 1e-5, P[f"cnn_conv{j + 1}.1.weight"],
                                             P[f"cnn_conv{j + 1}.1.bias"], allp, pp, None if keep else resid, keep_f32,
-                                            nxt, stats)
+                                            nxt, stats, pad_hw=None if last else (H, W))
                 self.launches += 2
                 resid = keep_f32
                 act = nxt
@@ -305,6 +317,15 @@ class NativeEngine:
         if nsp == 1:
             return out_pad.clone()
         return par.gather_tokens(out_pad)[:F * pp].contiguous()
+
+    def _buf_zero(self, name: str, shape: Sequence[int], dtype) -> torch.Tensor:
+        """A workspace that is zero when first handed out (halo / padding of the convolution grids)."""
+        key = (name, tuple(shape), dtype)
+        fresh = key not in self._ws
+        t = self._buf(name, shape, dtype)
+        if fresh:
+            t.zero_()
+        return t
 
     def _context(self, context: List[torch.Tensor]) -> torch.Tensor:
         """zero-pad to text_len, text_embedding MLP (:958-964) -> [B*text_len, D] bf16."""

@@ -345,18 +345,52 @@ def groupnorm_partials(x: torch.Tensor, frames: int, groups: int, partials: torc
     return partials
 
 
+def conv_gemm(act: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, T: int, H: int,
+              W: int, kt: int, ks: int, epilogue: int = FX_EPI_BF16) -> torch.Tensor:
+    """Implicit-GEMM convolution (see fx_conv_gemm_bf16). act: bf16 zero-padded channel-last [(T+kt-1)*Hp*Wp, Cin]
+    contiguous; w: bf16 [Cout, kt*ks*ks*Cin]; out: dense [T*H*W, Cout] view (row stride free)."""
+    _req(act, bf16, "conv_gemm.act"), _req(w, bf16, "conv_gemm.w")
+    Cin, Cout = act.shape[1], w.shape[0]
+    Hp, Wp = (H + 2, W + 2) if ks == 3 else (H, W)
+    if not act.is_contiguous() or act.shape[0] != (T + kt - 1) * Hp * Wp or w.shape[1] != kt * ks * ks * Cin \
+            or not w.is_contiguous() or tuple(out.shape) != (T * H * W, Cout):
+        raise _l.FlexamNativeError(f"conv_gemm: shape mismatch act{tuple(act.shape)} w{tuple(w.shape)} out{tuple(out.shape)}")
+    _req(out, bf16 if epilogue in (FX_EPI_BF16, FX_EPI_GELU_BF16) else f32, "conv_gemm.out")
+    if bias is not None:
+        _req(bias, bf16, "conv_gemm.bias")
+    st = _l.load().fx_conv_gemm_bf16(_p(act), _p(w), _p(bias), _p(out), out.stride(0), T, H, W, Cin, Cout, kt, ks,
+                                     epilogue, _stream())
+    _l.check(st, "fx_conv_gemm_bf16")
+    return out
+
+
+def nchw_to_nhwc_padded(src: torch.Tensor, dst: torch.Tensor, c0: int, F: int, H: int, W: int) -> torch.Tensor:
+    """src: bf16 [C, F*H*W] contiguous; dst: bf16 [F*(H+2)*(W+2), ld] zero-padded channel-last grid, columns [c0, c0+C)."""
+    _req(src, bf16, "nchw_to_nhwc_padded.src"), _req(dst, bf16, "nchw_to_nhwc_padded.dst")
+    Cc, P = src.shape
+    if P != F * H * W or dst.shape[0] != F * (H + 2) * (W + 2) or not src.is_contiguous():
+        raise _l.FlexamNativeError("nchw_to_nhwc_padded: shape mismatch")
+    _l.check(_l.load().fx_nchw_to_nhwc_padded(_p(src), _p(dst), dst.stride(0), c0, Cc, F, H, W, _stream()),
+             "fx_nchw_to_nhwc_padded")
+    return dst
+
+
 def groupnorm_silu_partials(x: torch.Tensor, groups: int, eps: float, gamma: torch.Tensor, beta: torch.Tensor,
                             partials: torch.Tensor, pix_per_frame: int, resid: Optional[torch.Tensor],
-                            y_f32: Optional[torch.Tensor], y_bf16: Optional[torch.Tensor], stats: torch.Tensor) -> None:
+                            y_f32: Optional[torch.Tensor], y_bf16: Optional[torch.Tensor], stats: torch.Tensor,
+                            pad_hw: Optional[Sequence[int]] = None) -> None:
     """GroupNorm + SiLU (+ resid) of the local pixels x [P, C] with the statistics of ALL frames: partials f64
-    [Ft, groups, 2] in frame order (see fx_groupnorm_silu_partials)."""
+    [Ft, groups, 2] in frame order (see fx_groupnorm_silu_partials). pad_hw=(H, W): y_bf16 is the zero-padded grid
+    [frames*(H+2)*(W+2), ld] the next implicit-GEMM convolution reads (interior positions are written)."""
     _req(x, bf16, "groupnorm_silu_partials.x"), _req(partials, torch.float64, "groupnorm_silu_partials.partials")
     if partials.dim() != 3 or partials.shape[1] != groups or not partials.is_contiguous():
         raise _l.FlexamNativeError("groupnorm_silu_partials: partials must be contiguous [Ft, groups, 2]")
     P, Cc = x.shape
+    ph, pw = (int(pad_hw[0]), int(pad_hw[1])) if pad_hw is not None else (0, 0)
+    ld_b = y_bf16.stride(0) if (y_bf16 is not None and pad_hw is not None) else 0
     st = _l.load().fx_groupnorm_silu_partials(_p(x), P, Cc, groups, eps, _p(gamma), _p(beta), _p(partials),
-                                              partials.shape[0], pix_per_frame, _p(resid), _p(y_f32), _p(y_bf16),
-                                              _p(stats), _stream())
+                                              partials.shape[0], pix_per_frame, _p(resid), _p(y_f32), _p(y_bf16), ph, pw,
+                                              ld_b, _p(stats), _stream())
     _l.check(st, "fx_groupnorm_silu_partials")
 
 

@@ -170,7 +170,19 @@ int fx_groupnorm_silu(const void* x, int64_t P, int C, int G, float eps, const v
 int fx_groupnorm_partials(const void* x, int F, int64_t pp, int C, int G, double* partials, void* stream);
 int fx_groupnorm_silu_partials(const void* x, int64_t P, int C, int G, float eps, const void* gamma, const void* beta,
                                const double* partials, int Ft, int64_t pp, const float* resid, float* y_f32,
-                               void* y_bf16, float* stats, void* stream);
+                               void* y_bf16, int pad_H, int pad_W, int64_t ld_bf16, float* stats, void* stream);
+/* Convolution as an implicit GEMM on the tcgen05 kernels, no im2col buffer (the control fuser's cnn_conv1..4
+ * :680-711,874-880; replaces cuDNN Conv3d with kernel (1,3,3)). act: bf16 channel-last, ZERO-PADDED
+ * [T + kt - 1, Hp, Wp, Cin] with Hp = H + 2, Wp = W + 2 when ks == 3 (H, W when ks == 1) and kt - 1 leading frames of
+ * causal history; Cin % 64 == 0 (pad channels with zeros). w: bf16 [Cout, kt*ks*ks*Cin], K order (dt, dy, dx, cin).
+ * out: DENSE [T*H*W, ldo] with the fx_gemm_bf16 epilogues FX_EPI_BF16 / _GELU_BF16 / _F32 / _F32_EXACT (+ bias).
+ * Tap (dt, dy, dx) reads the activation matrix shifted by dt*Hp*Wp + (dy-1)*Wp + (dx-1) rows: one TMA coordinate change
+ * per tap; positions of the padded grid that are halo are computed and dropped.
+ * fx_nchw_to_nhwc_padded: fx_nchw_to_nhwc into that padded layout (interior positions only: the halo stays as the caller
+ * zeroed it). fx_groupnorm_silu_partials with pad_H > 0 writes y_bf16 into the padded layout [.., pad_H+2, pad_W+2, ld_bf16]. */
+int fx_conv_gemm_bf16(const void* act, const void* w, const void* bias, void* out, int64_t ldo, int T, int H, int W,
+                      int Cin, int Cout, int kt, int ks, int epilogue, void* stream);
+int fx_nchw_to_nhwc_padded(const void* src, void* dst, int64_t ldd, int c0, int C, int F, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Sampler glue (pipeline_wan2_2_fun_control_FlexAM.py:926-934): CFG combine + Euler flow step + first-frame

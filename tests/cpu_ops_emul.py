@@ -180,7 +180,35 @@ def groupnorm_partials(x, frames, groups, partials):
     return partials
 
 
-def groupnorm_silu_partials(x, groups, eps, gamma, beta, partials, pix_per_frame, resid, y_f32, y_bf16, stats):
+def _padded_rows(P, H, W):
+    p = torch.arange(P)
+    f, r = p // (H * W), p % (H * W)
+    return (f * (H + 2) + r // W + 1) * (W + 2) + r % W + 1
+
+
+def conv_gemm(act, w, bias, out, T, H, W, kt, ks, epilogue=0):
+    Cin, Cout = act.shape[1], w.shape[0]
+    Hp, Wp = (H + 2, W + 2) if ks == 3 else (H, W)
+    x = act.double().view(T + kt - 1, Hp, Wp, Cin).permute(3, 0, 1, 2)[None]
+    wt = w.double().view(Cout, kt, ks, ks, Cin).permute(0, 4, 1, 2, 3)
+    y = F.conv3d(x, wt)[0].permute(1, 2, 3, 0).reshape(T * H * W, Cout)
+    if bias is not None:
+        y = y + bias.double()
+    if epilogue == 4:
+        return out.copy_(y.float())
+    y = _rb(y.float())
+    if epilogue == 1:
+        y = F.gelu(y, approximate="tanh")
+    return out.copy_(y.to(out.dtype))
+
+
+def nchw_to_nhwc_padded(src, dst, c0, Fr, H, W):
+    dst[_padded_rows(src.shape[1], H, W), c0:c0 + src.shape[0]] = src.t()
+    return dst
+
+
+def groupnorm_silu_partials(x, groups, eps, gamma, beta, partials, pix_per_frame, resid, y_f32, y_bf16, stats,
+                            pad_hw=None):
     P, C = x.shape
     n = partials.shape[0] * pix_per_frame * (C // groups)
     mean = partials[..., 0].sum(0) / n
@@ -195,7 +223,10 @@ def groupnorm_silu_partials(x, groups, eps, gamma, beta, partials, pix_per_frame
     if y_f32 is not None:
         y_f32.copy_(y)
     if y_bf16 is not None:
-        y_bf16.copy_(y.to(bf16))
+        if pad_hw is None:
+            y_bf16.copy_(y.to(bf16))
+        else:
+            y_bf16[_padded_rows(P, pad_hw[0], pad_hw[1]), :C] = y.to(bf16)
 
 
 def swap01(src, out):
@@ -394,7 +425,7 @@ def gated_gelu(fc1, gate, out):
     return out.copy_((fc1.float() * _rb(_rb(0.5 * g) * _rb(1.0 + th))).to(bf16))
 
 
-NAMES = ("embedding", "t5_layernorm", "t5_attention", "add_bf16_", "gated_gelu", "groupnorm_partials", "groupnorm_silu_partials", "linear_f32_tc", "dedup_f32", "fingerprint_table", "fingerprint", "gemm", "ln_modulate", "modulation_tables", "ln_scale_shift", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
+NAMES = ("conv_gemm", "nchw_to_nhwc_padded", "embedding", "t5_layernorm", "t5_attention", "add_bf16_", "gated_gelu", "groupnorm_partials", "groupnorm_silu_partials", "linear_f32_tc", "dedup_f32", "fingerprint_table", "fingerprint", "gemm", "ln_modulate", "modulation_tables", "ln_scale_shift", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
                  "linear_f32", "nchw_to_nhwc", "im2col3x3", "groupnorm_silu", "swap01", "cfg_euler_step", "add_", "sub", "split3", "join3",
                  "ln_f32", "rmsnorm_rope_f32", "gelu_f32_", "gated_residual_f32_", "attention_f32",
                  "groupnorm_silu_f32")

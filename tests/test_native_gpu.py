@@ -135,6 +135,38 @@ def test_fmha_rows_are_convex_combinations_of_v(dev):
     assert (out.float() - 0.75).abs().max().item() < 1e-2
 
 
+@pytest.mark.parametrize("T,H,W,Cin,Cout,kt,ks", [(3, 8, 12, 64, 192, 1, 3), (2, 16, 28, 320, 192, 1, 3),
+                                                  (5, 32, 56, 192, 96, 1, 3), (4, 10, 14, 128, 256, 3, 3),
+                                                  (6, 8, 8, 64, 16, 3, 1), (2, 64, 112, 128, 96, 1, 3)])
+def test_conv_as_implicit_gemm(dev, T, H, W, Cin, Cout, kt, ks):
+    """fx_conv_gemm_bf16 (tap-shifted TMA reads of a zero-padded channel-last activation, no im2col) against
+    torch's conv3d: per-frame 3x3 (the control fuser, :680-711), causal 3x3x3 and 3x1x1 time kernels."""
+    from flexam_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(T * H + Cin + Cout + kt)
+    Hp, Wp = (H + 2, W + 2) if ks == 3 else (H, W)
+    x = torch.randn(T + kt - 1, H, W, Cin, device=dev, generator=g).bfloat16()          # kt-1 leading history frames
+    act = torch.zeros(T + kt - 1, Hp, Wp, Cin, device=dev, dtype=torch.bfloat16)
+    if ks == 3:
+        act[:, 1:-1, 1:-1] = x
+    else:
+        act.copy_(x)
+    w = (torch.randn(Cout, kt, ks, ks, Cin, device=dev, generator=g) * (kt * ks * ks * Cin) ** -0.5).bfloat16()
+    b = torch.randn(Cout, device=dev, generator=g).bfloat16()
+    out = torch.full((T * H * W, Cout), float("nan"), device=dev, dtype=torch.bfloat16)
+    ops.conv_gemm(act.view(-1, Cin), w.view(Cout, -1), b, out, T, H, W, kt, ks)
+    xin = x.float().permute(3, 0, 1, 2)[None]                                             # [1, Cin, T+kt-1, H, W]
+    want = torch.nn.functional.conv3d(xin, w.float().permute(0, 4, 1, 2, 3), b.float(), padding=(0, ks // 2, ks // 2))
+    want = want[0].permute(1, 2, 3, 0).reshape(T * H * W, Cout)
+    assert torch.isfinite(out.float()).all() and _rel(out, want) < 3e-3
+    # the padded-layout writers put data where the convolution looks for it
+    if ks == 3 and kt == 1:
+        src = torch.randn(Cin, T * H * W, device=dev, generator=g).bfloat16()
+        grid = torch.zeros(T * Hp * Wp, Cin, device=dev, dtype=torch.bfloat16)
+        ops.nchw_to_nhwc_padded(src, grid, 0, T, H, W)
+        assert torch.equal(grid.view(T, Hp, Wp, Cin)[:, 1:-1, 1:-1].reshape(-1, Cin), src.t())
+        assert grid.view(T, Hp, Wp, Cin)[:, 0].abs().max().item() == 0
+
+
 def test_ln_and_rmsnorm_rope(dev):
     from flexam_b200 import ops
     from oracle import flexam_oracle as O
