@@ -601,6 +601,83 @@ def run_t5(args):
                    "library_rel_l2_vs_oracle": rel(lib_out, want), "gate": 1e-2, "checksum_sha256_16": output_checksum(out)}}))
 
 
+def run_vae(args):
+    """SURVEY §8f N2 (decode half): the Wan2.2 VAE decoder at its real width on the 25 x 32 x 56 latents of the metric's
+    clip -> 97 frames 512 x 896, native vs the module's bf16 execution with stock torch ops (cuDNN convolutions, SDPA)
+    on the same GPU, parity against the fp32 oracle. Runs once per video; not the bench line."""
+    import torch
+    from flexam_b200 import lib
+    from flexam_b200.vae import AutoencoderKLWan3_8
+    from oracle import vae_oracle as V
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    lib.check(lib.load().fx_check_device(dev.index), "fx_check_device")
+    cfg = V.VAE_CONFIGS["real"]
+    scale = V.latent_scale(cfg)
+    m = AutoencoderKLWan3_8(latent_channels=cfg["z_dim"], dec_dim=cfg["dec_dim"], dim_mult=cfg["dim_mult"],
+                            temperal_downsample=cfg["temperal_downsample"], latents_mean=scale[0],
+                            latents_std=1.0 / scale[1], device=dev)
+    sd = V.state_dict_torch(cfg, dev, torch.bfloat16)
+    m.load_state_dict({"model." + k: v for k, v in sd.items()}, strict=True)
+    T, H, W = GRID if args.vae_frames <= 0 else (args.vae_frames, GRID[1], GRID[2])
+    z = torch.from_numpy(V.latents(cfg, T, H, W)).to(dev).bfloat16()
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            out = fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return out, e0.elapsed_time(e1) / steps
+    out, ms = timed(lambda: m.decode(z).sample, max(1, min(args.steps, 3)), 1)
+    # algorithmic FLOPs: 2 * out pixels * Cout * taps * Cin over every convolution, frames as the chunks see them
+    dims, n = V.decoder_dims(cfg), len(cfg["dim_mult"])
+    t_up = cfg["temperal_downsample"][::-1]
+    fl = 0.0
+    for first in (True, False):
+        reps = 1 if first else T - 1
+        tc, h, w = 1, H, W
+        f = 2.0 * tc * h * w * (27 * cfg["z_dim"] * dims[0] + 4 * 27 * dims[0] ** 2 + 4 * dims[0] ** 2) + 4.0 * (h * w) ** 2 * dims[0]
+        for s_ in range(n):
+            ci, co = dims[s_], dims[s_ + 1]
+            f += 2.0 * tc * h * w * 27 * (ci * co + 5 * co * co) + (2.0 * tc * h * w * ci * co if ci != co else 0)
+            if s_ != n - 1:
+                if s_ < len(t_up) and t_up[s_] and not first:
+                    f += 2.0 * tc * h * w * 3 * co * 2 * co
+                    tc *= 2
+                h, w = 2 * h, 2 * w
+                f += 2.0 * tc * h * w * 9 * co * co
+        f += 2.0 * tc * h * w * 27 * dims[-1] * 12
+        fl += reps * f
+    res = {"workload": f"Wan2.2 VAE decode, {T} x {H} x {W} latents -> {1 + 4 * (T - 1)} frames {16 * H} x {16 * W}, bf16",
+           "ms": ms, "algorithmic_tflop": fl / 1e12, "tflops_per_s": fl / ms / 1e9, "gpu_launches": m.engine().launches}
+    with torch.no_grad():
+        try:
+            lib_out, lib_ms = timed(lambda: V.decode(sd, cfg, z, m.scale), 1, 1)
+            res["library_baseline"] = {"ms": lib_ms, "what": "the module's forward in stock torch bf16 ops (cuDNN Conv3d / "
+                                       "Conv2d, SDPA), same chunk loop and caches", "tflops_per_s": fl / lib_ms / 1e9}
+            res["speedup_vs_library"] = lib_ms / ms
+        except Exception as exc:   # noqa: BLE001
+            lib_out, res["library_baseline"] = None, {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}
+        rel = lambda a, b: (torch.linalg.vector_norm(a.float() - b.float()) / torch.linalg.vector_norm(b.float())).item()  # noqa: E731
+        par = {"checksum_sha256_16": output_checksum(out), "finite": bool(torch.isfinite(out.float()).all().item())}
+        if lib_out is not None:
+            par["native_rel_l2_vs_library"] = rel(out, lib_out)
+        if not args.checksum_only:
+            want = V.decode(_LazyF32(sd), cfg, z.float(), m.scale)
+            par["rel_l2_vs_fp32_oracle"] = rel(out, want)
+            if lib_out is not None:
+                par["library_rel_l2_vs_fp32_oracle"] = rel(lib_out, want)
+        res["parity"] = par
+    print(json.dumps(res))
+
+
 def run_loop(args):
     """BASELINE config 4: the full sampling loop (`full_edit`: first latent frame pinned, density 10 => the model sees
     0.1, guidance 6, flow-match Euler with shift 5) at 97 frames 512x896 through flexam_b200.sampler.DenoiseLoop — per
@@ -816,7 +893,8 @@ if __name__ == "__main__":
                     "around every launch, 3 extra steps outside the timed regions)")
     ap.add_argument("--loop-steps", type=int, default=50, help="sampling steps of --workload loop50")
     ap.add_argument("--graph", action="store_true", help="loop50: replay the transformer call from CUDA graphs (N = 1)")
-    ap.add_argument("--workload", default="config2", choices=["config2", "long", "loop50", "t5"],
+    ap.add_argument("--vae-frames", type=int, default=0, help="--workload vae: latent frames (default: the clip's 25)")
+    ap.add_argument("--workload", default="config2", choices=["config2", "long", "loop50", "t5", "vae"],
                     help="config2 = the metric's workload (default); long = BASELINE config 5, 193 frames 704x1280 "
                          "(43,120 tokens + 880 ref): a parity/stress case, not the bench line")
     a = ap.parse_args()
@@ -830,5 +908,7 @@ if __name__ == "__main__":
         run_loop(a)
     elif a.workload == "t5":
         run_t5(a)
+    elif a.workload == "vae":
+        run_vae(a)
     else:
         run_native(a)

@@ -56,6 +56,13 @@ SIGNATURES = {
     "fx_t5_attention": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _vp],
     "fx_add_bf16": [_vp, _vp, _i64, _vp],
     "fx_gated_gelu_bf16": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _vp],
+    # Wan2.2 VAE decoder (flexam_b200/vae.py)
+    "fx_vae_norm_act": [_vp, _i64, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _i, _i, _vp],
+    "fx_vae_upsample2x": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "fx_vae_time_interleave": [_vp, _vp, _i, _i64, _i, _vp],
+    "fx_vae_dupup_add": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "fx_softmax_rows_f32": [_vp, _i64, _vp, _i64, _i, _i, _f, _vp],
+    "fx_vae_unpatchify": [_vp, _i64, _vp, _i, _i, _i, _i, _i, _vp],
     "fx_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "fx_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
     # fp32 verification mode (flexam_b200/precise.py)

@@ -574,3 +574,71 @@ def gated_gelu(fc1: torch.Tensor, gate: torch.Tensor, out: torch.Tensor) -> torc
                                       _stream())
     _l.check(st, "fx_gated_gelu_bf16")
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Wan2.2 VAE decoder operators (see include/flexam_b200.h and flexam_b200/vae.py)
+# ----------------------------------------------------------------------------------------------------------
+def vae_norm_act(x: torch.Tensor, gamma: Optional[torch.Tensor], out: torch.Tensor, H: int, W: int, pad: int,
+                 frame0: int, silu: bool) -> torch.Tensor:
+    """x: bf16 [npix, C] (row stride free); out: bf16 [(frames)*(H+2pad)*(W+2pad), ldo] grid (or dense rows, pad 0)."""
+    _req(x, bf16, "vae_norm_act.x"), _req(out, bf16, "vae_norm_act.out")
+    if gamma is not None:
+        _req(gamma, bf16, "vae_norm_act.gamma")
+    npix, Cc = x.shape
+    frames = npix // (H * W)
+    if out.shape[0] < (frame0 + frames) * (H + 2 * pad) * (W + 2 * pad) or out.shape[1] < Cc:
+        raise _l.FlexamNativeError("vae_norm_act: output grid too small")
+    st = _l.load().fx_vae_norm_act(_p(x), x.stride(0), _p(gamma), _p(out), out.stride(0), npix, Cc, H, W, pad, frame0,
+                                   1 if silu else 0, _stream())
+    _l.check(st, "fx_vae_norm_act")
+    return out
+
+
+def vae_upsample2x(x: torch.Tensor, out: torch.Tensor, Fr: int, H: int, W: int) -> torch.Tensor:
+    _req(x, bf16, "vae_upsample2x.x"), _req(out, bf16, "vae_upsample2x.out")
+    Cc = x.shape[1]
+    if not (x.is_contiguous() and out.is_contiguous()) or x.shape[0] != Fr * H * W or \
+            tuple(out.shape) != (Fr * (2 * H + 2) * (2 * W + 2), Cc):
+        raise _l.FlexamNativeError("vae_upsample2x: shape mismatch")
+    _l.check(_l.load().fx_vae_upsample2x(_p(x), _p(out), Fr, H, W, Cc, _stream()), "fx_vae_upsample2x")
+    return out
+
+
+def vae_time_interleave(y: torch.Tensor, x: torch.Tensor, T: int, P: int) -> torch.Tensor:
+    _req(y, bf16, "vae_time_interleave.y"), _req(x, bf16, "vae_time_interleave.x")
+    Cc = x.shape[1]
+    if not (y.is_contiguous() and x.is_contiguous()) or tuple(y.shape) != (T * P, 2 * Cc) or x.shape[0] != 2 * T * P:
+        raise _l.FlexamNativeError("vae_time_interleave: shape mismatch")
+    _l.check(_l.load().fx_vae_time_interleave(_p(y), _p(x), T, P, Cc, _stream()), "fx_vae_time_interleave")
+    return x
+
+
+def vae_dupup_add_(main: torch.Tensor, x: torch.Tensor, Tout: int, H: int, W: int, ft: int, drop: int) -> torch.Tensor:
+    """main: bf16 [Tout*2H*2W, Cout] += DupUp3D(x: bf16 [T*H*W, Cin]) (see fx_vae_dupup_add)."""
+    _req(main, bf16, "vae_dupup_add.main"), _req(x, bf16, "vae_dupup_add.x")
+    if not (main.is_contiguous() and x.is_contiguous()) or main.shape[0] != Tout * 4 * H * W:
+        raise _l.FlexamNativeError("vae_dupup_add: shape mismatch")
+    st = _l.load().fx_vae_dupup_add(_p(main), _p(x), Tout, H, W, x.shape[1], main.shape[1], ft, drop, _stream())
+    _l.check(st, "fx_vae_dupup_add")
+    return main
+
+
+def softmax_rows(s: torch.Tensor, p: torch.Tensor, scale: float) -> torch.Tensor:
+    _req(s, f32, "softmax_rows.s"), _req(p, bf16, "softmax_rows.p")
+    rows, cols = s.shape
+    if tuple(p.shape) != (rows, cols):
+        raise _l.FlexamNativeError("softmax_rows: shape mismatch")
+    _l.check(_l.load().fx_softmax_rows_f32(_p(s), s.stride(0), _p(p), p.stride(0), rows, cols, scale, _stream()),
+             "fx_softmax_rows_f32")
+    return p
+
+
+def vae_unpatchify(y: torch.Tensor, video: torch.Tensor, T: int, H: int, W: int, frame0: int) -> torch.Tensor:
+    """y: bf16 [T*H*W, >=12]; video: bf16 [3, Ttot, 2H, 2W] contiguous, frames [frame0, frame0+T) written, clamped."""
+    _req(y, bf16, "vae_unpatchify.y"), _req(video, bf16, "vae_unpatchify.video")
+    if not video.is_contiguous() or video.shape[0] != 3 or tuple(video.shape[2:]) != (2 * H, 2 * W) or y.shape[0] != T * H * W:
+        raise _l.FlexamNativeError("vae_unpatchify: shape mismatch")
+    st = _l.load().fx_vae_unpatchify(_p(y), y.stride(0), _p(video), T, H, W, video.shape[1], frame0, _stream())
+    _l.check(st, "fx_vae_unpatchify")
+    return video

@@ -1,0 +1,381 @@
+"""Wan2.2 VAE decoder on the native kernels (decode half).
+
+``AutoencoderKLWan3_8`` mirrors the reference wrapper (FlexAM/models/wan_vae3_8.py:892-1057, cited as :line) for what the
+pipeline's last step calls — ``vae.decode(latents).sample`` — with the reference's parameter names for ``model.conv2.*``
+and ``model.decoder.*``. The forward is ``VaeDecoderEngine.decode``: the reference's frame-by-frame loop with its
+per-convolution feature cache (:820-849), every convolution an implicit GEMM on the tcgen05 kernels
+(``fx_conv_gemm_bf16``: causal 3x3x3, per-frame 3x3, (3,1,1) time convolution; 1x1 as plain GEMMs) reading zero-padded
+channel-last grids whose first two frames are the causal history, and the element-wise work between them (RMS_norm + SiLU,
+nearest 2x, temporal interleave, DupUp3D shortcut, residual adds, the attention block's softmax, unpatchify + clamp) as
+row kernels (csrc/vae.cu). ``encode`` is NOT built and raises. No torch compute, no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .lib import FX_EPI_BF16, FX_EPI_F32_EXACT, FlexamNativeError
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _pad64(c: int) -> int:
+    return -(-c // 64) * 64
+
+
+def decoder_dims(cfg: dict) -> List[int]:
+    d, mult = cfg["dec_dim"], cfg["dim_mult"]
+    return [d * u for u in [mult[-1]] + mult[::-1]]            # :642
+
+
+def param_shapes(cfg: dict) -> Dict[str, tuple]:
+    """state_dict keys / shapes of ``conv2`` + ``decoder`` of AutoencoderKLWan2_2_ (:739-782, :621-675)."""
+    z, dims = cfg["z_dim"], decoder_dims(cfg)
+    t_up = list(cfg["temperal_downsample"])[::-1]
+    out: Dict[str, tuple] = {}
+
+    def conv(name, co, ci, k):
+        out[name + ".weight"] = (co, ci) + tuple(k)
+        out[name + ".bias"] = (co,)
+
+    def res(name, ci, co):
+        out[name + ".residual.0.gamma"] = (ci, 1, 1, 1)
+        conv(name + ".residual.2", co, ci, (3, 3, 3))
+        out[name + ".residual.3.gamma"] = (co, 1, 1, 1)
+        conv(name + ".residual.6", co, co, (3, 3, 3))
+        if ci != co:
+            conv(name + ".shortcut", co, ci, (1, 1, 1))
+
+    conv("conv2", z, z, (1, 1, 1))
+    conv("decoder.conv1", dims[0], z, (3, 3, 3))
+    res("decoder.middle.0", dims[0], dims[0])
+    out["decoder.middle.1.norm.gamma"] = (dims[0], 1, 1)
+    conv("decoder.middle.1.to_qkv", 3 * dims[0], dims[0], (1, 1))
+    conv("decoder.middle.1.proj", dims[0], dims[0], (1, 1))
+    res("decoder.middle.2", dims[0], dims[0])
+    n = len(cfg["dim_mult"])
+    for i, (ci, co) in enumerate(zip(dims[:-1], dims[1:])):
+        for j in range(cfg["num_res_blocks"] + 1):
+            res(f"decoder.upsamples.{i}.upsamples.{j}", ci if j == 0 else co, co)
+        if i != n - 1:
+            j = cfg["num_res_blocks"] + 1
+            conv(f"decoder.upsamples.{i}.upsamples.{j}.resample.1", co, co, (3, 3))
+            if i < len(t_up) and t_up[i]:
+                conv(f"decoder.upsamples.{i}.upsamples.{j}.time_conv", 2 * co, co, (3, 1, 1))
+    out["decoder.head.0.gamma"] = (dims[-1], 1, 1, 1)
+    conv("decoder.head.2", 12, dims[-1], (3, 3, 3))
+    return out
+
+
+class VaeDecoderEngine:
+    """Packed weights, the per-convolution history grids and the launch sequence of one decode."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], cfg: dict, device: torch.device):
+        self.cfg, self.device, self.params = dict(cfg), torch.device(device), params
+        self.dims = decoder_dims(cfg)
+        for c in self.dims:
+            if c % 64 != 0:
+                raise FlexamNativeError(f"native VAE decoder: channel widths must be multiples of 64, got {self.dims}")
+        self._ws: Dict[tuple, torch.Tensor] = {}
+        self._hist: Dict[str, torch.Tensor] = {}
+        self.launches = 0
+        self._pack()
+
+    # -- weights: tap-major [Cout (padded to 8), taps * Cin (padded to 64)] ------------------------------------------
+    def _pack(self):
+        P, dev = self.params, self.device
+        for k, v in P.items():
+            if v.device != dev or v.dtype != bf16:
+                raise FlexamNativeError(f"parameter {k}: expected bf16 on {dev}, got {v.dtype} on {v.device}")
+        self.w: Dict[str, torch.Tensor] = {}
+        self.b: Dict[str, torch.Tensor] = {}
+        for k, v in P.items():
+            if not k.endswith(".weight"):
+                continue
+            name = k[:-7]
+            co, ci = v.shape[:2]
+            taps = int(math.prod(v.shape[2:]))
+            cip, cop = _pad64(ci), -(-co // 8) * 8
+            wt = torch.zeros((cop, taps, cip), dtype=bf16, device=dev)
+            wt[:co, :, :ci] = v.reshape(co, ci, taps).permute(0, 2, 1)          # K order (dt, dy, dx, cin)
+            self.w[name] = wt.view(cop, taps * cip).contiguous()
+            bias = torch.zeros((cop,), dtype=bf16, device=dev)
+            bias[:co] = P[name + ".bias"]
+            self.b[name] = bias
+        self.gamma = {k[:-6]: v.reshape(-1).contiguous() for k, v in P.items() if k.endswith(".gamma")}
+        # attention block: q|k and v as separate projections (v must be contiguous for the transpose)
+        C = self.dims[0]
+        wq = P["decoder.middle.1.to_qkv.weight"].reshape(3 * C, C)
+        bq = P["decoder.middle.1.to_qkv.bias"]
+        self.w_qk, self.b_qk = wq[:2 * C].contiguous(), bq[:2 * C].contiguous()
+        self.w_v, self.b_v = wq[2 * C:].contiguous(), bq[2 * C:].contiguous()
+        self._versions = tuple(p._version for p in P.values())
+        self._scale_key = None
+
+    def _fold_scale(self, scale: Sequence[torch.Tensor]):
+        """conv2(z / scale[1] + scale[0]) (:824-831) as ONE projection of the raw latents: the per-channel affine is
+        folded into conv2's weight and bias in fp32 once per (mean, 1/std) pair (weight-side constant folding)."""
+        key = (scale[0].data_ptr(), scale[1].data_ptr(), scale[0]._version, scale[1]._version)
+        if self._scale_key == key:
+            return
+        zd = self.cfg["z_dim"]
+        w = self.params["conv2.weight"].reshape(zd, zd).float()
+        mean, inv_std = scale[0].to(self.device, f32), scale[1].to(self.device, f32)
+        wf = torch.zeros((_pad64(zd), _pad64(zd)), dtype=bf16, device=self.device)
+        wf[:zd, :zd] = (w / inv_std.view(1, zd)).to(bf16)
+        bfold = torch.zeros((_pad64(zd),), dtype=bf16, device=self.device)
+        bfold[:zd] = (self.params["conv2.bias"].float() + w @ mean).to(bf16)
+        self.w_conv2, self.b_conv2 = wf, bfold
+        self._scale_key = key
+        self._scale_ref = (scale[0], scale[1])
+
+    # -- buffers ---------------------------------------------------------------------------------------------------
+    def _buf(self, name, shape, dtype=bf16, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
+            self._ws[key] = t
+        return t
+
+    def _grid(self, name: str, frames: int, Hp: int, Wp: int, C: int, keep_rows: int = 0) -> torch.Tensor:
+        """The zero-padded input grid of convolution ``name``: [frames, Hp, Wp, C] flattened to rows. Halo positions and
+        the history frames start as zeros and only interior / live positions are ever written. A chunk with more frames
+        than any before (the first chunk is not up-sampled in time) grows the grid and keeps its ``keep_rows`` history."""
+        need = frames * Hp * Wp
+        t = self._hist.get(name)
+        if t is None or t.shape[0] < need or t.shape[1] != C:
+            new = torch.zeros((need, C), dtype=bf16, device=self.device)
+            if t is not None and t.shape[1] == C and keep_rows:
+                new[:keep_rows].copy_(t[:keep_rows])
+            self._hist[name] = t = new
+        return t
+
+    def _reset_history(self):
+        for t in self._hist.values():
+            t.zero_()
+
+    # -- building blocks -------------------------------------------------------------------------------------------
+    def _cconv(self, name, x, T, H, W, gamma=None, silu=False, kt=3, ks=3):
+        """[RMS_norm + SiLU ->] causal convolution ``name`` over the chunk x (dense [T*H*W, Cin]) with the two cached
+        history frames in front (CausalConv3d :22-47 + the cache rule of its callers :219-238): returns dense
+        [T*H*W, Cout]. The history grid then keeps the last two input frames for the next chunk."""
+        w = self.w[name]
+        cin = w.shape[1] // (kt * ks * ks)
+        pad = 1 if ks == 3 else 0
+        Hp, Wp = H + 2 * pad, W + 2 * pad
+        hist = kt - 1
+        grid = self._grid(name, hist + T, Hp, Wp, cin, keep_rows=hist * Hp * Wp)
+        ops.vae_norm_act(x, gamma, grid, H, W, pad, hist, silu)
+        out = self._buf("out:" + name, (T * H * W, w.shape[0]))
+        rows = (hist + T) * Hp * Wp
+        ops.conv_gemm(grid[:rows], w, self.b[name], out, T, H, W, kt, ks, FX_EPI_BF16)
+        self.launches += 2
+        if hist:
+            plane = Hp * Wp
+            src = grid[T * plane:(T + hist) * plane]
+            grid[:hist * plane].copy_(src.clone() if T < hist else src)       # last two frames become the history
+        return out
+
+    def _res(self, name, x, T, H, W):
+        """ResidualBlock (:198-240)."""
+        if name + ".shortcut" in self.w:
+            w = self.w[name + ".shortcut"]
+            h = self._buf("sc:" + name, (x.shape[0], w.shape[0]))
+            ops.gemm(x, w, self.b[name + ".shortcut"], h, FX_EPI_BF16)
+            self.launches += 1
+        else:
+            h = x
+        y = self._cconv(name + ".residual.2", x, T, H, W, self.gamma[name + ".residual.0"], True)
+        y = self._cconv(name + ".residual.6", y, T, H, W, self.gamma[name + ".residual.3"], True)
+        ops.add_bf16_(y, h)
+        self.launches += 1
+        return y
+
+    def _attn(self, name, x, T, H, W):
+        """AttentionBlock (:243-282): one head of width C over the H*W tokens of each frame. S = Q K^T and O = P V are
+        GEMMs on the tensor cores (V transposed once into the [C, tokens] weight layout), softmax a row kernel."""
+        C, P = x.shape[1], H * W
+        out = self._buf("attn_out", (T * P, C))
+        for f in range(T):
+            xf = x[f * P:(f + 1) * P]
+            y = self._buf("attn_norm", (P, C))
+            ops.vae_norm_act(xf, self.gamma[name + ".norm"], y, H, W, 0, 0, False)
+            qk = self._buf("attn_qk", (P, 2 * C))
+            v = self._buf("attn_v", (P, C))
+            ops.gemm(y, self.w_qk, self.b_qk, qk, FX_EPI_BF16)
+            ops.gemm(y, self.w_v, self.b_v, v, FX_EPI_BF16)
+            s = self._buf("attn_s", (P, P), f32)
+            ops.gemm(qk[:, :C], qk[:, C:], None, s, FX_EPI_F32_EXACT)
+            p = self._buf("attn_p", (P, P))
+            ops.softmax_rows(s, p, 1.0 / math.sqrt(C))
+            vt = self._buf("attn_vt", (C, P))
+            ops.nchw_to_nhwc(v, vt, 0)                                    # [P, C] -> [C, P]
+            o = self._buf("attn_o", (P, C))
+            ops.gemm(p, vt, None, o, FX_EPI_BF16)
+            of = out[f * P:(f + 1) * P]
+            ops.gemm(o, self.w[name + ".proj"], self.b[name + ".proj"], of, FX_EPI_BF16)
+            ops.add_bf16_(of, xf.contiguous())
+            self.launches += 9
+        return out
+
+    def _resample(self, name, x, T, H, W, temporal, first):
+        """Resample upsample2d / upsample3d (:117-160)."""
+        C = x.shape[1]
+        if temporal and not first:        # the first chunk is not up-sampled in time (the "Rep" rule :121-123)
+            y = self._cconv(name + ".time_conv", x, T, H, W, None, False, kt=3, ks=1)            # [T*HW, 2C]
+            x2 = self._buf("tint:" + name, (2 * T * H * W, C))
+            ops.vae_time_interleave(y, x2, T, H * W)
+            self.launches += 1
+            x, T = x2, 2 * T
+        up = self._grid(name + ".resample.1", T, 2 * H + 2, 2 * W + 2, C)
+        rows = T * (2 * H + 2) * (2 * W + 2)
+        ops.vae_upsample2x(x.contiguous(), up[:rows], T, H, W)
+        w = self.w[name + ".resample.1"]
+        out = self._buf("out:" + name, (T * 4 * H * W, w.shape[0]))
+        ops.conv_gemm(up[:rows], w, self.b[name + ".resample.1"], out, T, 2 * H, 2 * W, 1, 3, FX_EPI_BF16)
+        self.launches += 2
+        return out, T
+
+    # -- decode ----------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, scale: Sequence[torch.Tensor]) -> torch.Tensor:
+        """z: [1, z_dim, T, H, W] normalised latents -> bf16 video [1, 3, 1 + 4 (T - 1), 16 H, 16 W] in [-1, 1]."""
+        if tuple(p._version for p in self.params.values()) != self._versions:
+            self._pack()
+        cfg, dev = self.cfg, self.device
+        zd = cfg["z_dim"]
+        if z.dim() != 5 or z.shape[0] != 1 or z.shape[1] != zd:
+            raise FlexamNativeError(f"VAE decode: expected latents [1, {zd}, T, H, W], got {tuple(z.shape)}")
+        self._fold_scale(scale)
+        self._reset_history()
+        self.launches = 0
+        _, _, T, H, W = z.shape
+        dims = self.dims
+        n = len(cfg["dim_mult"])
+        t_up = list(cfg["temperal_downsample"])[::-1]
+        nres = cfg["num_res_blocks"] + 1
+        P = H * W
+        zc = z[0].to(dev, bf16).contiguous().view(zd, T * P)
+        zl = self._buf("z_rows", (T * P, _pad64(zd)), zero=True)
+        ops.nchw_to_nhwc(zc, zl, 0)
+        x_all = self._buf("conv2_out", (T * P, _pad64(zd)))
+        ops.gemm(zl, self.w_conv2, self.b_conv2, x_all, FX_EPI_BF16)            # un-normalise + conv2 (:824-831)
+        self.launches += 2
+        Tout = 1 + 4 * (T - 1)
+        up_s = 2 ** (n - 1)
+        video = torch.empty((3, Tout, 2 * up_s * H, 2 * up_s * W), dtype=bf16, device=dev)
+        f_out = 0
+        for i in range(T):                                                       # :832-846, one latent frame per chunk
+            first = i == 0
+            Tc, h, w = 1, H, W
+            x = self._cconv("decoder.conv1", x_all[i * P:(i + 1) * P], Tc, h, w)
+            x = self._res("decoder.middle.0", x, Tc, h, w)
+            x = self._attn("decoder.middle.1", x, Tc, h, w)
+            x = self._res("decoder.middle.2", x, Tc, h, w)
+            for s in range(n):                                                   # Up_ResidualBlock :494-502
+                name = f"decoder.upsamples.{s}.upsamples."
+                up = s != n - 1
+                temporal = up and s < len(t_up) and bool(t_up[s])
+                x_in = x
+                main = x
+                for j in range(nres):
+                    main = self._res(name + str(j), main, Tc, h, w)
+                if up:
+                    if main is x_in or main.data_ptr() == x_in.data_ptr():
+                        raise FlexamNativeError("internal: residual output aliases the block input")
+                    main, T2 = self._resample(name + str(nres), main, Tc, h, w, temporal, first)
+                    ft = 2 if temporal else 1
+                    ops.vae_dupup_add_(main, x_in.contiguous(), T2, h, w, ft, ft - 1 if first else 0)
+                    self.launches += 1
+                    Tc, h, w = T2, 2 * h, 2 * w
+                x = main
+            y = self._cconv("decoder.head.2", x, Tc, h, w, self.gamma["decoder.head.0"], True)
+            ops.vae_unpatchify(y, video, Tc, h, w, f_out)
+            self.launches += 1
+            f_out += Tc
+        if f_out != Tout:
+            raise FlexamNativeError(f"internal: decoded {f_out} frames, expected {Tout}")
+        return video.unsqueeze(0)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# nn.Module with the reference wrapper's surface
+# ----------------------------------------------------------------------------------------------------------
+class DecoderOutput:
+    def __init__(self, sample):
+        self.sample = sample
+
+
+def _set_param(root: nn.Module, dotted: str, p: nn.Parameter):
+    parts = dotted.split(".")
+    m = root
+    for name in parts[:-1]:
+        child = m._modules.get(name)
+        if child is None:
+            child = nn.Module()
+            m.add_module(name, child)
+        m = child
+    m.register_parameter(parts[-1], p)
+
+
+class AutoencoderKLWan3_8(nn.Module):
+    """Drop-in for the DECODE side of FlexAM.models.AutoencoderKLWan3_8 (:892-1057): ``decode(z).sample``. Parameters
+    carry the reference's names under ``model.`` (``model.conv2.*``, ``model.decoder.*``); a full checkpoint loads with
+    ``strict=False`` (the encoder half is not built: ``encode`` raises)."""
+
+    def __init__(self, latent_channels=48, c_dim=160, vae_pth=None, dim_mult=(1, 2, 4, 4),
+                 temperal_downsample=(False, True, True), temporal_compression_ratio=4, spatial_compression_ratio=8,
+                 dec_dim=256, latents_mean=None, latents_std=None, dtype=torch.bfloat16, device=None):
+        super().__init__()
+        self.cfg = dict(z_dim=latent_channels, dec_dim=dec_dim, dim_mult=list(dim_mult), num_res_blocks=2,
+                        temperal_downsample=list(temperal_downsample))
+        self.temporal_compression_ratio = temporal_compression_ratio
+        self.spatial_compression_ratio = spatial_compression_ratio
+        for name, shape in param_shapes(self.cfg).items():
+            _set_param(self, "model." + name, nn.Parameter(torch.empty(shape, dtype=dtype, device=device),
+                                                           requires_grad=False))
+        mean = torch.zeros(latent_channels) if latents_mean is None else torch.as_tensor(latents_mean, dtype=f32)
+        std = torch.ones(latent_channels) if latents_std is None else torch.as_tensor(latents_std, dtype=f32)
+        self.scale = [mean, 1.0 / std]          # the reference hard-codes the Wan2.2 statistics here (:906-1008)
+        self._engine: Optional[VaeDecoderEngine] = None
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def engine(self) -> VaeDecoderEngine:
+        params = {k[len("model."):]: v.detach() for k, v in self.named_parameters()}
+        if self._engine is None or tuple(p.data_ptr() for p in self._engine.params.values()) != \
+                tuple(p.data_ptr() for p in params.values()):
+            self._engine = VaeDecoderEngine(params, self.cfg, next(iter(params.values())).device)
+        return self._engine
+
+    def _decode(self, zs: torch.Tensor) -> DecoderOutput:                       # :1041-1049
+        eng = self.engine()
+        with (torch.cuda.device(eng.device) if eng.device.type == "cuda" else _null()), ops.stream_scope():
+            dec = [eng.decode(u.unsqueeze(0), self.scale)[0] for u in zs]
+        return DecoderOutput(torch.stack(dec))
+
+    def decode(self, z: torch.Tensor, return_dict: bool = True):                # :1051-1057
+        decoded = self._decode(z).sample
+        return DecoderOutput(decoded) if return_dict else (decoded,)
+
+    def encode(self, x, return_dict: bool = True):
+        raise FlexamNativeError("the VAE encoder half (wan_vae3_8.py:788-819) is not built on the native path")
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

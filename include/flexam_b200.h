@@ -293,6 +293,32 @@ int fx_add_bf16(void* x, const void* y, int64_t n, void* stream);
 int fx_gated_gelu_bf16(const void* fc1, int64_t ld1, const void* gate, int64_t ldg, void* out, int64_t ldo, int64_t M,
                        int N, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Wan2.2 VAE decoder (decode half; FlexAM/models/wan_vae3_8.py). Activations are channel-last bf16
+ * [frames, H, W, C]; every convolution (CausalConv3d :22-47, Resample's per-frame 3x3 :93-97 and (3,1,1) time convolution
+ * :98-99, 1x1 shortcuts, the attention block's 1x1 projections) is fx_conv_gemm_bf16 / fx_gemm_bf16. The rest:
+ *   fx_vae_norm_act        out[grid row of pixel p][:C] = act(x[p] / max(||x[p]||_2, 1e-12) * sqrt(C) * gamma): RMS_norm
+ *                          :50-64 (+ SiLU when silu != 0) written into the zero-padded grid [frames, H+2*pad, W+2*pad, ldo]
+ *                          the next convolution reads, starting at frame `frame0` (the frames before it are the causal
+ *                          history the caller keeps); gamma == NULL: plain copy into that layout; pad = 0: dense rows
+ *   fx_vae_upsample2x      nearest-exact 2x of [F, H, W, C] into the padded grid [F, 2H+2, 2W+2, C]        (:67-73, :93-95)
+ *   fx_vae_time_interleave x[2t+k][p][c] = y[t][p][k*C+c]: the frame doubling after the time convolution    (:139-142)
+ *   fx_vae_dupup_add       main += DupUp3D(x) (channel repeat + 2x2(x2) pixel shuffle, first chunk drops ft-1 frames),
+ *                          bf16 add                                                                   (:395-417, :497-500)
+ *   fx_softmax_rows_f32    p bf16 [rows, cols] = softmax(s f32 * scale) per row (the attention block's single head of
+ *                          width C over the H*W tokens of a frame: S = Q K^T and P V are fx_gemm_bf16 calls)  (:260-282)
+ *   fx_vae_unpatchify      video bf16 [3, Ttot, 2H, 2W] frames [frame0, frame0+T) = clamp(unpatchify(y [T,H,W,>=12]))
+ *                                                                                                      (:304-318, :1043)
+ */
+int fx_vae_norm_act(const void* x, int64_t ldx, const void* gamma, void* out, int64_t ldo, int64_t npix, int C, int H,
+                    int W, int pad, int frame0, int silu, void* stream);
+int fx_vae_upsample2x(const void* x, void* out, int F, int H, int W, int C, void* stream);
+int fx_vae_time_interleave(const void* y, void* x, int T, int64_t P, int C, void* stream);
+int fx_vae_dupup_add(void* main_io, const void* x, int Tout, int H, int W, int Cin, int Cout, int ft, int drop,
+                     void* stream);
+int fx_softmax_rows_f32(const float* s, int64_t lds, void* p, int64_t ldp, int rows, int cols, float scale, void* stream);
+int fx_vae_unpatchify(const void* y, int64_t ldy, void* video, int T, int H, int W, int Ttot, int frame0, void* stream);
+
 /* Small utility kernels used by the host glue. */
 int fx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int fx_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);

@@ -34,7 +34,7 @@ CASES = {
     "real2_frac": ("real2", (5, 16, 28), "frac"),
 }
 DEFAULT = ("tiny_tok", "tiny_sample", "real2_tok", "tiny_frac", "real2_frac", "tiny_loop", "rope_tables", "t5_tiny",
-           "t5_real2")
+           "t5_real2", "vae_tiny")
 
 
 def run_case(name: str):
@@ -165,6 +165,33 @@ def run_t5(name: str):
                         meta=np.array([L, step] + list(lens), dtype=np.int64), config=np.array(cfg_name))
 
 
+VAE_CASES = {
+    # name: (vae config, latent grid (T, H, W)); 3 latent frames cover the first chunk, the "Rep" rule and the cached path
+    "vae_tiny": ("tiny", (3, 4, 6)),
+}
+
+
+def run_vae(name: str):
+    """The REAL Wan2.2 VAE decoder (FlexAM/models/wan_vae3_8.py:820-849 + the wrapper's clamp :1043) on synthetic weights."""
+    from oracle import vae_oracle as V
+    cfg_name, (T, H, W) = VAE_CASES[name]
+    cfg = V.VAE_CONFIGS[cfg_name]
+    t0 = time.time()
+    model = ref_import.build_reference_vae(cfg).eval()
+    sd = {k: torch.from_numpy(v) for k, v in V.state_dict(cfg).items()}
+    missing = model.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and all(k.startswith(("encoder", "conv1")) for k in missing.missing_keys)
+    z, scale = torch.from_numpy(V.latents(cfg, T, H, W)), V.latent_scale(cfg)
+    with torch.no_grad():
+        ref = model.decode(z, scale).clamp_(-1, 1)
+        mine = V.decode(sd, cfg, z, scale)
+    rel = ((ref - mine).norm() / ref.norm()).item()
+    print(f"{name}: reference out {tuple(ref.shape)} mean |x| {ref.abs().mean():.3f}  oracle rel-L2 {rel:.2e}  ({time.time() - t0:.1f}s)")
+    assert rel < 2e-5, "VAE decoder oracle disagrees with the reference"
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), out=ref.numpy().astype(np.float32),
+                        meta=np.array([T, H, W], dtype=np.int64), config=np.array(cfg_name))
+
+
 def run_rope(name: str = "rope_tables"):
     """RoPE tables of the REAL reference module, default and after enable_riflex() with its default arguments
     (:774-788): a few position rows of the complex128 / complex64 tables as float64 (cos, sin)."""
@@ -187,4 +214,4 @@ if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     for n in (sys.argv[1:] or DEFAULT):
         (run_loop(n) if n == "tiny_loop" else run_rope(n) if n == "rope_tables" else run_t5(n) if n in T5_CASES
-         else run_case(n))
+         else run_vae(n) if n in VAE_CASES else run_case(n))

@@ -127,3 +127,23 @@ def build_reference_t5(cfg: dict):
     return mod.WanT5EncoderModel(vocab=cfg["vocab"], dim=cfg["dim"], dim_attn=cfg["dim_attn"], dim_ffn=cfg["dim_ffn"],
                                  num_heads=cfg["num_heads"], num_layers=cfg["num_layers"],
                                  num_buckets=cfg["num_buckets"], shared_pos=False, dropout=0.0)
+
+
+def build_reference_vae(cfg: dict):
+    """The REAL Wan2.2 VAE core (FlexAM/models/wan_vae3_8.py:739-870, AutoencoderKLWan2_2_) with the decoder width of
+    ``cfg`` (the encoder is built at a small width: only decode() is exercised)."""
+    import_reference()
+    import torch
+
+    class _Out:
+        def __init__(self, sample=None, latent_dist=None):
+            self.sample, self.latent_dist = sample, latent_dist
+    _mod("diffusers.models.autoencoders")
+    _mod("diffusers.models.autoencoders.vae", DecoderOutput=_Out, DiagonalGaussianDistribution=object)
+    _mod("diffusers.models.modeling_outputs", AutoencoderKLOutput=_Out)
+    _mod("diffusers.utils.accelerate_utils", apply_forward_hook=lambda f: f)
+    name = "FlexAM.models.wan_vae3_8"
+    mod = sys.modules.get(name) or _load(name, os.path.join(REF_ROOT, "FlexAM", "models", "wan_vae3_8.py"))
+    return mod.AutoencoderKLWan2_2_(dim=16, dec_dim=cfg["dec_dim"], z_dim=cfg["z_dim"], dim_mult=list(cfg["dim_mult"]),
+                                    num_res_blocks=cfg["num_res_blocks"],
+                                    temperal_downsample=list(cfg["temperal_downsample"]))

@@ -425,7 +425,59 @@ def gated_gelu(fc1, gate, out):
     return out.copy_((fc1.float() * _rb(_rb(0.5 * g) * _rb(1.0 + th))).to(bf16))
 
 
-NAMES = ("conv_gemm", "nchw_to_nhwc_padded", "embedding", "t5_layernorm", "t5_attention", "add_bf16_", "gated_gelu", "groupnorm_partials", "groupnorm_silu_partials", "linear_f32_tc", "dedup_f32", "fingerprint_table", "fingerprint", "gemm", "ln_modulate", "modulation_tables", "ln_scale_shift", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
+def _grid_rows(npix, H, W, pad, f0):
+    p = torch.arange(npix)
+    f, r = p // (H * W), p % (H * W)
+    return ((f + f0) * (H + 2 * pad) + r // W + pad) * (W + 2 * pad) + r % W + pad
+
+
+def vae_norm_act(x, gamma, out, H, W, pad, frame0, silu):
+    npix, C = x.shape
+    y = x.float()
+    if gamma is not None:
+        y = _rb(y * (C ** 0.5 / y.norm(dim=1, keepdim=True).clamp(min=1e-12))) * gamma.float()
+        if silu:
+            y = F.silu(_rb(y))
+    out[_grid_rows(npix, H, W, pad, frame0), :C] = y.to(bf16)
+    return out
+
+
+def vae_upsample2x(x, out, Fr, H, W):
+    C = x.shape[1]
+    u = x.view(Fr, H, W, C).repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    out.view(Fr, 2 * H + 2, 2 * W + 2, C)[:, 1:-1, 1:-1] = u
+    return out
+
+
+def vae_time_interleave(y, x, T, P):
+    C = x.shape[1]
+    x.copy_(y.view(T, P, 2, C).permute(0, 2, 1, 3).reshape(2 * T * P, C))
+    return x
+
+
+def vae_dupup_add_(main, x, Tout, H, W, ft, drop):
+    Cin, Cout = x.shape[1], main.shape[1]
+    T = x.shape[0] // (H * W)
+    factor = 4 * ft
+    rep = Cout * factor // Cin
+    v = x.float().view(T, H, W, Cin).permute(3, 0, 1, 2)[None].repeat_interleave(rep, dim=1)
+    v = v.view(1, Cout, ft, 2, 2, T, H, W).permute(0, 1, 5, 2, 6, 3, 7, 4).reshape(1, Cout, T * ft, 2 * H, 2 * W)
+    v = v[:, :, drop:][0].permute(1, 2, 3, 0).reshape(Tout * 4 * H * W, Cout)
+    return main.copy_((main.float() + v).to(bf16))
+
+
+def softmax_rows(s, p, scale):
+    return p.copy_(F.softmax(s * scale, dim=-1).to(bf16))
+
+
+def vae_unpatchify(y, video, T, H, W, frame0):
+    u = y[:, :12].float().view(T, H, W, 3, 2, 2).permute(3, 0, 1, 5, 2, 4).reshape(3, T, 2 * H, 2 * W)   # c f h q w r
+    video[:, frame0:frame0 + T] = u.clamp(-1, 1).to(bf16)
+    return video
+
+
+NAMES = ("vae_norm_act", "vae_upsample2x", "vae_time_interleave", "vae_dupup_add_", "softmax_rows", "vae_unpatchify",
+         "conv_gemm", "nchw_to_nhwc_padded", "embedding", "t5_layernorm", "t5_attention", "add_bf16_", "gated_gelu", "groupnorm_partials", "groupnorm_silu_partials", "linear_f32_tc", "dedup_f32", "fingerprint_table", "fingerprint", "gemm", "ln_modulate", "modulation_tables", "ln_scale_shift", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
                  "linear_f32", "nchw_to_nhwc", "im2col3x3", "groupnorm_silu", "swap01", "cfg_euler_step", "add_", "sub", "split3", "join3",
                  "ln_f32", "rmsnorm_rope_f32", "gelu_f32_", "gated_residual_f32_", "attention_f32",
                  "groupnorm_silu_f32")

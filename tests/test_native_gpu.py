@@ -800,6 +800,104 @@ def test_t5_encoder_full_depth(dev):
     assert rel < 1.5 * rel_lib + BF16_GATE and rel_nl < 1.5 * rel_lib + BF16_GATE
 
 
+# ------------------------------------------------------------------------------------------------------
+# Wan2.2 VAE decoder (decode half; FlexAM/models/wan_vae3_8.py)
+# ------------------------------------------------------------------------------------------------------
+def test_vae_operators(dev):
+    from flexam_b200 import ops
+    from oracle import vae_oracle as V
+    g = torch.Generator(device=dev).manual_seed(61)
+    T, H, W, C = 3, 6, 10, 256
+    x = torch.randn(T * H * W, C, device=dev, generator=g).bfloat16()
+    gam = (1 + 0.1 * torch.randn(C, device=dev, generator=g)).bfloat16()
+    grid = torch.zeros((T + 2) * (H + 2) * (W + 2), C, device=dev, dtype=torch.bfloat16)
+    ops.vae_norm_act(x, gam, grid, H, W, 1, 2, True)
+    want = torch.nn.functional.silu(torch.nn.functional.normalize(x.float(), dim=1) * C ** 0.5 * gam.float())
+    g5 = grid.view(T + 2, H + 2, W + 2, C)
+    assert _rel(g5[2:, 1:-1, 1:-1].reshape(-1, C), want) < 4e-3
+    assert g5[:2].abs().max().item() == 0 and g5[:, 0].abs().max().item() == 0 and g5[:, :, -1].abs().max().item() == 0
+    dense = torch.empty_like(x)
+    ops.vae_norm_act(x, None, dense, H, W, 0, 0, False)
+    assert torch.equal(dense, x)
+    up = torch.zeros(T * (2 * H + 2) * (2 * W + 2), C, device=dev, dtype=torch.bfloat16)
+    ops.vae_upsample2x(x, up, T, H, W)
+    ref_up = x.view(T, H, W, C).repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    assert torch.equal(up.view(T, 2 * H + 2, 2 * W + 2, C)[:, 1:-1, 1:-1], ref_up)
+    y = torch.randn(T * H * W, 2 * C, device=dev, generator=g).bfloat16()
+    xi = torch.empty(2 * T * H * W, C, device=dev, dtype=torch.bfloat16)
+    ops.vae_time_interleave(y, xi, T, H * W)
+    assert torch.equal(xi, y.view(T, H * W, 2, C).permute(0, 2, 1, 3).reshape(-1, C))
+    for ft, first, cout in ((2, False, 256), (2, True, 256), (1, False, 128)):
+        Tout = T * ft - (ft - 1 if first else 0)
+        main = torch.randn(Tout * 4 * H * W, cout, device=dev, generator=g).bfloat16()
+        keep = main.clone()
+        ops.vae_dupup_add_(main, x, Tout, H, W, ft, ft - 1 if first else 0)
+        xc = x.float().view(T, H, W, C).permute(3, 0, 1, 2)[None]
+        sh = V.dup_up3d(xc, cout, ft, 2, first)[0].permute(1, 2, 3, 0).reshape(-1, cout)
+        assert torch.equal(main, (keep.float() + sh).bfloat16())
+    s_ = torch.randn(200, 1792, device=dev, generator=g) * 30
+    p = torch.empty(200, 1792, device=dev, dtype=torch.bfloat16)
+    ops.softmax_rows(s_, p, 1.0 / 32)
+    assert _rel(p, torch.softmax(s_ / 32, dim=-1)) < 3e-3
+    yh = torch.randn(T * H * W, 16, device=dev, generator=g).bfloat16() * 0.8
+    video = torch.full((3, T + 1, 2 * H, 2 * W), 7.0, device=dev, dtype=torch.bfloat16)
+    ops.vae_unpatchify(yh, video, T, H, W, 1)
+    ref_v = yh[:, :12].float().view(T, H, W, 3, 2, 2).permute(3, 0, 1, 5, 2, 4).reshape(3, T, 2 * H, 2 * W).clamp(-1, 1)
+    assert torch.equal(video[:, 1:], ref_v.bfloat16()) and (video[:, 0] == 7.0).all()
+
+
+def _vae_model(cfg_name, dev):
+    from flexam_b200.vae import AutoencoderKLWan3_8
+    from oracle import vae_oracle as V
+    cfg = V.VAE_CONFIGS[cfg_name]
+    scale = V.latent_scale(cfg)
+    m = AutoencoderKLWan3_8(latent_channels=cfg["z_dim"], dec_dim=cfg["dec_dim"], dim_mult=cfg["dim_mult"],
+                            temperal_downsample=cfg["temperal_downsample"], latents_mean=scale[0],
+                            latents_std=1.0 / scale[1], device=dev)
+    sd = V.state_dict_torch(cfg, dev, torch.bfloat16)
+    m.load_state_dict({"model." + k: v for k, v in sd.items()}, strict=True)
+    return m, cfg, sd
+
+
+def test_vae_decode_matches_reference_golden(dev, golden_dir):
+    """Native VAE decode vs the REAL module's fp32 CPU output (tests/golden/vae_tiny.npz), the bf16-policy oracle and the
+    module's own bf16 execution with stock torch ops (cuDNN convolutions), all on the same weights and latents."""
+    from oracle import vae_oracle as V
+    g = np.load(os.path.join(golden_dir, "vae_tiny.npz"))
+    T, H, W = (int(v) for v in g["meta"])
+    m, cfg, sd = _vae_model(str(g["config"]), dev)
+    z = torch.from_numpy(V.latents(cfg, T, H, W)).to(dev)
+    out = m.decode(z.bfloat16()).sample
+    torch.cuda.synchronize()
+    gold = torch.from_numpy(g["out"]).to(dev)
+    assert out.shape == gold.shape and torch.isfinite(out.float()).all()
+    want = V.decode({k: v.float() for k, v in sd.items()}, cfg, z, m.scale, policy="bf16")
+    lib_out = V.decode(sd, cfg, z.bfloat16(), m.scale).float()
+    r_g, r_o, r_l, gap = _rel(out, gold), _rel(out, want), _rel(out, lib_out), _rel(lib_out, gold)
+    print(f"vae_tiny: native vs fp32 reference golden {r_g:.3e}; vs bf16-policy oracle {r_o:.3e}; vs the module's bf16 "
+          f"execution (library) {r_l:.3e}; library vs fp32 golden {gap:.3e}")
+    assert r_g < 1.5 * gap + 5e-3 and r_l < 2.5e-2 and r_o < 2.5e-2
+    out2 = m.decode(z.bfloat16()).sample                       # the history grids are reset per decode
+    assert torch.equal(out, out2)
+
+
+def test_vae_decode_real_width(dev):
+    """The Wan2.2 decoder at its real width (1024/1024/1024/512/256 channels, single-head attention of width 1024) on a
+    small latent grid: 3 latent frames of 8 x 12 -> 9 frames of 128 x 192."""
+    from oracle import vae_oracle as V
+    m, cfg, sd = _vae_model("real", dev)
+    z = torch.from_numpy(V.latents(cfg, 3, 8, 12)).to(dev)
+    out = m.decode(z.bfloat16()).sample
+    torch.cuda.synchronize()
+    assert out.shape == (1, 3, 9, 128, 192) and torch.isfinite(out.float()).all()
+    fp32 = V.decode({k: v.float() for k, v in sd.items()}, cfg, z, m.scale)
+    lib_out = V.decode(sd, cfg, z.bfloat16(), m.scale).float()
+    r_f, r_l, gap = _rel(out, fp32), _rel(out, lib_out), _rel(lib_out, fp32)
+    print(f"vae real width: native vs fp32 oracle {r_f:.3e}; native vs library bf16 execution {r_l:.3e}; library vs fp32 "
+          f"{gap:.3e} ({m.engine().launches} launches)")
+    assert r_f < 1.5 * gap + 5e-3 and r_l < 1.5 * gap + 1e-2
+
+
 def test_missing_extension_fails_loudly(monkeypatch):
     from flexam_b200 import lib
     monkeypatch.setattr(lib, "_lib", None)
