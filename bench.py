@@ -616,10 +616,10 @@ def run_vae(args):
     lib.check(lib.load().fx_check_device(dev.index), "fx_check_device")
     cfg = V.VAE_CONFIGS["real"]
     scale = V.latent_scale(cfg)
-    m = AutoencoderKLWan3_8(latent_channels=cfg["z_dim"], dec_dim=cfg["dec_dim"], dim_mult=cfg["dim_mult"],
-                            temperal_downsample=cfg["temperal_downsample"], latents_mean=scale[0],
-                            latents_std=1.0 / scale[1], device=dev)
-    sd = V.state_dict_torch(cfg, dev, torch.bfloat16)
+    m = AutoencoderKLWan3_8(latent_channels=cfg["z_dim"], c_dim=cfg["enc_dim"], dec_dim=cfg["dec_dim"],
+                            dim_mult=cfg["dim_mult"], temperal_downsample=cfg["temperal_downsample"],
+                            latents_mean=scale[0], latents_std=1.0 / scale[1], device=dev)
+    sd = {**V.encoder_state_dict_torch(cfg, dev, torch.bfloat16), **V.state_dict_torch(cfg, dev, torch.bfloat16)}
     m.load_state_dict({"model." + k: v for k, v in sd.items()}, strict=True)
     T, H, W = GRID if args.vae_frames <= 0 else (args.vae_frames, GRID[1], GRID[2])
     z = torch.from_numpy(V.latents(cfg, T, H, W)).to(dev).bfloat16()
@@ -675,6 +675,23 @@ def run_vae(args):
             if lib_out is not None:
                 par["library_rel_l2_vs_fp32_oracle"] = rel(lib_out, want)
         res["parity"] = par
+        # the encoder half on a video of the same size (the pipeline encodes 8 such clips per generation, :662-819)
+        xv = torch.from_numpy(V.video(cfg, 1 + 4 * (T - 1), 16 * H, 16 * W)).to(dev).bfloat16()
+        enc, enc_ms = timed(lambda: m.encode(xv).latent_dist.parameters, 1, 1)
+        enc_res = {"ms": enc_ms, "gpu_launches": m.engine().launches, "checksum_sha256_16": output_checksum(enc),
+                   "finite": bool(torch.isfinite(enc.float()).all().item())}
+        try:
+            lib_enc, lib_enc_ms = timed(lambda: V.encode(sd, cfg, xv, m.scale), 1, 1)
+            enc_res["library_ms"] = lib_enc_ms
+            enc_res["speedup_vs_library"] = lib_enc_ms / enc_ms
+            enc_res["native_rel_l2_vs_library"] = rel(enc, lib_enc)
+            if not args.checksum_only:
+                want_e = V.encode(_LazyF32(sd), cfg, xv.float(), m.scale)
+                enc_res["rel_l2_vs_fp32_oracle"] = rel(enc, want_e)
+                enc_res["library_rel_l2_vs_fp32_oracle"] = rel(lib_enc, want_e)
+        except Exception as exc:   # noqa: BLE001
+            enc_res["library_error"] = f"{type(exc).__name__}: {str(exc)[:160]}"
+        res["encode"] = enc_res
     print(json.dumps(res))
 
 

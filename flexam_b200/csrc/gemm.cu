@@ -54,6 +54,7 @@ struct GemmParams {
   // conv_off[tap] (the tap's (dt, dy, dx) as a row distance on the padded grid; rows outside the buffer are TMA zero fill);
   // output row m is a position of the padded grid: interior positions are written to the dense [T*H*W, N] result.
   int conv_taps, conv_kb_per_tap, conv_Hp, conv_Wp, conv_H, conv_W;
+  int conv_stride_s, conv_stride_t;   // 2: keep only odd interior positions / odd frames (stride-2 convolutions)
   int conv_off[27];
   int b_k_wrap;        // > 0: the weight's K extent; A is [M, planes * b_k_wrap] (bf16 planes of an fp32 matrix side by
                        // side) and the weight column of k-block kb is (kb * 64) % b_k_wrap — one accumulation over all planes
@@ -104,7 +105,10 @@ __device__ __forceinline__ long long conv_dense_row(const GemmParams& p, int row
   const int xp = r - yp * p.conv_Wp;
   const int y = yp - (p.conv_Hp - p.conv_H) / 2, x = xp - (p.conv_Wp - p.conv_W) / 2;
   if (y < 0 || y >= p.conv_H || x < 0 || x >= p.conv_W) return -1;
-  return (static_cast<long long>(t) * p.conv_H + y) * p.conv_W + x;
+  if (p.conv_stride_s == 2 && !((y & 1) && (x & 1))) return -1;   // ZeroPad2d((0,1,0,1)) + stride 2: centres (2y+1, 2x+1)
+  if (p.conv_stride_t == 2 && !(t & 1)) return -1;                 // time kernel 3, stride 2 over [last cached frame | chunk]
+  const int ss = p.conv_stride_s, st = p.conv_stride_t;
+  return (static_cast<long long>(t / st) * (p.conv_H / ss) + y / ss) * (p.conv_W / ss) + x / ss;
 }
 
 // Direct-store epilogues: one 32-column slab of one output row, v[j] = accumulator bits for column col0 + j.
@@ -648,7 +652,7 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
 
 namespace fx {
 struct ConvSpec {   // implicit-GEMM convolution over a zero-padded channel-last activation (see fx_conv_gemm_bf16)
-  int taps, cin, Hp, Wp, H, W;
+  int taps, cin, Hp, Wp, H, W, stride_s, stride_t;
   long long a_rows;   // rows of the padded activation buffer (Tin * Hp * Wp)
   int off[27];
 };
@@ -709,6 +713,7 @@ int fx::gemm_impl(const void* a, int64_t lda, const void* w, int64_t ldw, const 
     p.conv_taps = conv->taps;
     p.conv_kb_per_tap = conv->cin / kBK;
     p.conv_Hp = conv->Hp; p.conv_Wp = conv->Wp; p.conv_H = conv->H; p.conv_W = conv->W;
+    p.conv_stride_s = conv->stride_s; p.conv_stride_t = conv->stride_t;
     for (int i = 0; i < conv->taps; ++i) p.conv_off[i] = conv->off[i];
   }
 
@@ -824,10 +829,14 @@ extern "C" int fx_linear_f32_tc(const float* in, int64_t ldi, const void* w, int
 // [T, Hp, Wp]; tap (dt, dy, dx) reads the SAME matrix shifted by dt*Hp*Wp + (dy-1)*Wp + (dx-1) rows, so the K loop
 // walks taps x Cin with one TMA coordinate change per tap; halo positions are computed and dropped (1.5-9 % extra work),
 // interior ones are written densely as [T*H*W, Cout]. Weight: bf16 [Cout, taps*Cin], K order (dt, dy, dx, cin).
+// stride_s = 2: nn.ZeroPad2d((0,1,0,1)) + Conv2d(3, stride 2) (the VAE's downsample, wan_vae3_8.py:101-107): only the
+// centres (2y+1, 2x+1) are kept -> [T*(H/2)*(W/2), Cout]; stride_t = 2: Conv3d((3,1,1), stride (2,1,1)) over [last cached
+// frame | chunk] (:108-109, :150-153): only odd frames of the causal form are kept. The dropped positions are computed.
 // Used by the control fuser's 3x3 convolutions (cnn_conv1..4, wan_transformer3d_FlexAM.py:680-711).
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int fx_conv_gemm_bf16(const void* act, const void* w, const void* bias, void* out, int64_t ldo, int T,
-                                 int H, int W, int Cin, int Cout, int kt, int ks, int epilogue, void* stream) {
+                                 int H, int W, int Cin, int Cout, int kt, int ks, int stride_s, int stride_t,
+                                 int epilogue, void* stream) {
   using namespace fx;
   FX_CHECK_ARG(act && w && out, "fx_conv_gemm_bf16: null pointer");
   FX_CHECK_ARG(T > 0 && H > 0 && W > 0 && Cin > 0 && Cin % kBK == 0 && Cout > 0 && Cout % 8 == 0,
@@ -837,7 +846,12 @@ extern "C" int fx_conv_gemm_bf16(const void* act, const void* w, const void* bia
   FX_CHECK_ARG(epilogue == FX_EPI_BF16 || epilogue == FX_EPI_GELU_BF16 || epilogue == FX_EPI_F32 ||
                    epilogue == FX_EPI_F32_EXACT,
                "fx_conv_gemm_bf16: epilogue %d unsupported", epilogue);
+  FX_CHECK_ARG((stride_s == 1 || (stride_s == 2 && ks == 3 && H % 2 == 0 && W % 2 == 0)) &&
+                   (stride_t == 1 || (stride_t == 2 && kt == 3 && T % 2 == 0)),
+               "fx_conv_gemm_bf16: stride (%d, %d) needs a 3-tap kernel along it and even extents", stride_s, stride_t);
   ConvSpec c{};
+  c.stride_s = stride_s;
+  c.stride_t = stride_t;
   c.taps = kt * ks * ks;
   c.cin = Cin;
   c.H = H; c.W = W;

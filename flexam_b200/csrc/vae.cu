@@ -167,7 +167,79 @@ __global__ void vae_unpatchify_kernel(const __nv_bfloat16* y, long long ldy, __n
   }
 }
 
+// rows[(f*h + y)*w + x][c*4 + r*2 + q] = video[c][f][2y + q][2x + r]   (patchify :285-301); columns >= 12 untouched
+__global__ void vae_patchify_kernel(const __nv_bfloat16* video, __nv_bfloat16* rows, long long ldr, int T, int h, int w,
+                                    int Ttot, int f0) {
+  const long long total = 12LL * T * h * w;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total; i += stride) {
+    const int ch = static_cast<int>(i % 12);
+    const long long pix = i / 12;
+    const int x = static_cast<int>(pix % w);
+    const int y = static_cast<int>((pix / w) % h);
+    const int f = static_cast<int>(pix / (static_cast<long long>(w) * h));
+    const int c = ch >> 2, r = (ch >> 1) & 1, q = ch & 1;
+    rows[pix * ldr + ch] = video[((static_cast<long long>(c) * Ttot + f0 + f) * (2 * h) + 2 * y + q) * (2 * w) + 2 * x + r];
+  }
+}
+
+// main[to][yo][xo][co] += mean_g x'[co*group + g][to][yo][xo]   (AvgDown3D :340-372), where x' is x with its time axis
+// front-padded to a multiple of ft and (ft, fs, fs) blocks folded into channels: channel cf = c*factor + a*fs*fs + b*fs + d
+// reads x[c][to*ft + a - pad_t][yo*fs + b][xo*fs + d] (zero for padded frames). x: bf16 [T, H, W, Cin] channel-last.
+__global__ void vae_avgdown_add_kernel(__nv_bfloat16* main, const __nv_bfloat16* x, long long nout, int T, int H, int W,
+                                       int Cin, int Cout, int ft, int fs) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const int Ho = H / fs, Wo = W / fs, factor = ft * fs * fs;
+  const int group = Cin * factor / Cout;
+  const int pad_t = (ft - T % ft) % ft;
+  for (; i < nout; i += stride) {
+    const int co = static_cast<int>(i % Cout);
+    const long long pix = i / Cout;
+    const int xo = static_cast<int>(pix % Wo);
+    const int yo = static_cast<int>((pix / Wo) % Ho);
+    const int to = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+    float acc = 0.f;
+    for (int g = 0; g < group; ++g) {
+      const int cf = co * group + g;
+      const int c = cf / factor, rem = cf - c * factor;
+      const int a = rem / (fs * fs), b = (rem / fs) % fs, d = rem % fs;
+      const int tin = to * ft + a - pad_t;
+      if (tin >= 0)
+        acc += __bfloat162float(x[((static_cast<long long>(tin) * H + yo * fs + b) * W + xo * fs + d) * Cin + c]);
+    }
+    main[i] = __float2bfloat16_rn(__bfloat162float(main[i]) + __bfloat162float(__float2bfloat16_rn(acc / group)));
+  }
+}
+
 }  // namespace fx
+
+extern "C" int fx_vae_patchify(const void* video, void* rows, int64_t ldr, int T, int h, int w, int Ttot, int frame0,
+                               void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(video && rows && T > 0 && h > 0 && w > 0 && ldr >= 12 && frame0 >= 0 && frame0 + T <= Ttot,
+               "fx_vae_patchify: bad arguments");
+  vae_patchify_kernel<<<vae_grid(12LL * T * h * w), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(video), reinterpret_cast<__nv_bfloat16*>(rows), ldr, T, h, w, Ttot, frame0);
+  FX_CHECK_LAUNCH("fx_vae_patchify");
+  return FX_OK;
+}
+
+extern "C" int fx_vae_avgdown_add(void* main_io, const void* x, int T, int H, int W, int Cin, int Cout, int ft, int fs,
+                                  void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(main_io && x && T > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (ft == 1 || ft == 2) &&
+                   (fs == 1 || fs == 2) && H % fs == 0 && W % fs == 0 && (Cin * ft * fs * fs) % Cout == 0,
+               "fx_vae_avgdown_add: bad arguments");
+  const int To = (T + ft - 1) / ft;
+  const long long nout = static_cast<long long>(To) * (H / fs) * (W / fs) * Cout;
+  vae_avgdown_add_kernel<<<vae_grid(nout), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(main_io), reinterpret_cast<const __nv_bfloat16*>(x), nout, T, H, W, Cin, Cout, ft,
+      fs);
+  FX_CHECK_LAUNCH("fx_vae_avgdown_add");
+  return FX_OK;
+}
 
 extern "C" int fx_vae_norm_act(const void* x, int64_t ldx, const void* gamma, void* out, int64_t ldo, int64_t npix,
                                int C, int H, int W, int pad, int frame0, int silu, void* stream) {

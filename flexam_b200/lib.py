@@ -42,7 +42,7 @@ SIGNATURES = {
     "fx_groupnorm_silu": [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "fx_groupnorm_partials": [_vp, _i, _i64, _i, _i, _vp, _vp],
     "fx_groupnorm_silu_partials": [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _i, _i64, _vp, _vp],
-    "fx_conv_gemm_bf16": [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "fx_conv_gemm_bf16": [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "fx_nchw_to_nhwc_padded": [_vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
     "fx_cfg_euler_step": [_vp, _vp, _f, _f, _vp, _vp, _vp, _i64, _vp],
     "fx_swap01_bf16": [_vp, _i64, _vp, _i, _i, _i, _vp],
@@ -63,6 +63,8 @@ SIGNATURES = {
     "fx_vae_dupup_add": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "fx_softmax_rows_f32": [_vp, _i64, _vp, _i64, _i, _i, _f, _vp],
     "fx_vae_unpatchify": [_vp, _i64, _vp, _i, _i, _i, _i, _i, _vp],
+    "fx_vae_patchify": [_vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
+    "fx_vae_avgdown_add": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "fx_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "fx_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
     # fp32 verification mode (flexam_b200/precise.py)

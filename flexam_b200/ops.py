@@ -346,20 +346,20 @@ def groupnorm_partials(x: torch.Tensor, frames: int, groups: int, partials: torc
 
 
 def conv_gemm(act: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, T: int, H: int,
-              W: int, kt: int, ks: int, epilogue: int = FX_EPI_BF16) -> torch.Tensor:
+              W: int, kt: int, ks: int, epilogue: int = FX_EPI_BF16, stride_s: int = 1, stride_t: int = 1) -> torch.Tensor:
     """Implicit-GEMM convolution (see fx_conv_gemm_bf16). act: bf16 zero-padded channel-last [(T+kt-1)*Hp*Wp, Cin]
     contiguous; w: bf16 [Cout, kt*ks*ks*Cin]; out: dense [T*H*W, Cout] view (row stride free)."""
     _req(act, bf16, "conv_gemm.act"), _req(w, bf16, "conv_gemm.w")
     Cin, Cout = act.shape[1], w.shape[0]
     Hp, Wp = (H + 2, W + 2) if ks == 3 else (H, W)
     if not act.is_contiguous() or act.shape[0] != (T + kt - 1) * Hp * Wp or w.shape[1] != kt * ks * ks * Cin \
-            or not w.is_contiguous() or tuple(out.shape) != (T * H * W, Cout):
+            or not w.is_contiguous() or tuple(out.shape) != ((T // stride_t) * (H // stride_s) * (W // stride_s), Cout):
         raise _l.FlexamNativeError(f"conv_gemm: shape mismatch act{tuple(act.shape)} w{tuple(w.shape)} out{tuple(out.shape)}")
     _req(out, bf16 if epilogue in (FX_EPI_BF16, FX_EPI_GELU_BF16) else f32, "conv_gemm.out")
     if bias is not None:
         _req(bias, bf16, "conv_gemm.bias")
     st = _l.load().fx_conv_gemm_bf16(_p(act), _p(w), _p(bias), _p(out), out.stride(0), T, H, W, Cin, Cout, kt, ks,
-                                     epilogue, _stream())
+                                     stride_s, stride_t, epilogue, _stream())
     _l.check(st, "fx_conv_gemm_bf16")
     return out
 
@@ -642,3 +642,24 @@ def vae_unpatchify(y: torch.Tensor, video: torch.Tensor, T: int, H: int, W: int,
     st = _l.load().fx_vae_unpatchify(_p(y), y.stride(0), _p(video), T, H, W, video.shape[1], frame0, _stream())
     _l.check(st, "fx_vae_unpatchify")
     return video
+
+
+def vae_patchify(video: torch.Tensor, rows: torch.Tensor, T: int, h: int, w: int, frame0: int) -> torch.Tensor:
+    """video: bf16 [3, Ttot, 2h, 2w] contiguous; rows: bf16 [T*h*w, >=12] (columns [0, 12) written)."""
+    _req(video, bf16, "vae_patchify.video"), _req(rows, bf16, "vae_patchify.rows")
+    if not video.is_contiguous() or video.shape[0] != 3 or tuple(video.shape[2:]) != (2 * h, 2 * w) or rows.shape[0] != T * h * w:
+        raise _l.FlexamNativeError("vae_patchify: shape mismatch")
+    st = _l.load().fx_vae_patchify(_p(video), _p(rows), rows.stride(0), T, h, w, video.shape[1], frame0, _stream())
+    _l.check(st, "fx_vae_patchify")
+    return rows
+
+
+def vae_avgdown_add_(main: torch.Tensor, x: torch.Tensor, T: int, H: int, W: int, ft: int, fs: int) -> torch.Tensor:
+    """main: bf16 [ceil(T/ft)*(H/fs)*(W/fs), Cout] += AvgDown3D(x: bf16 [T*H*W, Cin]) (see fx_vae_avgdown_add)."""
+    _req(main, bf16, "vae_avgdown_add.main"), _req(x, bf16, "vae_avgdown_add.x")
+    To = -(-T // ft)
+    if not (main.is_contiguous() and x.is_contiguous()) or main.shape[0] != To * (H // fs) * (W // fs) or x.shape[0] != T * H * W:
+        raise _l.FlexamNativeError("vae_avgdown_add: shape mismatch")
+    st = _l.load().fx_vae_avgdown_add(_p(main), _p(x), T, H, W, x.shape[1], main.shape[1], ft, fs, _stream())
+    _l.check(st, "fx_vae_avgdown_add")
+    return main

@@ -1,4 +1,4 @@
-"""Wan2.2 VAE decoder on the native kernels (decode half).
+"""Wan2.2 VAE (decoder and encoder) on the native kernels.
 
 ``AutoencoderKLWan3_8`` mirrors the reference wrapper (FlexAM/models/wan_vae3_8.py:892-1057, cited as :line) for what the
 pipeline's last step calls — ``vae.decode(latents).sample`` — with the reference's parameter names for ``model.conv2.*``
@@ -7,7 +7,10 @@ per-convolution feature cache (:820-849), every convolution an implicit GEMM on 
 (``fx_conv_gemm_bf16``: causal 3x3x3, per-frame 3x3, (3,1,1) time convolution; 1x1 as plain GEMMs) reading zero-padded
 channel-last grids whose first two frames are the causal history, and the element-wise work between them (RMS_norm + SiLU,
 nearest 2x, temporal interleave, DupUp3D shortcut, residual adds, the attention block's softmax, unpatchify + clamp) as
-row kernels (csrc/vae.cu). ``encode`` is NOT built and raises. No torch compute, no CPU fallback.
+row kernels (csrc/vae.cu). ``encode`` (:788-819) is the mirror image: patchify, first frame alone then four frames per chunk
+through Encoder3d (:564-618) — the same residual / attention blocks, the stride-2 convolutions of ``Resample`` downsample2d /
+downsample3d as the stride forms of the implicit GEMM, AvgDown3D shortcuts — and ``conv1`` with the latent normalisation
+folded in. No torch compute, no CPU fallback.
 """
 from __future__ import annotations
 
@@ -71,15 +74,58 @@ def param_shapes(cfg: dict) -> Dict[str, tuple]:
     return out
 
 
+def encoder_dims(cfg: dict) -> List[int]:
+    return [cfg["enc_dim"] * u for u in [1] + list(cfg["dim_mult"])]          # :527
+
+
+def encoder_param_shapes(cfg: dict) -> Dict[str, tuple]:
+    """state_dict keys / shapes of ``encoder`` + ``conv1`` of AutoencoderKLWan2_2_ (:505-562, :771)."""
+    z, dims = cfg["z_dim"], encoder_dims(cfg)
+    t_dn = list(cfg["temperal_downsample"])
+    out: Dict[str, tuple] = {}
+
+    def conv(name, co, ci, k):
+        out[name + ".weight"] = (co, ci) + tuple(k)
+        out[name + ".bias"] = (co,)
+
+    def res(name, ci, co):
+        out[name + ".residual.0.gamma"] = (ci, 1, 1, 1)
+        conv(name + ".residual.2", co, ci, (3, 3, 3))
+        out[name + ".residual.3.gamma"] = (co, 1, 1, 1)
+        conv(name + ".residual.6", co, co, (3, 3, 3))
+        if ci != co:
+            conv(name + ".shortcut", co, ci, (1, 1, 1))
+
+    conv("encoder.conv1", dims[0], 12, (3, 3, 3))
+    n = len(cfg["dim_mult"])
+    for i, (ci, co) in enumerate(zip(dims[:-1], dims[1:])):
+        for j in range(cfg["num_res_blocks"]):
+            res(f"encoder.downsamples.{i}.downsamples.{j}", ci if j == 0 else co, co)
+        if i != n - 1:
+            j = cfg["num_res_blocks"]
+            conv(f"encoder.downsamples.{i}.downsamples.{j}.resample.1", co, co, (3, 3))
+            if i < len(t_dn) and t_dn[i]:
+                conv(f"encoder.downsamples.{i}.downsamples.{j}.time_conv", co, co, (3, 1, 1))
+    res("encoder.middle.0", dims[-1], dims[-1])
+    out["encoder.middle.1.norm.gamma"] = (dims[-1], 1, 1)
+    conv("encoder.middle.1.to_qkv", 3 * dims[-1], dims[-1], (1, 1))
+    conv("encoder.middle.1.proj", dims[-1], dims[-1], (1, 1))
+    res("encoder.middle.2", dims[-1], dims[-1])
+    out["encoder.head.0.gamma"] = (dims[-1], 1, 1, 1)
+    conv("encoder.head.2", 2 * z, dims[-1], (3, 3, 3))
+    conv("conv1", 2 * z, 2 * z, (1, 1, 1))
+    return out
+
+
 class VaeDecoderEngine:
-    """Packed weights, the per-convolution history grids and the launch sequence of one decode."""
+    """Packed weights, the per-convolution history grids and the launch sequences of decode and encode."""
 
     def __init__(self, params: Dict[str, torch.Tensor], cfg: dict, device: torch.device):
         self.cfg, self.device, self.params = dict(cfg), torch.device(device), params
         self.dims = decoder_dims(cfg)
-        for c in self.dims:
-            if c % 64 != 0:
-                raise FlexamNativeError(f"native VAE decoder: channel widths must be multiples of 64, got {self.dims}")
+        for c in self.dims + (encoder_dims(cfg) if "enc_dim" in cfg else []):
+            if c % 8 != 0:
+                raise FlexamNativeError(f"native VAE: channel widths must be multiples of 8, got {c}")
         self._ws: Dict[tuple, torch.Tensor] = {}
         self._hist: Dict[str, torch.Tensor] = {}
         self.launches = 0
@@ -99,7 +145,8 @@ class VaeDecoderEngine:
             name = k[:-7]
             co, ci = v.shape[:2]
             taps = int(math.prod(v.shape[2:]))
-            cip, cop = _pad64(ci), -(-co // 8) * 8
+            # k-blocks of the implicit GEMM are 64 channels of ONE tap: pad Cin; 1x1 convolutions are plain GEMMs (K = Cin)
+            cip, cop = (ci if taps == 1 else _pad64(ci)), -(-co // 8) * 8
             wt = torch.zeros((cop, taps, cip), dtype=bf16, device=dev)
             wt[:co, :, :ci] = v.reshape(co, ci, taps).permute(0, 2, 1)          # K order (dt, dy, dx, cin)
             self.w[name] = wt.view(cop, taps * cip).contiguous()
@@ -107,14 +154,18 @@ class VaeDecoderEngine:
             bias[:co] = P[name + ".bias"]
             self.b[name] = bias
         self.gamma = {k[:-6]: v.reshape(-1).contiguous() for k, v in P.items() if k.endswith(".gamma")}
-        # attention block: q|k and v as separate projections (v must be contiguous for the transpose)
-        C = self.dims[0]
-        wq = P["decoder.middle.1.to_qkv.weight"].reshape(3 * C, C)
-        bq = P["decoder.middle.1.to_qkv.bias"]
-        self.w_qk, self.b_qk = wq[:2 * C].contiguous(), bq[:2 * C].contiguous()
-        self.w_v, self.b_v = wq[2 * C:].contiguous(), bq[2 * C:].contiguous()
+        # attention blocks: q|k and v as separate projections (v must be contiguous for the transpose)
+        self.attn_w = {}
+        for k, v in P.items():
+            if k.endswith(".to_qkv.weight"):
+                name = k[:-len(".to_qkv.weight")]
+                C = v.shape[1]
+                wq, bq = v.reshape(3 * C, C), P[name + ".to_qkv.bias"]
+                self.attn_w[name] = (wq[:2 * C].contiguous(), bq[:2 * C].contiguous(), wq[2 * C:].contiguous(),
+                                     bq[2 * C:].contiguous())
         self._versions = tuple(p._version for p in P.values())
         self._scale_key = None
+        self._enc_scale_key = None
 
     def _fold_scale(self, scale: Sequence[torch.Tensor]):
         """conv2(z / scale[1] + scale[0]) (:824-831) as ONE projection of the raw latents: the per-channel affine is
@@ -160,7 +211,7 @@ class VaeDecoderEngine:
             t.zero_()
 
     # -- building blocks -------------------------------------------------------------------------------------------
-    def _cconv(self, name, x, T, H, W, gamma=None, silu=False, kt=3, ks=3):
+    def _cconv(self, name, x, T, H, W, gamma=None, silu=False, kt=3, ks=3, stride_s=1, stride_t=1, run=True):
         """[RMS_norm + SiLU ->] causal convolution ``name`` over the chunk x (dense [T*H*W, Cin]) with the two cached
         history frames in front (CausalConv3d :22-47 + the cache rule of its callers :219-238): returns dense
         [T*H*W, Cout]. The history grid then keeps the last two input frames for the next chunk."""
@@ -171,10 +222,12 @@ class VaeDecoderEngine:
         hist = kt - 1
         grid = self._grid(name, hist + T, Hp, Wp, cin, keep_rows=hist * Hp * Wp)
         ops.vae_norm_act(x, gamma, grid, H, W, pad, hist, silu)
-        out = self._buf("out:" + name, (T * H * W, w.shape[0]))
-        rows = (hist + T) * Hp * Wp
-        ops.conv_gemm(grid[:rows], w, self.b[name], out, T, H, W, kt, ks, FX_EPI_BF16)
-        self.launches += 2
+        out = None
+        if run:
+            out = self._buf("out:" + name, ((T // stride_t) * (H // stride_s) * (W // stride_s), w.shape[0]))
+            rows = (hist + T) * Hp * Wp
+            ops.conv_gemm(grid[:rows], w, self.b[name], out, T, H, W, kt, ks, FX_EPI_BF16, stride_s, stride_t)
+        self.launches += 2 if run else 1
         if hist:
             plane = Hp * Wp
             src = grid[T * plane:(T + hist) * plane]
@@ -207,8 +260,9 @@ class VaeDecoderEngine:
             ops.vae_norm_act(xf, self.gamma[name + ".norm"], y, H, W, 0, 0, False)
             qk = self._buf("attn_qk", (P, 2 * C))
             v = self._buf("attn_v", (P, C))
-            ops.gemm(y, self.w_qk, self.b_qk, qk, FX_EPI_BF16)
-            ops.gemm(y, self.w_v, self.b_v, v, FX_EPI_BF16)
+            w_qk, b_qk, w_v, b_v = self.attn_w[name]
+            ops.gemm(y, w_qk, b_qk, qk, FX_EPI_BF16)
+            ops.gemm(y, w_v, b_v, v, FX_EPI_BF16)
             s = self._buf("attn_s", (P, P), f32)
             ops.gemm(qk[:, :C], qk[:, C:], None, s, FX_EPI_F32_EXACT)
             p = self._buf("attn_p", (P, P))
@@ -303,12 +357,133 @@ class VaeDecoderEngine:
         return video.unsqueeze(0)
 
 
+    # -- encode ----------------------------------------------------------------------------------------------------
+    def _fold_enc_scale(self, scale: Sequence[torch.Tensor]):
+        """conv1 followed by (mu - mean) * (1 / std) on the first z_dim channels (:811-816) as ONE projection: the affine
+        is folded into conv1's weight rows and bias in fp32 once per (mean, 1/std) pair."""
+        key = (scale[0].data_ptr(), scale[1].data_ptr(), scale[0]._version, scale[1]._version)
+        if self._enc_scale_key == key:
+            return
+        zd = self.cfg["z_dim"]
+        w = self.params["conv1.weight"].reshape(2 * zd, 2 * zd).float().clone()
+        b = self.params["conv1.bias"].float().clone()
+        mean, inv_std = scale[0].to(self.device, f32), scale[1].to(self.device, f32)
+        w[:zd] *= inv_std.view(zd, 1)
+        b[:zd] = (b[:zd] - mean) * inv_std
+        self.w_conv1, self.b_conv1 = w.to(bf16).contiguous(), b.to(bf16).contiguous()
+        self._enc_scale_key = key
+        self._enc_scale_ref = (scale[0], scale[1])
+
+    def _downsample(self, name, x, T, H, W, temporal, first):
+        """Resample downsample2d / downsample3d (:117-160): ZeroPad2d((0,1,0,1)) + 3x3 stride-2 convolution per frame,
+        then (3,1,1) stride-(2,1,1) convolution over [last cached frame | chunk] (the first chunk only seeds the cache)."""
+        C = x.shape[1]
+        grid = self._grid(name + ".resample.1", T, H + 2, W + 2, _pad64(C))
+        rows = T * (H + 2) * (W + 2)
+        ops.vae_norm_act(x, None, grid, H, W, 1, 0, False)
+        w = self.w[name + ".resample.1"]
+        out = self._buf("out:" + name, (T * (H // 2) * (W // 2), w.shape[0]))
+        ops.conv_gemm(grid[:rows], w, self.b[name + ".resample.1"], out, T, H, W, 1, 3, FX_EPI_BF16, 2, 1)
+        self.launches += 2
+        H, W = H // 2, W // 2
+        if temporal:
+            if first:
+                self._cconv(name + ".time_conv", out, T, H, W, None, False, kt=3, ks=1, run=False)     # :147-149
+            else:
+                out = self._cconv(name + ".time_conv", out, T, H, W, None, False, kt=3, ks=1, stride_t=2)
+                T //= 2
+        return out, T, H, W
+
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor, scale: Sequence[torch.Tensor]) -> torch.Tensor:
+        """x: [1, 3, T, H, W] pixels in [-1, 1] (T = 1 + 4k, H and W multiples of 16) -> bf16 [1, 2 z_dim, 1 + k, H/16,
+        W/16]: normalised mean | log-variance (:788-819)."""
+        if "enc_dim" not in self.cfg or "encoder.conv1.weight" not in self.params:
+            raise FlexamNativeError("this VAE engine was built without encoder parameters")
+        if tuple(p._version for p in self.params.values()) != self._versions:
+            self._pack()
+        cfg, dev = self.cfg, self.device
+        zd = cfg["z_dim"]
+        n = len(cfg["dim_mult"])
+        if x.dim() != 5 or x.shape[0] != 1 or x.shape[1] != 3 or (x.shape[2] - 1) % 4 != 0 or \
+                x.shape[3] % (2 ** n) != 0 or x.shape[4] % (2 ** n) != 0:
+            raise FlexamNativeError(f"VAE encode: expected video [1, 3, 1+4k, 16a, 16b], got {tuple(x.shape)}")
+        self._fold_enc_scale(scale)
+        self._reset_history()
+        self.launches = 0
+        _, _, T, H, W = x.shape
+        dims = encoder_dims(cfg)
+        t_dn = list(cfg["temperal_downsample"])
+        nres = cfg["num_res_blocks"]
+        vid = x[0].to(dev, bf16).contiguous()
+        h0, w0 = H // 2, W // 2
+        chunks = 1 + (T - 1) // 4
+        hl, wl = H // (2 ** n), W // (2 ** n)
+        lat = self._buf("enc_lat", (chunks * hl * wl, 2 * zd))
+        for i in range(chunks):                                                  # :795-810
+            first = i == 0
+            f0, Tc = (0, 1) if first else (1 + 4 * (i - 1), 4)
+            h, w = h0, w0
+            rows = self._buf("enc_rows", (Tc * h * w, 64), zero=True)            # 12 patch channels, zero-padded to 64
+            ops.vae_patchify(vid, rows, Tc, h, w, f0)
+            self.launches += 1
+            y = self._cconv("encoder.conv1", rows, Tc, h, w)
+            for s in range(n):                                                   # Down_ResidualBlock :452-457
+                name = f"encoder.downsamples.{s}.downsamples."
+                down = s != n - 1
+                temporal = down and s < len(t_dn) and bool(t_dn[s])
+                y_in, T_in, h_in, w_in = y, Tc, h, w
+                for j in range(nres):
+                    y = self._res(name + str(j), y, Tc, h, w)
+                if down:
+                    y, Tc, h, w = self._downsample(name + str(nres), y, Tc, h, w, temporal, first)
+                ops.vae_avgdown_add_(y, y_in.contiguous(), T_in, h_in, w_in, 2 if temporal else 1, 2 if down else 1)
+                self.launches += 1
+            y = self._res("encoder.middle.0", y, Tc, h, w)
+            y = self._attn("encoder.middle.1", y, Tc, h, w)
+            y = self._res("encoder.middle.2", y, Tc, h, w)
+            y = self._cconv("encoder.head.2", y, Tc, h, w, self.gamma["encoder.head.0"], True)
+            if Tc != 1 or (h, w) != (hl, wl):
+                raise FlexamNativeError(f"internal: encoder chunk ended at {Tc} x {h} x {w}")
+            lat[i * hl * wl:(i + 1) * hl * wl].copy_(y[:, :2 * zd])
+        out_rows = self._buf("enc_out_rows", (chunks * hl * wl, 2 * zd))
+        ops.gemm(lat, self.w_conv1, self.b_conv1, out_rows, FX_EPI_BF16)         # conv1 + latent normalisation :811-816
+        out = torch.empty((2 * zd, chunks * hl * wl), dtype=bf16, device=dev)
+        ops.nchw_to_nhwc(out_rows, out, 0)                                       # [P, 2z] -> [2z, P] (channel-first)
+        self.launches += 2
+        return out.view(1, 2 * zd, chunks, hl, wl)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # nn.Module with the reference wrapper's surface
 # ----------------------------------------------------------------------------------------------------------
 class DecoderOutput:
     def __init__(self, sample):
         self.sample = sample
+
+
+class AutoencoderKLOutput:
+    def __init__(self, latent_dist):
+        self.latent_dist = latent_dist
+
+
+class DiagonalGaussianDistribution:
+    """The part of diffusers' class the FlexAM pipeline uses on ``vae.encode(x)[0]`` (``.mode()`` / ``.sample()``):
+    parameters = mean | log-variance along dim 1, log-variance clamped to [-30, 20]."""
+
+    def __init__(self, parameters: torch.Tensor):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
+
+    def sample(self, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + self.std * noise
 
 
 def _set_param(root: nn.Module, dotted: str, p: nn.Parameter):
@@ -325,18 +500,18 @@ def _set_param(root: nn.Module, dotted: str, p: nn.Parameter):
 
 class AutoencoderKLWan3_8(nn.Module):
     """Drop-in for the DECODE side of FlexAM.models.AutoencoderKLWan3_8 (:892-1057): ``decode(z).sample``. Parameters
-    carry the reference's names under ``model.`` (``model.conv2.*``, ``model.decoder.*``); a full checkpoint loads with
-    ``strict=False`` (the encoder half is not built: ``encode`` raises)."""
+    carry the reference's names under ``model.`` (``model.encoder.*``, ``model.conv1.*``, ``model.conv2.*``,
+    ``model.decoder.*``): the reference checkpoint loads strictly. ``encode(x).latent_dist`` / ``decode(z).sample``."""
 
     def __init__(self, latent_channels=48, c_dim=160, vae_pth=None, dim_mult=(1, 2, 4, 4),
                  temperal_downsample=(False, True, True), temporal_compression_ratio=4, spatial_compression_ratio=8,
                  dec_dim=256, latents_mean=None, latents_std=None, dtype=torch.bfloat16, device=None):
         super().__init__()
-        self.cfg = dict(z_dim=latent_channels, dec_dim=dec_dim, dim_mult=list(dim_mult), num_res_blocks=2,
+        self.cfg = dict(z_dim=latent_channels, dec_dim=dec_dim, enc_dim=c_dim, dim_mult=list(dim_mult), num_res_blocks=2,
                         temperal_downsample=list(temperal_downsample))
         self.temporal_compression_ratio = temporal_compression_ratio
         self.spatial_compression_ratio = spatial_compression_ratio
-        for name, shape in param_shapes(self.cfg).items():
+        for name, shape in {**encoder_param_shapes(self.cfg), **param_shapes(self.cfg)}.items():
             _set_param(self, "model." + name, nn.Parameter(torch.empty(shape, dtype=dtype, device=device),
                                                            requires_grad=False))
         mean = torch.zeros(latent_channels) if latents_mean is None else torch.as_tensor(latents_mean, dtype=f32)
@@ -369,8 +544,14 @@ class AutoencoderKLWan3_8(nn.Module):
         decoded = self._decode(z).sample
         return DecoderOutput(decoded) if return_dict else (decoded,)
 
-    def encode(self, x, return_dict: bool = True):
-        raise FlexamNativeError("the VAE encoder half (wan_vae3_8.py:788-819) is not built on the native path")
+    def _encode(self, x: torch.Tensor) -> torch.Tensor:                         # :1021-1028
+        eng = self.engine()
+        with (torch.cuda.device(eng.device) if eng.device.type == "cuda" else _null()), ops.stream_scope():
+            return torch.stack([eng.encode(u.unsqueeze(0), self.scale)[0].clone() for u in x])
+
+    def encode(self, x: torch.Tensor, return_dict: bool = True):                # :1030-1039
+        posterior = DiagonalGaussianDistribution(self._encode(x))
+        return AutoencoderKLOutput(posterior) if return_dict else (posterior,)
 
 
 class _null:

@@ -179,9 +179,12 @@ int fx_groupnorm_silu_partials(const void* x, int64_t P, int C, int G, float eps
  * Tap (dt, dy, dx) reads the activation matrix shifted by dt*Hp*Wp + (dy-1)*Wp + (dx-1) rows: one TMA coordinate change
  * per tap; positions of the padded grid that are halo are computed and dropped.
  * fx_nchw_to_nhwc_padded: fx_nchw_to_nhwc into that padded layout (interior positions only: the halo stays as the caller
- * zeroed it). fx_groupnorm_silu_partials with pad_H > 0 writes y_bf16 into the padded layout [.., pad_H+2, pad_W+2, ld_bf16]. */
+ * zeroed it). fx_groupnorm_silu_partials with pad_H > 0 writes y_bf16 into the padded layout [.., pad_H+2, pad_W+2, ld_bf16].
+ * stride_s = 2 (ks == 3): nn.ZeroPad2d((0,1,0,1)) + Conv2d(3, stride 2) of the VAE encoder (wan_vae3_8.py:101-107): out is
+ * [T*(H/2)*(W/2), ldo]; stride_t = 2 (kt == 3): Conv3d((3,1,1), stride (2,1,1)) over [last cached frame | chunk]
+ * (:108-109, :150-153): out is [(T/2)*H*W, ldo]. */
 int fx_conv_gemm_bf16(const void* act, const void* w, const void* bias, void* out, int64_t ldo, int T, int H, int W,
-                      int Cin, int Cout, int kt, int ks, int epilogue, void* stream);
+                      int Cin, int Cout, int kt, int ks, int stride_s, int stride_t, int epilogue, void* stream);
 int fx_nchw_to_nhwc_padded(const void* src, void* dst, int64_t ldd, int c0, int C, int F, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -318,6 +321,14 @@ int fx_vae_dupup_add(void* main_io, const void* x, int Tout, int H, int W, int C
                      void* stream);
 int fx_softmax_rows_f32(const float* s, int64_t lds, void* p, int64_t ldp, int rows, int cols, float scale, void* stream);
 int fx_vae_unpatchify(const void* y, int64_t ldy, void* video, int T, int H, int W, int Ttot, int frame0, void* stream);
+/* Encoder half (:788-819, Encoder3d :505-618, Down_ResidualBlock :420-457):
+ *   fx_vae_patchify     rows[(f*h+y)*w+x][c*4+r*2+q] = video bf16 [3, Ttot, 2h, 2w][c][frame0+f][2y+q][2x+r]     (:285-301)
+ *   fx_vae_avgdown_add  main += AvgDown3D(x): (ft, fs, fs) blocks folded into channels, time front-padded to a multiple of
+ *                       ft, mean over groups of Cin*ft*fs*fs/Cout channels; x bf16 [T,H,W,Cin], main bf16
+ *                       [ceil(T/ft), H/fs, W/fs, Cout]                                                     (:340-372, :457)
+ * The stride-2 convolutions of Resample downsample2d / downsample3d are fx_conv_gemm_bf16 with stride_s / stride_t = 2. */
+int fx_vae_patchify(const void* video, void* rows, int64_t ldr, int T, int h, int w, int Ttot, int frame0, void* stream);
+int fx_vae_avgdown_add(void* main_io, const void* x, int T, int H, int W, int Cin, int Cout, int ft, int fs, void* stream);
 
 /* Small utility kernels used by the host glue. */
 int fx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);

@@ -178,18 +178,22 @@ def run_vae(name: str):
     cfg = V.VAE_CONFIGS[cfg_name]
     t0 = time.time()
     model = ref_import.build_reference_vae(cfg).eval()
-    sd = {k: torch.from_numpy(v) for k, v in V.state_dict(cfg).items()}
-    missing = model.load_state_dict(sd, strict=False)
-    assert not missing.unexpected_keys and all(k.startswith(("encoder", "conv1")) for k in missing.missing_keys)
+    sd = {k: torch.from_numpy(v) for k, v in {**V.encoder_state_dict(cfg), **V.state_dict(cfg)}.items()}
+    model.load_state_dict(sd, strict=True)
     z, scale = torch.from_numpy(V.latents(cfg, T, H, W)), V.latent_scale(cfg)
+    x = torch.from_numpy(V.video(cfg, 1 + 4 * (T - 1), 16 * H, 16 * W))
     with torch.no_grad():
         ref = model.decode(z, scale).clamp_(-1, 1)
         mine = V.decode(sd, cfg, z, scale)
-    rel = ((ref - mine).norm() / ref.norm()).item()
-    print(f"{name}: reference out {tuple(ref.shape)} mean |x| {ref.abs().mean():.3f}  oracle rel-L2 {rel:.2e}  ({time.time() - t0:.1f}s)")
-    assert rel < 2e-5, "VAE decoder oracle disagrees with the reference"
+        ref_e = model.encode(x, scale)
+        mine_e = V.encode(sd, cfg, x, scale)
+    rel, rel_e = ((ref - mine).norm() / ref.norm()).item(), ((ref_e - mine_e).norm() / ref_e.norm()).item()
+    print(f"{name}: reference decode {tuple(ref.shape)} oracle rel-L2 {rel:.2e}; encode {tuple(ref_e.shape)} oracle rel-L2 "
+          f"{rel_e:.2e}  ({time.time() - t0:.1f}s)")
+    assert rel < 2e-5 and rel_e < 2e-5, "VAE oracle disagrees with the reference"
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), out=ref.numpy().astype(np.float32),
-                        meta=np.array([T, H, W], dtype=np.int64), config=np.array(cfg_name))
+                        enc=ref_e.numpy().astype(np.float32), meta=np.array([T, H, W], dtype=np.int64),
+                        config=np.array(cfg_name))
 
 
 def run_rope(name: str = "rope_tables"):

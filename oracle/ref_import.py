@@ -131,7 +131,7 @@ def build_reference_t5(cfg: dict):
 
 def build_reference_vae(cfg: dict):
     """The REAL Wan2.2 VAE core (FlexAM/models/wan_vae3_8.py:739-870, AutoencoderKLWan2_2_) with the decoder width of
-    ``cfg`` (the encoder is built at a small width: only decode() is exercised)."""
+    ``cfg`` and the encoder width ``cfg["enc_dim"]``."""
     import_reference()
     import torch
 
@@ -144,6 +144,7 @@ def build_reference_vae(cfg: dict):
     _mod("diffusers.utils.accelerate_utils", apply_forward_hook=lambda f: f)
     name = "FlexAM.models.wan_vae3_8"
     mod = sys.modules.get(name) or _load(name, os.path.join(REF_ROOT, "FlexAM", "models", "wan_vae3_8.py"))
-    return mod.AutoencoderKLWan2_2_(dim=16, dec_dim=cfg["dec_dim"], z_dim=cfg["z_dim"], dim_mult=list(cfg["dim_mult"]),
+    return mod.AutoencoderKLWan2_2_(dim=cfg.get("enc_dim", 16), dec_dim=cfg["dec_dim"], z_dim=cfg["z_dim"],
+                                    dim_mult=list(cfg["dim_mult"]),
                                     num_res_blocks=cfg["num_res_blocks"],
                                     temperal_downsample=list(cfg["temperal_downsample"]))

@@ -103,9 +103,11 @@ def latent_scale(cfg: dict):
 
 VAE_CONFIGS = {
     # Wan2.2 VAE as AutoencoderKLWan3_8 builds it (:1009-1017): z 48, decoder width 256, 4 x 16 x 16 compression
-    "real": dict(z_dim=48, dec_dim=256, dim_mult=[1, 2, 4, 4], num_res_blocks=2, temperal_downsample=[False, True, True]),
+    "real": dict(z_dim=48, dec_dim=256, enc_dim=160, dim_mult=[1, 2, 4, 4], num_res_blocks=2,
+                 temperal_downsample=[False, True, True]),
     # same topology, decoder width 64 (channels 256/256/256/128/64: still multiples of 64): CPU-runnable in seconds
-    "tiny": dict(z_dim=48, dec_dim=64, dim_mult=[1, 2, 4, 4], num_res_blocks=2, temperal_downsample=[False, True, True]),
+    "tiny": dict(z_dim=48, dec_dim=64, enc_dim=32, dim_mult=[1, 2, 4, 4], num_res_blocks=2,
+                 temperal_downsample=[False, True, True]),
 }
 
 
@@ -183,6 +185,28 @@ class _Run:
         return u.reshape(b, t, c, 2 * h, 2 * w).permute(0, 2, 1, 3, 4)
 
 
+def _run_downsample(self, name, x, temporal):                   # Resample downsample2d / downsample3d :117-160
+    b, c, t, h, w = x.shape
+    u = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+    u = F.pad(u, (0, 1, 0, 1))                                  # ZeroPad2d((0, 1, 0, 1)) :101-107
+    u = _r(F.conv2d(u, self.sd[name + ".resample.1.weight"], self.sd[name + ".resample.1.bias"], stride=2), self.policy)
+    x = u.reshape(b, t, c, h // 2, w // 2).permute(0, 2, 1, 3, 4)
+    if temporal:
+        key = name + ".time_conv"
+        prev = self.cache.get(key)
+        if prev is None:
+            self.cache[key] = x.clone()                        # first chunk: kept as history, no temporal stride :147-149
+        else:
+            cache_x = x[:, :, -1:].clone()
+            xin = torch.cat([prev[:, :, -1:], x], dim=2)
+            x = _r(F.conv3d(xin, self.sd[key + ".weight"], self.sd[key + ".bias"], stride=(2, 1, 1)), self.policy)
+            self.cache[key] = cache_x
+    return x
+
+
+_Run.downsample = _run_downsample
+
+
 def dup_up3d(x, out_ch, factor_t, factor_s, first_chunk):      # DupUp3D :395-417
     factor = factor_t * factor_s * factor_s
     rep = out_ch * factor // x.shape[1]
@@ -191,6 +215,120 @@ def dup_up3d(x, out_ch, factor_t, factor_s, first_chunk):      # DupUp3D :395-41
     x = x.permute(0, 1, 5, 2, 6, 3, 7, 4).contiguous()
     x = x.view(x.size(0), out_ch, x.size(2) * factor_t, x.size(4) * factor_s, x.size(6) * factor_s)
     return x[:, :, factor_t - 1:] if first_chunk else x
+
+
+def avg_down3d(x, out_ch, factor_t, factor_s):                  # AvgDown3D :340-372
+    pad_t = (factor_t - x.shape[2] % factor_t) % factor_t
+    x = F.pad(x, (0, 0, 0, 0, pad_t, 0))
+    B, C, T, H, W = x.shape
+    factor = factor_t * factor_s * factor_s
+    x = x.view(B, C, T // factor_t, factor_t, H // factor_s, factor_s, W // factor_s, factor_s)
+    x = x.permute(0, 1, 3, 5, 7, 2, 4, 6).contiguous()
+    x = x.view(B, C * factor, T // factor_t, H // factor_s, W // factor_s)
+    x = x.view(B, out_ch, C * factor // out_ch, T // factor_t, H // factor_s, W // factor_s)
+    return x.mean(dim=2)
+
+
+def encoder_dims(cfg: dict) -> List[int]:
+    return [cfg["enc_dim"] * u for u in [1] + list(cfg["dim_mult"])]      # :527
+
+
+def encoder_param_specs(cfg: dict):
+    """[(key, shape, std, mean)] of the encoder half of AutoencoderKLWan2_2_ (encoder + conv1, :505-562, :771)."""
+    z, dims = cfg["z_dim"], encoder_dims(cfg)
+    t_dn = list(cfg["temperal_downsample"])
+    specs = []
+
+    def conv(name, co, ci, k):
+        fan = ci * math.prod(k)
+        specs.append((name + ".weight", (co, ci) + tuple(k), fan ** -0.5, 0.0))
+        specs.append((name + ".bias", (co,), 0.02, 0.0))
+
+    def res(name, ci, co):
+        specs.append((name + ".residual.0.gamma", (ci, 1, 1, 1), 0.1, 1.0))
+        conv(name + ".residual.2", co, ci, (3, 3, 3))
+        specs.append((name + ".residual.3.gamma", (co, 1, 1, 1), 0.1, 1.0))
+        conv(name + ".residual.6", co, co, (3, 3, 3))
+        if ci != co:
+            conv(name + ".shortcut", co, ci, (1, 1, 1))
+
+    conv("encoder.conv1", dims[0], 12, (3, 3, 3))
+    n = len(cfg["dim_mult"])
+    for i, (ci, co) in enumerate(zip(dims[:-1], dims[1:])):
+        for j in range(cfg["num_res_blocks"]):
+            res(f"encoder.downsamples.{i}.downsamples.{j}", ci if j == 0 else co, co)
+        if i != n - 1:
+            j = cfg["num_res_blocks"]
+            conv(f"encoder.downsamples.{i}.downsamples.{j}.resample.1", co, co, (3, 3))
+            if i < len(t_dn) and t_dn[i]:
+                conv(f"encoder.downsamples.{i}.downsamples.{j}.time_conv", co, co, (3, 1, 1))
+    res("encoder.middle.0", dims[-1], dims[-1])
+    specs.append(("encoder.middle.1.norm.gamma", (dims[-1], 1, 1), 0.1, 1.0))
+    conv("encoder.middle.1.to_qkv", 3 * dims[-1], dims[-1], (1, 1))
+    conv("encoder.middle.1.proj", dims[-1], dims[-1], (1, 1))
+    res("encoder.middle.2", dims[-1], dims[-1])
+    specs.append(("encoder.head.0.gamma", (dims[-1], 1, 1, 1), 0.1, 1.0))
+    conv("encoder.head.2", 2 * z, dims[-1], (3, 3, 3))
+    conv("conv1", 2 * z, 2 * z, (1, 1, 1))
+    return specs
+
+
+def encoder_state_dict(cfg: dict, tag: str = "vae"):
+    from oracle import synth
+    return {name: synth.tensor(f"{tag}/{name}", shape, std, mean) for name, shape, std, mean in encoder_param_specs(cfg)}
+
+
+def encoder_state_dict_torch(cfg: dict, device, dtype=None, tag: str = "vae"):
+    from oracle import synth
+    return {name: synth.tensor_torch(f"{tag}/{name}", shape, std, mean, device=device, dtype=dtype)
+            for name, shape, std, mean in encoder_param_specs(cfg)}
+
+
+def video(cfg: dict, T: int, H: int, W: int, tag: str = "vaex"):
+    """Synthetic pixel video [1, 3, T, H, W] in [-1, 1]."""
+    from oracle import synth
+    return np_clip(synth.tensor(f"{tag}/video", (1, 3, T, H, W), 0.5))
+
+
+def np_clip(a):
+    import numpy as np
+    return np.clip(a, -1.0, 1.0)
+
+
+def encode(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, scale, policy: str = "fp32") -> torch.Tensor:
+    """AutoencoderKLWan2_2_.encode (:788-819): x [1, 3, T, H, W] (T = 1 + 4k) -> [1, 2*z_dim, 1 + k, H/16, W/16] =
+    normalised mean | log-variance. Patchify, first frame alone then 4 frames per chunk through the encoder with its
+    feature cache, conv1, (mu - mean) * (1 / std)."""
+    run = _Run(sd, policy)
+    dims = encoder_dims(cfg)
+    t_dn = list(cfg["temperal_downsample"])
+    n = len(cfg["dim_mult"])
+    zd = cfg["z_dim"]
+    b, c, f, h, w = x.shape                                                                # patchify :285-301
+    x = x.view(b, c, f, h // 2, 2, w // 2, 2).permute(0, 1, 6, 4, 2, 3, 5).reshape(b, c * 4, f, h // 2, w // 2)
+    outs = []
+    for i in range(1 + (f - 1) // 4):                                                       # :795-810
+        xc = x[:, :, :1] if i == 0 else x[:, :, 1 + 4 * (i - 1):1 + 4 * i]
+        y = run.cconv("encoder.conv1", xc)
+        for s in range(n):                                                                  # Down_ResidualBlock :452-457
+            name = f"encoder.downsamples.{s}.downsamples."
+            down = s != n - 1
+            temporal = down and s < len(t_dn) and bool(t_dn[s])
+            y_in = y
+            for j in range(cfg["num_res_blocks"]):
+                y = run.res(name + str(j), y)
+            if down:
+                y = run.downsample(name + str(cfg["num_res_blocks"]), y, temporal)
+            y = _r(y + avg_down3d(y_in, dims[s + 1], 2 if temporal else 1, 2 if down else 1), policy)
+        y = run.res("encoder.middle.0", y)
+        y = run.attn("encoder.middle.1", y)
+        y = run.res("encoder.middle.2", y)
+        y = _r(F.silu(run.rms("encoder.head.0", y)), policy)
+        outs.append(run.cconv("encoder.head.2", y))
+    out = run.cconv("conv1", torch.cat(outs, dim=2), cached=False)                          # :811
+    mu, log_var = out.chunk(2, dim=1)
+    mu = _r((mu - scale[0].view(1, zd, 1, 1, 1).to(mu)) * scale[1].view(1, zd, 1, 1, 1).to(mu), policy)   # :812-816
+    return torch.cat([mu, log_var], dim=1)
 
 
 def decode(sd: Dict[str, torch.Tensor], cfg: dict, z: torch.Tensor, scale, policy: str = "fp32") -> torch.Tensor:

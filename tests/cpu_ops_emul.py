@@ -186,12 +186,17 @@ def _padded_rows(P, H, W):
     return (f * (H + 2) + r // W + 1) * (W + 2) + r % W + 1
 
 
-def conv_gemm(act, w, bias, out, T, H, W, kt, ks, epilogue=0):
+def conv_gemm(act, w, bias, out, T, H, W, kt, ks, epilogue=0, stride_s=1, stride_t=1):
     Cin, Cout = act.shape[1], w.shape[0]
     Hp, Wp = (H + 2, W + 2) if ks == 3 else (H, W)
     x = act.double().view(T + kt - 1, Hp, Wp, Cin).permute(3, 0, 1, 2)[None]
     wt = w.double().view(Cout, kt, ks, ks, Cin).permute(0, 4, 1, 2, 3)
-    y = F.conv3d(x, wt)[0].permute(1, 2, 3, 0).reshape(T * H * W, Cout)
+    y = F.conv3d(x, wt)[0].permute(1, 2, 3, 0)                       # [T, H, W, Cout] at every position
+    if stride_s == 2:
+        y = y[:, 1::2, 1::2]
+    if stride_t == 2:
+        y = y[1::2]
+    y = y.reshape(-1, Cout)
     if bias is not None:
         y = y + bias.double()
     if epilogue == 4:
@@ -476,7 +481,26 @@ def vae_unpatchify(y, video, T, H, W, frame0):
     return video
 
 
-NAMES = ("vae_norm_act", "vae_upsample2x", "vae_time_interleave", "vae_dupup_add_", "softmax_rows", "vae_unpatchify",
+def vae_patchify(video, rows, T, h, w, frame0):
+    v = video[:, frame0:frame0 + T].float().view(3, T, h, 2, w, 2)                  # c f y q x r
+    rows[:, :12] = v.permute(1, 2, 4, 0, 5, 3).reshape(T * h * w, 12).to(bf16)       # f y x (c r q)
+    return rows
+
+
+def vae_avgdown_add_(main, x, T, H, W, ft, fs):
+    Cin, Cout = x.shape[1], main.shape[1]
+    v = x.float().view(T, H, W, Cin).permute(3, 0, 1, 2)[None]
+    pad_t = (ft - T % ft) % ft
+    v = F.pad(v, (0, 0, 0, 0, pad_t, 0))
+    B, C, Tp, _, _ = v.shape
+    factor = ft * fs * fs
+    v = v.view(B, C, Tp // ft, ft, H // fs, fs, W // fs, fs).permute(0, 1, 3, 5, 7, 2, 4, 6).contiguous()
+    v = v.view(B, Cout, C * factor // Cout, Tp // ft, H // fs, W // fs).mean(dim=2)
+    v = v[0].permute(1, 2, 3, 0).reshape(-1, Cout)
+    return main.copy_((main.float() + _rb(v)).to(bf16))
+
+
+NAMES = ("vae_patchify", "vae_avgdown_add_", "vae_norm_act", "vae_upsample2x", "vae_time_interleave", "vae_dupup_add_", "softmax_rows", "vae_unpatchify",
          "conv_gemm", "nchw_to_nhwc_padded", "embedding", "t5_layernorm", "t5_attention", "add_bf16_", "gated_gelu", "groupnorm_partials", "groupnorm_silu_partials", "linear_f32_tc", "dedup_f32", "fingerprint_table", "fingerprint", "gemm", "ln_modulate", "modulation_tables", "ln_scale_shift", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
                  "linear_f32", "nchw_to_nhwc", "im2col3x3", "groupnorm_silu", "swap01", "cfg_euler_step", "add_", "sub", "split3", "join3",
                  "ln_f32", "rmsnorm_rope_f32", "gelu_f32_", "gated_residual_f32_", "attention_f32",

@@ -158,6 +158,19 @@ def test_conv_as_implicit_gemm(dev, T, H, W, Cin, Cout, kt, ks):
     want = torch.nn.functional.conv3d(xin, w.float().permute(0, 4, 1, 2, 3), b.float(), padding=(0, ks // 2, ks // 2))
     want = want[0].permute(1, 2, 3, 0).reshape(T * H * W, Cout)
     assert torch.isfinite(out.float()).all() and _rel(out, want) < 3e-3
+    # stride forms (the VAE encoder's downsample): ZeroPad2d((0,1,0,1)) + 3x3 stride 2; (3,1,1) kernel with time stride 2
+    if ks == 3 and kt == 1 and H % 2 == 0 and W % 2 == 0:
+        out2 = torch.full((T * (H // 2) * (W // 2), Cout), float("nan"), device=dev, dtype=torch.bfloat16)
+        ops.conv_gemm(act.view(-1, Cin), w.view(Cout, -1), b, out2, T, H, W, 1, 3, ops.FX_EPI_BF16, 2, 1)
+        x2 = torch.nn.functional.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1))              # [T, Cin, H+1, W+1]
+        want2 = torch.nn.functional.conv2d(x2, w.float()[:, 0].permute(0, 3, 1, 2), b.float(), stride=2)
+        assert _rel(out2, want2.permute(0, 2, 3, 1).reshape(-1, Cout)) < 3e-3
+    if ks == 1 and kt == 3 and T % 2 == 0:
+        out3 = torch.full(((T // 2) * H * W, Cout), float("nan"), device=dev, dtype=torch.bfloat16)
+        ops.conv_gemm(act.view(-1, Cin), w.view(Cout, -1), b, out3, T, H, W, 3, 1, ops.FX_EPI_BF16, 1, 2)
+        xin3 = x.float().permute(3, 0, 1, 2)[None][:, :, 1:]                                    # [last cached frame | chunk]
+        want3 = torch.nn.functional.conv3d(xin3, w.float().permute(0, 4, 1, 2, 3), b.float(), stride=(2, 1, 1))
+        assert _rel(out3, want3[0].permute(1, 2, 3, 0).reshape(-1, Cout)) < 3e-3
     # the padded-layout writers put data where the convolution looks for it
     if ks == 3 and kt == 1:
         src = torch.randn(Cin, T * H * W, device=dev, generator=g).bfloat16()
@@ -835,6 +848,20 @@ def test_vae_operators(dev):
         xc = x.float().view(T, H, W, C).permute(3, 0, 1, 2)[None]
         sh = V.dup_up3d(xc, cout, ft, 2, first)[0].permute(1, 2, 3, 0).reshape(-1, cout)
         assert torch.equal(main, (keep.float() + sh).bfloat16())
+    vid = torch.randn(3, T + 2, 2 * H, 2 * W, device=dev, generator=g).bfloat16()
+    prow = torch.zeros(T * H * W, 64, device=dev, dtype=torch.bfloat16)
+    ops.vae_patchify(vid, prow, T, H, W, 2)
+    ref_p = vid[:, 2:].view(3, T, H, 2, W, 2).permute(1, 2, 4, 0, 5, 3).reshape(T * H * W, 12)
+    assert torch.equal(prow[:, :12], ref_p) and prow[:, 12:].abs().max().item() == 0
+    for ft, fs, cout, Tin in ((2, 2, 512, 4), (2, 2, 512, 1), (1, 2, 256, 3), (1, 1, 256, 3)):
+        xa = torch.randn(Tin * H * W, C, device=dev, generator=g).bfloat16()
+        To = -(-Tin // ft)
+        main = torch.randn(To * (H // fs) * (W // fs), cout, device=dev, generator=g).bfloat16()
+        keep = main.clone()
+        ops.vae_avgdown_add_(main, xa, Tin, H, W, ft, fs)
+        sh = V.avg_down3d(xa.float().view(Tin, H, W, C).permute(3, 0, 1, 2)[None], cout, ft, fs)[0]
+        want_m = (keep.float() + sh.permute(1, 2, 3, 0).reshape(-1, cout).bfloat16().float()).bfloat16()
+        assert (main.float() - want_m.float()).abs().max().item() <= 2 ** -6 and _rel(main, want_m) < 1e-3
     s_ = torch.randn(200, 1792, device=dev, generator=g) * 30
     p = torch.empty(200, 1792, device=dev, dtype=torch.bfloat16)
     ops.softmax_rows(s_, p, 1.0 / 32)
@@ -851,10 +878,10 @@ def _vae_model(cfg_name, dev):
     from oracle import vae_oracle as V
     cfg = V.VAE_CONFIGS[cfg_name]
     scale = V.latent_scale(cfg)
-    m = AutoencoderKLWan3_8(latent_channels=cfg["z_dim"], dec_dim=cfg["dec_dim"], dim_mult=cfg["dim_mult"],
-                            temperal_downsample=cfg["temperal_downsample"], latents_mean=scale[0],
-                            latents_std=1.0 / scale[1], device=dev)
-    sd = V.state_dict_torch(cfg, dev, torch.bfloat16)
+    m = AutoencoderKLWan3_8(latent_channels=cfg["z_dim"], c_dim=cfg["enc_dim"], dec_dim=cfg["dec_dim"],
+                            dim_mult=cfg["dim_mult"], temperal_downsample=cfg["temperal_downsample"],
+                            latents_mean=scale[0], latents_std=1.0 / scale[1], device=dev)
+    sd = {**V.encoder_state_dict_torch(cfg, dev, torch.bfloat16), **V.state_dict_torch(cfg, dev, torch.bfloat16)}
     m.load_state_dict({"model." + k: v for k, v in sd.items()}, strict=True)
     return m, cfg, sd
 
@@ -879,6 +906,30 @@ def test_vae_decode_matches_reference_golden(dev, golden_dir):
     assert r_g < 1.5 * gap + 5e-3 and r_l < 2.5e-2 and r_o < 2.5e-2
     out2 = m.decode(z.bfloat16()).sample                       # the history grids are reset per decode
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("cfg_name,T,H,W", [("tiny", 9, 64, 96), ("real", 9, 128, 192)])
+def test_vae_encode(dev, golden_dir, cfg_name, T, H, W):
+    """Native VAE encode (patchify, chunked Encoder3d with stride-2 implicit-GEMM convolutions and AvgDown3D shortcuts,
+    conv1 + latent normalisation) vs the REAL module's fp32 output (tiny fixture), the fp32 oracle and the module's bf16
+    execution with stock torch ops; real width = 160/160/320/640/640 channels (160 is not a multiple of 64: padded)."""
+    from oracle import vae_oracle as V
+    m, cfg, sd = _vae_model(cfg_name, dev)
+    x = torch.from_numpy(V.video(cfg, T, H, W)).to(dev)
+    dist = m.encode(x.bfloat16()).latent_dist
+    out = dist.parameters
+    torch.cuda.synchronize()
+    assert out.shape == (1, 2 * cfg["z_dim"], 1 + (T - 1) // 4, H // 16, W // 16) and torch.isfinite(out.float()).all()
+    fp32 = V.encode({k: v.float() for k, v in sd.items()}, cfg, x, m.scale)
+    lib_out = V.encode(sd, cfg, x.bfloat16(), m.scale).float()
+    r_f, r_l, gap = _rel(out, fp32), _rel(out, lib_out), _rel(lib_out, fp32)
+    msg = f"vae encode {cfg_name}: native vs fp32 oracle {r_f:.3e}; vs library bf16 execution {r_l:.3e}; library vs fp32 {gap:.3e}"
+    if cfg_name == "tiny":
+        gold = torch.from_numpy(np.load(os.path.join(golden_dir, "vae_tiny.npz"))["enc"]).to(dev)
+        msg += f"; native vs the real module's fp32 output {_rel(out, gold):.3e}"
+        assert _rel(out, gold) < 1.5 * gap + 5e-3
+    print(msg + f" ({m.engine().launches} launches)")
+    assert r_f < 1.5 * gap + 5e-3 and r_l < 1.5 * gap + 1e-2
 
 
 def test_vae_decode_real_width(dev):

@@ -23,6 +23,24 @@ def _case(golden_dir, name="vae_tiny"):
     return cfg, torch.from_numpy(V.latents(cfg, T, H, W)), V.latent_scale(cfg), torch.from_numpy(g["out"])
 
 
+def _enc_case(golden_dir, name="vae_tiny"):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    T, H, W = (int(v) for v in g["meta"])
+    cfg = V.VAE_CONFIGS[str(g["config"])]
+    return cfg, torch.from_numpy(V.video(cfg, 1 + 4 * (T - 1), 16 * H, 16 * W)), V.latent_scale(cfg), torch.from_numpy(g["enc"])
+
+
+def _full_sd(cfg):
+    return {**V.encoder_state_dict(cfg), **V.state_dict(cfg)}
+
+
+def test_vae_encoder_oracle_matches_reference_golden(golden_dir):
+    cfg, x, scale, gold = _enc_case(golden_dir)
+    sd = {k: torch.from_numpy(v) for k, v in _full_sd(cfg).items()}
+    out = V.encode(sd, cfg, x, scale)
+    assert out.shape == gold.shape and _rel(out, gold) < 2e-5
+
+
 def test_vae_oracle_matches_reference_golden(golden_dir):
     cfg, z, scale, gold = _case(golden_dir)
     sd = {k: torch.from_numpy(v) for k, v in V.state_dict(cfg).items()}
@@ -36,20 +54,24 @@ def test_vae_oracle_matches_live_reference():
     """Another latent grid and frame count (5 latent frames -> 17 frames: two cached chunks after the "Rep" one)."""
     cfg = V.VAE_CONFIGS["tiny"]
     model = ref_import.build_reference_vae(cfg).eval()
-    sd = {k: torch.from_numpy(v) for k, v in V.state_dict(cfg).items()}
-    model.load_state_dict(sd, strict=False)
+    sd = {k: torch.from_numpy(v) for k, v in _full_sd(cfg).items()}
+    model.load_state_dict(sd, strict=True)
     z, scale = torch.from_numpy(V.latents(cfg, 5, 2, 4, tag="live")), V.latent_scale(cfg)
+    x = torch.from_numpy(V.video(cfg, 13, 32, 48, tag="live"))
     with torch.no_grad():
         ref = model.decode(z, scale).clamp_(-1, 1)
-    assert ref.shape == (1, 3, 17, 32, 64)
+        ref_e = model.encode(x, scale)
+    assert ref.shape == (1, 3, 17, 32, 64) and ref_e.shape == (1, 96, 4, 2, 3)
     assert _rel(V.decode(sd, cfg, z, scale), ref) < 2e-5
+    assert _rel(V.encode(sd, cfg, x, scale), ref_e) < 2e-5
 
 
 def test_vae_param_tree_matches_the_reference_layout():
-    from flexam_b200.vae import param_shapes
+    from flexam_b200.vae import encoder_param_shapes, param_shapes
     for name in ("tiny", "real"):
         cfg = V.VAE_CONFIGS[name]
         assert param_shapes(cfg) == {n: tuple(s) for n, s, _, _ in V.param_specs(cfg)}
+        assert encoder_param_shapes(cfg) == {n: tuple(s) for n, s, _, _ in V.encoder_param_specs(cfg)}
 
 
 def test_vae_decoder_host_logic_matches_oracle(monkeypatch, golden_dir):
@@ -59,10 +81,10 @@ def test_vae_decoder_host_logic_matches_oracle(monkeypatch, golden_dir):
     cpu_ops_emul.install(monkeypatch)
     cfg, z, scale, gold = _case(golden_dir)
     std = 1.0 / scale[1]
-    m = AutoencoderKLWan3_8(latent_channels=cfg["z_dim"], dec_dim=cfg["dec_dim"], dim_mult=cfg["dim_mult"],
-                            temperal_downsample=cfg["temperal_downsample"], latents_mean=scale[0], latents_std=std,
-                            device="cpu")
-    np_sd = V.state_dict(cfg)
+    m = AutoencoderKLWan3_8(latent_channels=cfg["z_dim"], c_dim=cfg["enc_dim"], dec_dim=cfg["dec_dim"],
+                            dim_mult=cfg["dim_mult"], temperal_downsample=cfg["temperal_downsample"],
+                            latents_mean=scale[0], latents_std=std, device="cpu")
+    np_sd = _full_sd(cfg)
     m.load_state_dict({"model." + k: torch.from_numpy(v).bfloat16() for k, v in np_sd.items()}, strict=True)
     out = m.decode(z.bfloat16()).sample
     assert out.shape == gold.shape and out.dtype == torch.bfloat16
@@ -71,5 +93,12 @@ def test_vae_decoder_host_logic_matches_oracle(monkeypatch, golden_dir):
     print(f"emulated native VAE decode: vs bf16-policy oracle {r_o:.3e}, vs reference golden {r_g:.3e}")
     # two different bf16 emulations of a ~70-op chain (the oracle itself sits 1.2e-2 from fp32 here)
     assert r_o < 2.5e-2 and r_g < 3e-2
-    with pytest.raises(RuntimeError):
-        m.encode(torch.zeros(1, 3, 1, 16, 16))
+    # the encoder half through the same wrapper: vae.encode(x).latent_dist
+    _, x, _, gold_e = _enc_case(golden_dir)
+    dist = m.encode(x.bfloat16()).latent_dist
+    enc = dist.parameters
+    assert enc.shape == gold_e.shape and dist.mode().shape[1] == cfg["z_dim"]
+    want_e = V.encode({k: torch.from_numpy(v) for k, v in np_sd.items()}, cfg, x, m.scale, policy="bf16")
+    r_o, r_g = _rel(enc, want_e), _rel(enc, gold_e)
+    print(f"emulated native VAE encode: vs bf16-policy oracle {r_o:.3e}, vs reference golden {r_g:.3e}")
+    assert r_o < 2.5e-2 and r_g < 3e-2
