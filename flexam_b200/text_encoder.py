@@ -174,6 +174,27 @@ class WanT5EncoderModel(nn.Module):
     def device(self):
         return next(self.parameters()).device
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_path, additional_kwargs={}, low_cpu_mem_usage=False,
+                        torch_dtype=torch.bfloat16):
+        """The reference loader's contract (:306-393): constructor kwargs filtered from ``additional_kwargs``
+        (config/wan2.2/wan_civitai_5b_FlexAM.yaml:20-32), a ``.safetensors`` or ``torch.load`` checkpoint, non-strict load
+        with the missing / unexpected keys printed, cast to ``torch_dtype``. ``low_cpu_mem_usage`` is accepted and gives
+        the same result (the reference's meta-device path is an optimisation of the same load)."""
+        import inspect
+        valid = set(inspect.signature(cls.__init__).parameters) - {"self"}
+        model = cls(**{k: v for k, v in dict(additional_kwargs).items() if k in valid})
+        if str(pretrained_model_path).endswith(".safetensors"):
+            from safetensors.torch import load_file
+            state_dict = load_file(pretrained_model_path)
+        else:
+            state_dict = torch.load(pretrained_model_path, map_location="cpu")
+        own = model.state_dict()
+        m, u = model.load_state_dict({k: v.to(own[k].dtype) if k in own else v for k, v in state_dict.items()}, strict=False)
+        print(f"### missing keys: {len(m)}; \n### unexpected keys: {len(u)};")
+        print(m, u)
+        return model.to(torch_dtype)
+
     def engine(self) -> T5Engine:
         params = {k: v.detach() for k, v in self.named_parameters()}
         if self._engine is None or tuple(p.data_ptr() for p in self._engine.params.values()) != \

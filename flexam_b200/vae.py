@@ -498,6 +498,19 @@ def _set_param(root: nn.Module, dotted: str, p: nn.Parameter):
     m.register_parameter(parts[-1], p)
 
 
+# Per-channel statistics of the Wan2.2 latent space: model constants the reference wrapper carries (:906-1008)
+WAN22_LATENTS_MEAN = [
+    -0.2289, -0.0052, -0.1323, -0.2339, -0.2799, 0.0174, 0.1838, 0.1557, -0.1382, 0.0542, 0.2813, 0.0891, 0.1570, -0.0098,
+    0.0375, -0.1825, -0.2246, -0.1207, -0.0698, 0.5109, 0.2665, -0.2108, -0.2158, 0.2502, -0.2055, -0.0322, 0.1109, 0.1567,
+    -0.0729, 0.0899, -0.2799, -0.1230, -0.0313, -0.1649, 0.0117, 0.0723, -0.2839, -0.2083, -0.0520, 0.3748, 0.0152, 0.1957,
+    0.1433, -0.2944, 0.3573, -0.0548, -0.1681, -0.0667]
+WAN22_LATENTS_STD = [
+    0.4765, 1.0364, 0.4514, 1.1677, 0.5313, 0.4990, 0.4818, 0.5013, 0.8158, 1.0344, 0.5894, 1.0901, 0.6885, 0.6165, 0.8454,
+    0.4978, 0.5759, 0.3523, 0.7135, 0.6804, 0.5833, 1.4146, 0.8986, 0.5659, 0.7069, 0.5338, 0.4889, 0.4917, 0.4069, 0.4999,
+    0.6866, 0.4093, 0.5709, 0.6065, 0.6415, 0.4944, 0.5726, 1.2042, 0.5458, 1.6887, 0.3971, 1.0600, 0.3943, 0.5537, 0.5444,
+    0.4089, 0.7468, 0.7744]
+
+
 class AutoencoderKLWan3_8(nn.Module):
     """Drop-in for the DECODE side of FlexAM.models.AutoencoderKLWan3_8 (:892-1057): ``decode(z).sample``. Parameters
     carry the reference's names under ``model.`` (``model.encoder.*``, ``model.conv1.*``, ``model.conv2.*``,
@@ -514,9 +527,11 @@ class AutoencoderKLWan3_8(nn.Module):
         for name, shape in {**encoder_param_shapes(self.cfg), **param_shapes(self.cfg)}.items():
             _set_param(self, "model." + name, nn.Parameter(torch.empty(shape, dtype=dtype, device=device),
                                                            requires_grad=False))
+        if latents_mean is None and latents_std is None and latent_channels == len(WAN22_LATENTS_MEAN):
+            latents_mean, latents_std = WAN22_LATENTS_MEAN, WAN22_LATENTS_STD      # the reference's constants (:906-1008)
         mean = torch.zeros(latent_channels) if latents_mean is None else torch.as_tensor(latents_mean, dtype=f32)
         std = torch.ones(latent_channels) if latents_std is None else torch.as_tensor(latents_std, dtype=f32)
-        self.scale = [mean, 1.0 / std]          # the reference hard-codes the Wan2.2 statistics here (:906-1008)
+        self.scale = [mean, 1.0 / std]
         self._engine: Optional[VaeDecoderEngine] = None
 
     @property
@@ -526,6 +541,26 @@ class AutoencoderKLWan3_8(nn.Module):
     @property
     def device(self):
         return next(self.parameters()).device
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_path, additional_kwargs={}):
+        """The reference loader's contract (:1058-1079): constructor kwargs filtered from ``additional_kwargs``, a
+        ``.safetensors`` or ``torch.load`` checkpoint of the inner model whose keys get the ``model.`` prefix, non-strict
+        load with the missing / unexpected keys printed. (bf16 parameters: the pipeline casts the VAE to its weight dtype.)"""
+        import inspect
+        valid = set(inspect.signature(cls.__init__).parameters) - {"self"}
+        model = cls(**{k: v for k, v in dict(additional_kwargs).items() if k in valid})
+        if str(pretrained_model_path).endswith(".safetensors"):
+            from safetensors.torch import load_file
+            state_dict = load_file(pretrained_model_path)
+        else:
+            state_dict = torch.load(pretrained_model_path, map_location="cpu")
+        state_dict = {"model." + k: v for k, v in state_dict.items()}
+        own = model.state_dict()
+        m, u = model.load_state_dict({k: v.to(own[k].dtype) if k in own else v for k, v in state_dict.items()}, strict=False)
+        print(f"### missing keys: {len(m)}; \n### unexpected keys: {len(u)};")
+        print(m, u)
+        return model
 
     def engine(self) -> VaeDecoderEngine:
         params = {k[len("model."):]: v.detach() for k, v in self.named_parameters()}

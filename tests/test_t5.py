@@ -87,3 +87,25 @@ def test_t5_engine_host_logic_matches_oracle(monkeypatch, golden_dir):
     assert m.engine().launches == 10 * cfg["num_layers"] + 2
     nomask = m(ids)[0]
     assert _rel(nomask, T.forward({k: torch.from_numpy(v) for k, v in np_sd.items()}, cfg, ids, None, policy="bf16")) < 5e-3
+
+
+def test_t5_from_pretrained_follows_the_reference_contract(tmp_path):
+    """.safetensors and torch.save checkpoints, kwargs filtered from the yaml's text_encoder_kwargs (which also carries
+    tokenizer entries), non-strict load, dtype cast (reference :306-393)."""
+    from safetensors.torch import save_file
+    from flexam_b200.text_encoder import WanT5EncoderModel
+    cfg = T.T5_CONFIGS["tiny"]
+    sd = {k: torch.from_numpy(v) for k, v in T.state_dict(cfg).items()}
+    kwargs = dict(cfg, text_encoder_subpath="models_t5.pth", tokenizer_subpath="google/umt5-xxl", text_length=512,
+                  shared_pos=False, dropout=0.0)
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(tmp_path / "t5.safetensors"))
+    extra = dict(sd)
+    extra["something.else"] = torch.zeros(3)
+    del extra["norm.weight"]
+    torch.save(extra, str(tmp_path / "t5.pth"))
+    a = WanT5EncoderModel.from_pretrained(str(tmp_path / "t5.safetensors"), additional_kwargs=kwargs)
+    assert all(v.dtype == torch.bfloat16 for v in a.state_dict().values())
+    assert torch.equal(a.state_dict()["blocks.1.ffn.fc2.weight"], sd["blocks.1.ffn.fc2.weight"].bfloat16())
+    b = WanT5EncoderModel.from_pretrained(str(tmp_path / "t5.pth"), additional_kwargs=kwargs, low_cpu_mem_usage=True,
+                                          torch_dtype=torch.bfloat16)
+    assert torch.equal(b.state_dict()["token_embedding.weight"], sd["token_embedding.weight"].bfloat16())

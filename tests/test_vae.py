@@ -102,3 +102,22 @@ def test_vae_decoder_host_logic_matches_oracle(monkeypatch, golden_dir):
     r_o, r_g = _rel(enc, want_e), _rel(enc, gold_e)
     print(f"emulated native VAE encode: vs bf16-policy oracle {r_o:.3e}, vs reference golden {r_g:.3e}")
     assert r_o < 2.5e-2 and r_g < 3e-2
+
+
+def test_vae_from_pretrained_and_latent_statistics(tmp_path):
+    """The wrapper loader (:1058-1079: inner-model checkpoint, keys prefixed with `model.`) and the Wan2.2 latent
+    statistics the wrapper carries by default (:906-1008)."""
+    from safetensors.torch import save_file
+    from flexam_b200.vae import AutoencoderKLWan3_8, WAN22_LATENTS_MEAN, WAN22_LATENTS_STD
+    cfg = V.VAE_CONFIGS["tiny"]
+    sd = {k: torch.from_numpy(v) for k, v in _full_sd(cfg).items()}
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(tmp_path / "vae.safetensors"))
+    kw = dict(latent_channels=cfg["z_dim"], c_dim=cfg["enc_dim"], dec_dim=cfg["dec_dim"], vae_type="AutoencoderKLWan3_8",
+              vae_subpath="Wan2.2_VAE.pth")
+    m = AutoencoderKLWan3_8.from_pretrained(str(tmp_path / "vae.safetensors"), additional_kwargs=kw)
+    got = m.state_dict()
+    assert set(got) == {"model." + k for k in sd}
+    assert torch.equal(got["model.decoder.head.2.weight"], sd["decoder.head.2.weight"].bfloat16())
+    assert len(WAN22_LATENTS_MEAN) == len(WAN22_LATENTS_STD) == 48
+    assert torch.allclose(m.scale[0], torch.tensor(WAN22_LATENTS_MEAN)) and \
+        torch.allclose(m.scale[1], 1.0 / torch.tensor(WAN22_LATENTS_STD))
