@@ -695,6 +695,107 @@ def run_vae(args):
     print(json.dumps(res))
 
 
+def run_video(args):
+    """One whole generation on N GPUs of one box, every model of the path native: umT5 prompt encoding, the pipeline's 8
+    VAE encodes (7 clips of 97 frames + the reference image; sharded over the ranks), the 50-step CFG sampling loop
+    (CFG-branch x sequence parallel), VAE decode of the result. Synthetic pixels / token ids, random-init weights of the
+    real architectures. Seconds per video and the breakdown; not the bench line."""
+    import torch
+    import torch.distributed as dist
+    from flexam_b200 import dist as fdist
+    from flexam_b200 import lib
+    from flexam_b200.model import Wan2_2Transformer3DModel_FlexAM
+    from flexam_b200.sampler import DenoiseLoop, flow_match_euler_schedule
+    from flexam_b200.text_encoder import WanT5EncoderModel
+    from flexam_b200.vae import AutoencoderKLWan3_8
+    from oracle import t5_oracle as T5
+    from oracle import vae_oracle as V
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib.check(lib.load().fx_check_device(local), "fx_check_device")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = real_cfg()
+    dit = Wan2_2Transformer3DModel_FlexAM(**cfg, device=dev)
+    init_weights(torch, dit)
+    layout = fdist.setup(dit, world, rank) if world > 1 else "single"
+    tcfg = T5.T5_CONFIGS["real"]
+    t5 = WanT5EncoderModel(**tcfg, device=dev)
+    g = torch.Generator(device=dev).manual_seed(99)
+    for name, p in t5.named_parameters():
+        if "norm" in name:
+            p.data.fill_(1.0)
+        else:
+            std = 1.0 if name.startswith("token_embedding") else (0.5 if "pos_embedding" in name else p.shape[-1] ** -0.5)
+            p.data.copy_((torch.randn(p.shape, device=dev, generator=g) * std * (0.2 if name.endswith("attn.q.weight") else 1)).to(p.dtype))
+    vcfg = V.VAE_CONFIGS["real"]
+    vae = AutoencoderKLWan3_8(latent_channels=48, c_dim=vcfg["enc_dim"], dec_dim=vcfg["dec_dim"], device=dev)
+    sd = {**V.encoder_state_dict_torch(vcfg, dev, torch.bfloat16), **V.state_dict_torch(vcfg, dev, torch.bfloat16)}
+    vae.load_state_dict({"model." + k: v for k, v in sd.items()}, strict=True)
+    F, H, W = GRID
+    frames, ph, pw = 1 + 4 * (F - 1), 16 * H, 16 * W
+    gc = torch.Generator().manual_seed(7)
+    clips = [(torch.rand(1, 3, frames, ph, pw, generator=gc) * 2 - 1).bfloat16().to(dev) for _ in range(7)]
+    clips.append((torch.rand(1, 3, 1, ph, pw, generator=gc) * 2 - 1).bfloat16().to(dev))          # the reference image
+    ids, mask = T5.inputs(tcfg, L=512, lens=PROMPT_LENS)
+    ids, mask = torch.from_numpy(ids).to(dev), torch.from_numpy(mask).to(dev)
+    noise = torch.randn(1, 48, F, H, W, generator=gc).to(dev)
+    n = args.loop_steps
+    ts, sig = flow_match_euler_schedule(n, 5.0)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def generate():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
+        emb = t5(ids, mask)[0]                                            # [2, 512, 4096]: negative, positive prompt
+        neg, pos = [emb[0, :PROMPT_LENS[0]]], [emb[1, :PROMPT_LENS[1]]]    # u[:v] (pipeline _get_t5_prompt_embeds)
+        ev[1].record()
+        lat = [p[:, :48] for p in fdist.encode_many(vae, clips, world, rank)]     # latent_dist.mode()
+        masked_video, control, ref = lat[0], lat[1], lat[7][:, :, 0]
+        additional = torch.cat(lat[2:7], dim=1)                           # 5 x 48 = 240 additional control channels
+        lmask = torch.ones(1, 1, F, H, W, device=dev)
+        lmask[:, :, 0] = 0
+        mask_lat = (1 - lmask).expand(1, 4, F, H, W).contiguous()
+        ev[2].record()
+        loop = DenoiseLoop(dit, noise, lmask, masked_video, mask_lat, control, additional, ref, neg, pos, density=0.1,
+                           guidance_scale=6.0)
+        out = loop.run(ts, sig)
+        ev[3].record()
+        video = vae.decode(out).sample if rank == 0 or world == 1 else None
+        ev[4].record()
+        sync()
+        return video, [ev[i].elapsed_time(ev[i + 1]) for i in range(4)], loop
+    generate()                                                            # warm-up generation
+    sync()
+    t0 = time.perf_counter()
+    video, parts, loop = generate()
+    wall = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor(parts + [wall * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parts, wall = t[:4].tolist(), t[4].item() / 1e3
+    if rank == 0:
+        print(json.dumps({
+            "workload": f"one whole generation: umT5 prompt encoding, 8 VAE encodes, {n}-step CFG sampling loop, VAE decode; "
+                        f"{frames} frames {ph}x{pw}, bf16, synthetic inputs, random-init weights", "n_gpus": world,
+            "layout": layout, "seconds_per_video": sum(parts) / 1e3, "wall_seconds": wall,
+            "breakdown_ms": {"text_encoder": parts[0], "vae_encode_x8": parts[1], "denoise_loop": parts[2],
+                             "vae_decode": parts[3]},
+            "device_to_host_reads_in_loop": loop.host_reads,
+            "parity": {"video_checksum_sha256_16": output_checksum(video), "shape": list(video.shape),
+                       "finite": bool(torch.isfinite(video.float()).all().item())}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_loop(args):
     """BASELINE config 4: the full sampling loop (`full_edit`: first latent frame pinned, density 10 => the model sees
     0.1, guidance 6, flow-match Euler with shift 5) at 97 frames 512x896 through flexam_b200.sampler.DenoiseLoop — per
@@ -911,7 +1012,7 @@ if __name__ == "__main__":
     ap.add_argument("--loop-steps", type=int, default=50, help="sampling steps of --workload loop50")
     ap.add_argument("--graph", action="store_true", help="loop50: replay the transformer call from CUDA graphs (N = 1)")
     ap.add_argument("--vae-frames", type=int, default=0, help="--workload vae: latent frames (default: the clip's 25)")
-    ap.add_argument("--workload", default="config2", choices=["config2", "long", "loop50", "t5", "vae"],
+    ap.add_argument("--workload", default="config2", choices=["config2", "long", "loop50", "t5", "vae", "video"],
                     help="config2 = the metric's workload (default); long = BASELINE config 5, 193 frames 704x1280 "
                          "(43,120 tokens + 880 ref): a parity/stress case, not the bench line")
     a = ap.parse_args()
@@ -927,5 +1028,7 @@ if __name__ == "__main__":
         run_t5(a)
     elif a.workload == "vae":
         run_vae(a)
+    elif a.workload == "video":
+        run_video(a)
     else:
         run_native(a)

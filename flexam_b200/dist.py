@@ -256,3 +256,29 @@ def attach(model) -> None:
     if not dist.is_initialized():
         raise RuntimeError("enable_multi_gpus_inference: torch.distributed is not initialised")
     setup(model, dist.get_world_size(), dist.get_rank())
+
+
+def encode_many(vae, videos, world: Optional[int] = None, rank: Optional[int] = None):
+    """The pipeline encodes 8 independent clips per generation (masked video, control video, additional controls,
+    reference image; pipeline_wan2_2_fun_control_FlexAM.py:662-819): independent units, so across the ranks of one box
+    they are sharded round-robin with no data-path collective except the final all-gather of the (small) latents.
+    ``videos``: list of [1, 3, T, H, W] tensors, the same list on every rank (clips of one shape are gathered together).
+    Returns the list of ``vae.encode(v).latent_dist.parameters`` in input order, identical on every rank."""
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    mine = {i: vae.encode(v).latent_dist.parameters for i, v in enumerate(videos) if i % world == rank}
+    if world == 1:
+        return [mine[i] for i in range(len(videos))]
+    out = [None] * len(videos)
+    for i, v in enumerate(videos):          # one broadcast per clip from its owner (shapes are known on every rank)
+        owner = i % world
+        if owner == rank:
+            buf = mine[i].contiguous()
+        else:
+            T = v.shape[2]
+            buf = torch.empty((1, 2 * vae.cfg["z_dim"], 1 + (T - 1) // 4, v.shape[3] // 16, v.shape[4] // 16),
+                              dtype=torch.bfloat16, device=v.device)
+        dist.broadcast(buf, src=owner)
+        out[i] = buf
+    return out

@@ -186,3 +186,44 @@ def test_teacache_with_cfg_skip_under_cfg_parallel(tmp_path):
         # that re-applies the wrong branch's residual lands at 1.5e-2 (measured with the fetch disabled)
         assert err < 8e-3, f"rank {rank}: CFG-parallel loop differs from the single-process loop ({err:.2e})"
     assert res[0][2] == res[1][2], "the two CFG ranks disagree with each other"
+
+
+# ------------------------------------------------------------------------------------------------------
+# The pipeline's independent VAE encodes sharded over the ranks (flexam_b200.dist.encode_many)
+# ------------------------------------------------------------------------------------------------------
+def _encode_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    torch.set_num_threads(2)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _patch_ops()
+        from flexam_b200 import dist as fdist
+        from flexam_b200.vae import AutoencoderKLWan3_8
+        from oracle import vae_oracle as V
+        cfg = V.VAE_CONFIGS["tiny"]
+        m = AutoencoderKLWan3_8(latent_channels=cfg["z_dim"], c_dim=cfg["enc_dim"], dec_dim=cfg["dec_dim"], device="cpu")
+        sd = {**V.encoder_state_dict(cfg), **V.state_dict(cfg)}
+        m.load_state_dict({"model." + k: torch.from_numpy(v).bfloat16() for k, v in sd.items()}, strict=True)
+        clips = [torch.from_numpy(V.video(cfg, T, 32, 48, tag=f"clip{i}")).bfloat16() for i, T in enumerate((5, 5, 1))]
+        got = fdist.encode_many(m, clips)
+        want = [m.encode(c).latent_dist.parameters for c in clips]
+        q.put((rank, [tuple(g.shape) for g in got], all(torch.equal(a, b) for a, b in zip(got, want))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_vae_encodes_are_sharded_over_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_encode_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    for rank, shapes, same in sorted(q.get(timeout=10) for _ in range(2)):
+        assert shapes == [(1, 96, 2, 2, 3), (1, 96, 2, 2, 3), (1, 96, 1, 2, 3)] and same, (rank, shapes, same)
