@@ -604,16 +604,19 @@ def run_t5(args):
 def run_vae(args):
     """SURVEY §8f N2 (decode half): the Wan2.2 VAE decoder at its real width on the 25 x 32 x 56 latents of the metric's
     clip -> 97 frames 512 x 896, native vs the module's bf16 execution with stock torch ops (cuDNN convolutions, SDPA)
-    on the same GPU, parity against the fp32 oracle. Runs once per video; not the bench line."""
+    on the same GPU, parity against the fp32 oracle. Runs once per video; not the bench line. On N > 1 GPUs: the decode
+    split into bands of image rows over the ranks (flexam_b200.dist.SlabExchange) next to the one-GPU decode, checksums of both."""
     import torch
     from flexam_b200 import lib
     from flexam_b200.vae import AutoencoderKLWan3_8
     from oracle import vae_oracle as V
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     lib.check(lib.load().fx_check_device(dev.index), "fx_check_device")
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     cfg = V.VAE_CONFIGS["real"]
     scale = V.latent_scale(cfg)
     m = AutoencoderKLWan3_8(latent_channels=cfg["z_dim"], c_dim=cfg["enc_dim"], dec_dim=cfg["dec_dim"],
@@ -636,6 +639,25 @@ def run_vae(args):
         torch.cuda.synchronize()
         return out, e0.elapsed_time(e1) / steps
     out, ms = timed(lambda: m.decode(z).sample, max(1, min(args.steps, 3)), 1)
+    if world > 1:
+        one_launches = m.engine().launches
+        ex = m.enable_multi_gpus_inference()
+        dist.barrier()
+        out_n, ms_n = timed(lambda: m.decode(z).sample, max(1, min(args.steps, 3)), 2)
+        t = torch.tensor([ms_n], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(json.dumps({
+                "workload": f"Wan2.2 VAE decode in {world} bands of image rows, {T} x {H} x {W} latents -> "
+                            f"{1 + 4 * (T - 1)} frames {16 * H} x {16 * W}, bf16", "n_gpus": world, "ms": t.item(),
+                "ms_one_gpu": ms, "speedup": ms / t.item(), "exchange": type(ex).__name__,
+                "halo_exchanges_per_decode": ex.exchanges // (2 + max(1, min(args.steps, 3))),
+                "gpu_launches": m.engine().launches, "gpu_launches_one_gpu": one_launches,
+                "parity": {"checksum_sha256_16": output_checksum(out_n), "one_gpu_checksum_sha256_16": output_checksum(out),
+                           "identical": bool(torch.equal(out, out_n))}}))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     # algorithmic FLOPs: 2 * out pixels * Cout * taps * Cin over every convolution, frames as the chunks see them
     dims, n = V.decoder_dims(cfg), len(cfg["dim_mult"])
     t_up = cfg["temperal_downsample"][::-1]
@@ -736,6 +758,8 @@ def run_video(args):
     vae = AutoencoderKLWan3_8(latent_channels=48, c_dim=vcfg["enc_dim"], dec_dim=vcfg["dec_dim"], device=dev)
     sd = {**V.encoder_state_dict_torch(vcfg, dev, torch.bfloat16), **V.state_dict_torch(vcfg, dev, torch.bfloat16)}
     vae.load_state_dict({"model." + k: v for k, v in sd.items()}, strict=True)
+    if world > 1 and os.environ.get("FLEXAM_VAE_SLABS", "1") != "0":
+        vae.enable_multi_gpus_inference()
     F, H, W = GRID
     frames, ph, pw = 1 + 4 * (F - 1), 16 * H, 16 * W
     gc = torch.Generator().manual_seed(7)
@@ -769,7 +793,7 @@ def run_video(args):
                            guidance_scale=6.0)
         out = loop.run(ts, sig)
         ev[3].record()
-        video = vae.decode(out).sample if rank == 0 or world == 1 else None
+        video = vae.decode(out).sample                                    # N > 1: bands of image rows over the ranks
         ev[4].record()
         sync()
         return video, [ev[i].elapsed_time(ev[i + 1]) for i in range(4)], loop

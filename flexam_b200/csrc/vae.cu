@@ -213,6 +213,26 @@ __global__ void vae_avgdown_add_kernel(__nv_bfloat16* main, const __nv_bfloat16*
   }
 }
 
+// H-slab decode across GPUs (flexam_b200/dist.py SlabExchange): every rank owns a band of image rows of every padded grid
+// [frames, Hp, Wp, C]; its first / last interior row is the bottom / top halo row of the neighbour above / below. One
+// launch copies both rows of `T` live frames straight into the neighbours' grids (peer memory over NVLink).
+__global__ void __launch_bounds__(256)
+vae_halo_push_kernel(const uint4* grid, uint4* up, uint4* dn, int T, long long plane16, long long row16, int Hp) {
+  const long long per_side = static_cast<long long>(T) * row16;
+  const long long total = per_side * 2;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int side = i >= per_side;
+    const long long r = i - side * per_side;
+    const long long f = r / row16, c = r - f * row16;
+    if (side == 0) {
+      if (up != nullptr) up[f * plane16 + (Hp - 1) * row16 + c] = grid[f * plane16 + row16 + c];
+    } else {
+      if (dn != nullptr) dn[f * plane16 + c] = grid[f * plane16 + (Hp - 2) * row16 + c];
+    }
+  }
+}
+
 }  // namespace fx
 
 extern "C" int fx_vae_patchify(const void* video, void* rows, int64_t ldr, int T, int h, int w, int Ttot, int frame0,
@@ -309,5 +329,21 @@ extern "C" int fx_vae_unpatchify(const void* y, int64_t ldy, void* video, int T,
   vae_unpatchify_kernel<<<vae_grid(12LL * T * H * W), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(y), ldy, reinterpret_cast<__nv_bfloat16*>(video), T, H, W, Ttot, frame0);
   FX_CHECK_LAUNCH("fx_vae_unpatchify");
+  return FX_OK;
+}
+
+extern "C" int fx_vae_halo_push(const void* grid, void* up_grid, void* dn_grid, int frame0, int T, int Hp, int Wp, int C,
+                                void* stream) {
+  using namespace fx;
+  FX_CHECK_ARG(grid && frame0 >= 0 && T > 0 && Hp >= 3 && Wp > 0 && C > 0 && C % 8 == 0,
+               "fx_vae_halo_push: bad arguments");
+  FX_CHECK_ARG((reinterpret_cast<uintptr_t>(grid) | reinterpret_cast<uintptr_t>(up_grid) |
+                reinterpret_cast<uintptr_t>(dn_grid)) % 16 == 0, "fx_vae_halo_push: grids must be 16-byte aligned");
+  if (up_grid == nullptr && dn_grid == nullptr) return FX_OK;
+  const long long row16 = static_cast<long long>(Wp) * C / 8, plane16 = row16 * Hp, off = frame0 * plane16;
+  vae_halo_push_kernel<<<vae_grid(2LL * T * row16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(grid) + off, up_grid ? reinterpret_cast<uint4*>(up_grid) + off : nullptr,
+      dn_grid ? reinterpret_cast<uint4*>(dn_grid) + off : nullptr, T, plane16, row16, Hp);
+  FX_CHECK_LAUNCH("fx_vae_halo_push");
   return FX_OK;
 }

@@ -282,3 +282,123 @@ def encode_many(vae, videos, world: Optional[int] = None, rank: Optional[int] = 
         dist.broadcast(buf, src=owner)
         out[i] = buf
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# VAE decode split across the ranks of one box
+# ----------------------------------------------------------------------------------------------------------
+class SlabExchange:
+    """Band-of-rows decomposition of the VAE decode (``VaeDecoderEngine.slab``). The reference decodes the whole clip on
+    every rank (pipeline_wan2_2_fun_control_FlexAM.py:955-958); here rank r decodes rows [r H / P, (r + 1) H / P) of the
+    latent grid — and of every up-sampled stage — and the only coupling between bands is the one-row halo of each 3x3
+    spatial convolution (RMS norm, SiLU, nearest up-sampling, the time convolution and the DupUp3D shortcut are per
+    pixel) plus the single-head attention of the middle block, which every rank computes over the gathered frame. Every
+    output pixel is produced by the same K-ordered accumulation as on one GPU, so the decoded clip is bit-identical.
+
+    This base class moves halo rows with ``torch.distributed`` point-to-point calls (any backend: the world-size-2 gloo
+    tests run it); ``SymmSlabExchange`` is the NVLink form (peer stores into symmetric buffers + a stream barrier)."""
+
+    def __init__(self, world: int, rank: int, group=None):
+        self.world, self.rank, self.group = world, rank, group
+        self.exchanges = 0
+
+    def alloc(self, name: str, rows: int, C: int, device) -> torch.Tensor:
+        return torch.zeros((rows, C), dtype=torch.bfloat16, device=device)
+
+    def sync(self) -> None:
+        pass                                  # point-to-point receives land in private staging rows: nothing to order
+
+    def halo(self, grid: torch.Tensor, frame0: int, T: int, Hp: int, Wp: int) -> None:
+        g = grid[:(frame0 + T) * Hp * Wp].view(frame0 + T, Hp, Wp * grid.shape[1])[frame0:]
+        up, dn = self.rank - 1, self.rank + 1
+        reqs, recv = [], []
+        if up >= 0:
+            buf = torch.empty_like(g[:, 0])
+            recv.append((buf, 0))
+            reqs.append(dist.irecv(buf, src=self._global(up), group=self.group))
+            reqs.append(dist.isend(g[:, 1].contiguous(), dst=self._global(up), group=self.group))
+        if dn < self.world:
+            buf = torch.empty_like(g[:, 0])
+            recv.append((buf, Hp - 1))
+            reqs.append(dist.irecv(buf, src=self._global(dn), group=self.group))
+            reqs.append(dist.isend(g[:, Hp - 2].contiguous(), dst=self._global(dn), group=self.group))
+        for r in reqs:
+            r.wait()
+        for buf, row in recv:
+            g[:, row].copy_(buf)
+        self.exchanges += 1
+
+    def _global(self, r: int) -> int:
+        return r if self.group is None else dist.get_global_rank(self.group, r)
+
+    def gather_rows(self, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        dist.all_gather_into_tensor(out, x, group=self.group)
+        return out
+
+    def gather_video(self, v: torch.Tensor) -> torch.Tensor:
+        """v: [3, T, band rows, W] -> [3, T, world * band rows, W]."""
+        out = torch.empty((self.world * v.shape[0],) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+        dist.all_gather_into_tensor(out, v.contiguous(), group=self.group)           # rank-major along dim 0
+        return out.view((self.world,) + tuple(v.shape)).permute(1, 2, 0, 3, 4).reshape(v.shape[0], v.shape[1], self.world * v.shape[2], v.shape[3])
+
+
+class SymmSlabExchange(SlabExchange):
+    """Grids in symmetric memory: one ``fx_vae_halo_push`` launch stores both boundary rows into the neighbours' grids over
+    NVLink, then the buffer's own signal-pad barrier (a kernel on the stream, no host wait) orders it against their
+    convolutions."""
+
+    def __init__(self, world: int, rank: int, group=None):
+        super().__init__(world, rank, group)
+        self._h = {}
+        self._names = {}
+        self._sync_buf = None
+
+    def _symm(self, shape, dtype, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        t = symm_mem.empty(*shape, dtype=dtype, device=device)
+        t.zero_()
+        hdl = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+        hdl.barrier(0)                    # every rank has cleared its copy before any neighbour stores into it
+        return t, hdl
+
+    def alloc(self, name, rows, C, device):
+        old = self._names.pop(name, None)
+        if old is not None:
+            self._h.pop(old, None)
+        t, hdl = self._symm((rows, C), torch.bfloat16, device)
+        self._h[t.data_ptr()] = (hdl, [int(p) for p in hdl.buffer_ptrs], t)
+        self._names[name] = t.data_ptr()
+        return t
+
+    def sync(self):
+        if self._sync_buf is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self._sync_buf = self._symm((64,), torch.float32, dev)
+        self._sync_buf[1].barrier(0)
+
+    def halo(self, grid, frame0, T, Hp, Wp):
+        from . import ops
+        hdl, ptrs, _ = self._h[grid.data_ptr()]
+        up = ptrs[self.rank - 1] if self.rank > 0 else 0
+        dn = ptrs[self.rank + 1] if self.rank + 1 < self.world else 0
+        ops.vae_halo_push(grid, up, dn, frame0, T, Hp, Wp)
+        hdl.barrier(0)
+        self.exchanges += 1
+
+
+def enable_vae_slabs(vae, world: Optional[int] = None, rank: Optional[int] = None, group=None):
+    """Split ``vae.decode`` into bands of image rows over the ranks of ``group`` (default: all ranks). Every rank calls
+    ``vae.decode(latents)`` with the same latents and gets the same, complete clip back. Latent heights that do not divide
+    by the number of ranks fall back to the replicated decode."""
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+    ex = None
+    if world > 1:
+        nccl = dist.get_backend(group) == "nccl" and os.environ.get("FLEXAM_VAE_HALO", "symm") != "p2p"
+        ex = (SymmSlabExchange if nccl else SlabExchange)(world, rank, group)
+    if hasattr(vae, "_slab"):
+        vae._slab = ex                      # the mirror hands it to whichever engine it builds
+    else:
+        vae.slab = ex
+    return ex

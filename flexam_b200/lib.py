@@ -61,6 +61,7 @@ SIGNATURES = {
     "fx_vae_upsample2x": [_vp, _vp, _i, _i, _i, _i, _vp],
     "fx_vae_time_interleave": [_vp, _vp, _i, _i64, _i, _vp],
     "fx_vae_dupup_add": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "fx_vae_halo_push": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fx_softmax_rows_f32": [_vp, _i64, _vp, _i64, _i, _i, _f, _vp],
     "fx_vae_unpatchify": [_vp, _i64, _vp, _i, _i, _i, _i, _i, _vp],
     "fx_vae_patchify": [_vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],

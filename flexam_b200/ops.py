@@ -624,6 +624,17 @@ def vae_dupup_add_(main: torch.Tensor, x: torch.Tensor, Tout: int, H: int, W: in
     return main
 
 
+def vae_halo_push(grid: torch.Tensor, up_ptr: int, dn_ptr: int, frame0: int, T: int, Hp: int, Wp: int) -> None:
+    """grid: bf16 [>= (frame0+T)*Hp*Wp, C] contiguous; up_ptr / dn_ptr: device addresses of the SAME grid on the rank
+    above / below (0 = none). See fx_vae_halo_push."""
+    _req(grid, bf16, "vae_halo_push.grid")
+    if not grid.is_contiguous() or grid.shape[0] < (frame0 + T) * Hp * Wp:
+        raise _l.FlexamNativeError("vae_halo_push: grid too small")
+    st = _l.load().fx_vae_halo_push(_p(grid), C.c_void_p(up_ptr or None), C.c_void_p(dn_ptr or None), frame0, T,
+                                    Hp, Wp, grid.shape[1], _stream())
+    _l.check(st, "fx_vae_halo_push")
+
+
 def softmax_rows(s: torch.Tensor, p: torch.Tensor, scale: float) -> torch.Tensor:
     _req(s, f32, "softmax_rows.s"), _req(p, bf16, "softmax_rows.p")
     rows, cols = s.shape

@@ -129,6 +129,8 @@ class VaeDecoderEngine:
         self._ws: Dict[tuple, torch.Tensor] = {}
         self._hist: Dict[str, torch.Tensor] = {}
         self.launches = 0
+        self.slab = None            # flexam_b200.dist.SlabExchange: decode split into bands of image rows across the ranks
+        self._slab_on = False
         self._pack()
 
     # -- weights: tap-major [Cout (padded to 8), taps * Cin (padded to 64)] ------------------------------------------
@@ -198,17 +200,29 @@ class VaeDecoderEngine:
         the history frames start as zeros and only interior / live positions are ever written. A chunk with more frames
         than any before (the first chunk is not up-sampled in time) grows the grid and keeps its ``keep_rows`` history."""
         need = frames * Hp * Wp
-        t = self._hist.get(name)
+        key = ("slab:" if self._slab_on else "") + name       # band-sized, peer-mapped grids live next to the full-size ones
+        t = self._hist.get(key)
         if t is None or t.shape[0] < need or t.shape[1] != C:
-            new = torch.zeros((need, C), dtype=bf16, device=self.device)
+            if self._slab_on:
+                new = self.slab.alloc(key, need, C, self.device)       # zeroed; collective (every rank grows the same grid)
+            else:
+                new = torch.zeros((need, C), dtype=bf16, device=self.device)
             if t is not None and t.shape[1] == C and keep_rows:
                 new[:keep_rows].copy_(t[:keep_rows])
-            self._hist[name] = t = new
+            self._hist[key] = t = new
         return t
 
     def _reset_history(self):
         for t in self._hist.values():
             t.zero_()
+        if self._slab_on:
+            self.slab.sync()                 # nobody pushes a halo row into a grid its owner has not cleared yet
+
+    def _halo(self, grid, frame0, T, Hp, Wp):
+        """Slab decode: the first / last interior row of my band is the halo row of the band above / below."""
+        if self._slab_on:
+            self.slab.halo(grid, frame0, T, Hp, Wp)
+            self.launches += 2
 
     # -- building blocks -------------------------------------------------------------------------------------------
     def _cconv(self, name, x, T, H, W, gamma=None, silu=False, kt=3, ks=3, stride_s=1, stride_t=1, run=True):
@@ -222,6 +236,8 @@ class VaeDecoderEngine:
         hist = kt - 1
         grid = self._grid(name, hist + T, Hp, Wp, cin, keep_rows=hist * Hp * Wp)
         ops.vae_norm_act(x, gamma, grid, H, W, pad, hist, silu)
+        if pad:
+            self._halo(grid, hist, T, Hp, Wp)
         out = None
         if run:
             out = self._buf("out:" + name, ((T // stride_t) * (H // stride_s) * (W // stride_s), w.shape[0]))
@@ -253,6 +269,18 @@ class VaeDecoderEngine:
         """AttentionBlock (:243-282): one head of width C over the H*W tokens of each frame. S = Q K^T and O = P V are
         GEMMs on the tensor cores (V transposed once into the [C, tokens] weight layout), softmax a row kernel."""
         C, P = x.shape[1], H * W
+        if self._slab_on:        # every rank attends over the whole frame (25 GFLOP): gather the bands, keep my rows
+            ex = self.slab
+            if T != 1:
+                raise FlexamNativeError("internal: slab decode expects one frame per chunk at the attention block")
+            full = ex.gather_rows(x.contiguous(), self._buf("attn_gather", (ex.world * P, C)))
+            self._slab_on = False
+            try:
+                y = self._attn(name, full, 1, H * ex.world, W)
+            finally:
+                self._slab_on = True
+            self.launches += 1
+            return y[ex.rank * P:(ex.rank + 1) * P]
         out = self._buf("attn_out", (T * P, C))
         for f in range(T):
             xf = x[f * P:(f + 1) * P]
@@ -289,6 +317,7 @@ class VaeDecoderEngine:
         up = self._grid(name + ".resample.1", T, 2 * H + 2, 2 * W + 2, C)
         rows = T * (2 * H + 2) * (2 * W + 2)
         ops.vae_upsample2x(x.contiguous(), up[:rows], T, H, W)
+        self._halo(up, 0, T, 2 * H + 2, 2 * W + 2)
         w = self.w[name + ".resample.1"]
         out = self._buf("out:" + name, (T * 4 * H * W, w.shape[0]))
         ops.conv_gemm(up[:rows], w, self.b[name + ".resample.1"], out, T, 2 * H, 2 * W, 1, 3, FX_EPI_BF16)
@@ -306,15 +335,26 @@ class VaeDecoderEngine:
         if z.dim() != 5 or z.shape[0] != 1 or z.shape[1] != zd:
             raise FlexamNativeError(f"VAE decode: expected latents [1, {zd}, T, H, W], got {tuple(z.shape)}")
         self._fold_scale(scale)
+        _, _, T, H, W = z.shape
+        ex = self.slab
+        self._slab_on = ex is not None and ex.world > 1 and H % ex.world == 0
+        try:
+            return self._decode(z, T, H // ex.world if self._slab_on else H, W)
+        finally:
+            self._slab_on = False
+
+    def _decode(self, z, T, H, W):
+        """H: the rows of the latent grid this rank decodes (all of them, or its band of a slab decode)."""
+        cfg, dev, zd, ex = self.cfg, self.device, self.cfg["z_dim"], self.slab
         self._reset_history()
         self.launches = 0
-        _, _, T, H, W = z.shape
         dims = self.dims
         n = len(cfg["dim_mult"])
         t_up = list(cfg["temperal_downsample"])[::-1]
         nres = cfg["num_res_blocks"] + 1
         P = H * W
-        zc = z[0].to(dev, bf16).contiguous().view(zd, T * P)
+        zb = z[0, :, :, ex.rank * H:(ex.rank + 1) * H] if self._slab_on else z[0]
+        zc = zb.to(dev, bf16).contiguous().view(zd, T * P)
         zl = self._buf("z_rows", (T * P, _pad64(zd)), zero=True)
         ops.nchw_to_nhwc(zc, zl, 0)
         x_all = self._buf("conv2_out", (T * P, _pad64(zd)))
@@ -354,6 +394,8 @@ class VaeDecoderEngine:
             f_out += Tc
         if f_out != Tout:
             raise FlexamNativeError(f"internal: decoded {f_out} frames, expected {Tout}")
+        if self._slab_on:
+            video = ex.gather_video(video)                # [3, Tout, world * band rows, width] on every rank
         return video.unsqueeze(0)
 
 
@@ -533,6 +575,13 @@ class AutoencoderKLWan3_8(nn.Module):
         std = torch.ones(latent_channels) if latents_std is None else torch.as_tensor(latents_std, dtype=f32)
         self.scale = [mean, 1.0 / std]
         self._engine: Optional[VaeDecoderEngine] = None
+        self._slab = None
+
+    def enable_multi_gpus_inference(self, group=None):
+        """Split ``decode`` into bands of image rows over the ranks (``flexam_b200.dist.enable_vae_slabs``); the counterpart
+        of the transformer's ``enable_multi_gpus_inference`` — the reference decodes the whole clip on every rank."""
+        from .dist import enable_vae_slabs
+        return enable_vae_slabs(self, group=group)
 
     @property
     def dtype(self):
@@ -567,6 +616,7 @@ class AutoencoderKLWan3_8(nn.Module):
         if self._engine is None or tuple(p.data_ptr() for p in self._engine.params.values()) != \
                 tuple(p.data_ptr() for p in params.values()):
             self._engine = VaeDecoderEngine(params, self.cfg, next(iter(params.values())).device)
+        self._engine.slab = self._slab
         return self._engine
 
     def _decode(self, zs: torch.Tensor) -> DecoderOutput:                       # :1041-1049

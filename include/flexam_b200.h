@@ -329,6 +329,13 @@ int fx_vae_unpatchify(const void* y, int64_t ldy, void* video, int T, int H, int
  * The stride-2 convolutions of Resample downsample2d / downsample3d are fx_conv_gemm_bf16 with stride_s / stride_t = 2. */
 int fx_vae_patchify(const void* video, void* rows, int64_t ldr, int T, int h, int w, int Ttot, int frame0, void* stream);
 int fx_vae_avgdown_add(void* main_io, const void* x, int T, int H, int W, int Cin, int Cout, int ft, int fs, void* stream);
+/* Decode across the GPUs of one box (flexam_b200/dist.py SlabExchange; the reference decodes the whole clip on every rank,
+ * pipeline_wan2_2_fun_control_FlexAM.py:955-958): each rank owns a band of image rows of every padded grid
+ * [frames, Hp, Wp, C]. fx_vae_halo_push copies this rank's first / last interior row of frames [frame0, frame0+T) into the
+ * bottom halo row (Hp-1) of `up_grid` / the top halo row (0) of `dn_grid` — the same grid on the neighbouring ranks, peer
+ * memory; NULL = no neighbour (the image border keeps its zero padding). The caller orders it against the neighbours'
+ * reads (a stream barrier over the symmetric buffers). */
+int fx_vae_halo_push(const void* grid, void* up_grid, void* dn_grid, int frame0, int T, int Hp, int Wp, int C, void* stream);
 
 /* Small utility kernels used by the host glue. */
 int fx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);

@@ -471,6 +471,10 @@ def vae_dupup_add_(main, x, Tout, H, W, ft, drop):
     return main.copy_((main.float() + v).to(bf16))
 
 
+def vae_halo_push(grid, up_ptr, dn_ptr, frame0, T, Hp, Wp):
+    raise AssertionError("peer stores need CUDA symmetric memory: CPU tests use the point-to-point SlabExchange")
+
+
 def softmax_rows(s, p, scale):
     return p.copy_(F.softmax(s * scale, dim=-1).to(bf16))
 
@@ -500,7 +504,7 @@ def vae_avgdown_add_(main, x, T, H, W, ft, fs):
     return main.copy_((main.float() + _rb(v)).to(bf16))
 
 
-NAMES = ("vae_patchify", "vae_avgdown_add_", "vae_norm_act", "vae_upsample2x", "vae_time_interleave", "vae_dupup_add_", "softmax_rows", "vae_unpatchify",
+NAMES = ("vae_halo_push", "vae_patchify", "vae_avgdown_add_", "vae_norm_act", "vae_upsample2x", "vae_time_interleave", "vae_dupup_add_", "softmax_rows", "vae_unpatchify",
          "conv_gemm", "nchw_to_nhwc_padded", "embedding", "t5_layernorm", "t5_attention", "add_bf16_", "gated_gelu", "groupnorm_partials", "groupnorm_silu_partials", "linear_f32_tc", "dedup_f32", "fingerprint_table", "fingerprint", "gemm", "ln_modulate", "modulation_tables", "ln_scale_shift", "ln_affine", "rmsnorm_rope", "fmha", "patchify", "unpatchify", "sinusoid",
                  "linear_f32", "nchw_to_nhwc", "im2col3x3", "groupnorm_silu", "swap01", "cfg_euler_step", "add_", "sub", "split3", "join3",
                  "ln_f32", "rmsnorm_rope_f32", "gelu_f32_", "gated_residual_f32_", "attention_f32",

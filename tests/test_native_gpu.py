@@ -949,6 +949,84 @@ def test_vae_decode_real_width(dev):
     assert r_f < 1.5 * gap + 5e-3 and r_l < 1.5 * gap + 1e-2
 
 
+def test_vae_decode_in_row_bands_on_one_gpu(dev):
+    """flexam_b200.dist.SlabExchange with the real kernels: two engines in two threads on this GPU each decode one band of
+    image rows, boundary rows travel through fx_vae_halo_push into the other engine's grids (the peer-store path of the
+    multi-GPU decode with local peers), the attention block runs over the gathered frame. The clip must equal the
+    one-engine decode bit for bit. (The N-GPU form is measured by `bench.py --workload vae --gpus N`.)"""
+    import threading
+    from flexam_b200 import dist as fdist
+    from flexam_b200 import ops
+    from oracle import vae_oracle as V
+    m, cfg, sd = _vae_model("real", dev)
+    z = torch.from_numpy(V.latents(cfg, 3, 8, 12)).to(dev).bfloat16()
+    want = m.decode(z).sample
+    torch.cuda.synchronize()
+    world, shared, bar = 2, {}, threading.Barrier(2, timeout=300)
+
+    class ThreadSlab(fdist.SlabExchange):
+        def __init__(self, rank):
+            super().__init__(world, rank)
+            self.names, self.pushes = {}, 0
+
+        def alloc(self, name, rows, C, device):
+            t = torch.zeros((rows, C), dtype=torch.bfloat16, device=device)
+            shared[(name, self.rank)] = t
+            self.names[t.data_ptr()] = name
+            bar.wait()                               # every engine has (re)registered this grid
+            return t
+
+        def sync(self):
+            bar.wait()
+
+        def halo(self, grid, frame0, T, Hp, Wp):
+            name = self.names[grid.data_ptr()]
+            up = shared[(name, self.rank - 1)].data_ptr() if self.rank > 0 else 0
+            dn = shared[(name, self.rank + 1)].data_ptr() if self.rank + 1 < world else 0
+            ops.vae_halo_push(grid, up, dn, frame0, T, Hp, Wp)
+            self.pushes += 1
+            bar.wait()                               # both pushes are enqueued (one stream) before either convolution
+
+        def _gather(self, key, x):
+            shared[(key, self.rank)] = x
+            bar.wait()
+            parts = [shared[(key, r)] for r in range(world)]
+            out = torch.cat(parts, dim=0 if x.dim() == 2 else 2)
+            bar.wait()
+            return out
+
+        def gather_rows(self, x, out):
+            return out.copy_(self._gather("rows", x))
+
+        def gather_video(self, v):
+            return self._gather("video", v)
+
+    from flexam_b200.vae import VaeDecoderEngine
+    outs, errs = {}, []
+
+    def work(rank):
+        try:
+            torch.cuda.set_device(dev)
+            eng = VaeDecoderEngine(m.engine().params, m.cfg, dev)
+            eng.slab = ThreadSlab(rank)
+            outs[rank] = (eng.decode(z, m.scale), eng.slab.pushes, eng.decode(z, m.scale))
+        except BaseException as exc:  # noqa: BLE001
+            errs.append(exc)
+            bar.abort()
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(600)
+    torch.cuda.synchronize()
+    assert not errs, errs
+    for r in range(world):
+        got, pushes, again = outs[r]
+        assert got.shape == want.shape and pushes > 60
+        assert torch.equal(got, want) and torch.equal(again, want), (r, _rel(got, want))
+    print(f"slab decode, 2 bands on one GPU: bit-identical to the one-engine decode, {outs[0][1]} halo pushes per engine per decode x 2")
+
+
 def test_missing_extension_fails_loudly(monkeypatch):
     from flexam_b200 import lib
     monkeypatch.setattr(lib, "_lib", None)
