@@ -688,8 +688,9 @@ int fx::gemm_impl(const void* a, int64_t lda, const void* w, int64_t ldw, const 
                "fx_gemm_bf16: pointers must be 16-byte aligned");
   FX_CHECK_ARG(gate_e_stride % 4 == 0, "fx_gemm_bf16: gate_e_stride must be a multiple of 4");
 
-  // tile width: least padded N among {256,192,128,64}; ties go to the wider tile
-  const int cands[4] = {256, 192, 128, 64};
+  // tile width: least padded N among {256,192,160,128,64}; ties go to the wider tile (a 128 x 64 MMA is bound by the
+  // shared-memory reads of A, and every extra tile column re-reads the A panel: N = 320 runs as 2 x 160, not 5 x 64)
+  const int cands[5] = {256, 192, 160, 128, 64};
   int bn = 256, best = 1 << 30;
   for (int c : cands) {
     const int padded = (N + c - 1) / c * c;
@@ -766,6 +767,7 @@ int fx::gemm_impl(const void* a, int64_t lda, const void* w, int64_t ldw, const 
   switch (bn) {
     case 256: return dispatch_epi<256>(epilogue, ta, tb, tout, p, s);
     case 192: return dispatch_epi<192>(epilogue, ta, tb, tout, p, s);
+    case 160: return dispatch_epi<160>(epilogue, ta, tb, tout, p, s);
     case 128: return dispatch_epi<128>(epilogue, ta, tb, tout, p, s);
     default: return dispatch_epi<64>(epilogue, ta, tb, tout, p, s);
   }

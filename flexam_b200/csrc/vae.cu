@@ -110,22 +110,33 @@ __global__ void vae_time_interleave_kernel(const uint4* y, uint4* x, long long n
 
 // main[to][yo][xo][co] += x[(to + drop) / ft][yo / 2][xo / 2][(co * factor + a*4 + b*2 + d) / rep]   (DupUp3D :395-417)
 // with a = (to + drop) % ft, b = yo % 2, d = xo % 2, factor = 4 ft, rep = Cout * factor / Cin; bf16 add (:500).
-__global__ void vae_dupup_add_kernel(__nv_bfloat16* main, const __nv_bfloat16* x, long long nout, int H, int W, int Cin,
-                                     int Cout, int ft, int drop) {
+// One thread per 8 consecutive output channels (16-byte read-modify-write of main, the pixel decoded once per vector).
+__global__ void __launch_bounds__(256)
+vae_dupup_add_kernel(__nv_bfloat16* main, const __nv_bfloat16* x, long long nvec, int H, int W, int Cin, int Cout, int ft,
+                     int drop) {
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  const int H2 = 2 * H, W2 = 2 * W, factor = 4 * ft;
+  const int H2 = 2 * H, W2 = 2 * W, factor = 4 * ft, cvec = Cout / 8;
   const int rep = Cout * factor / Cin;
-  for (; i < nout; i += stride) {
-    const int co = static_cast<int>(i % Cout);
-    const long long pix = i / Cout;
+  for (; i < nvec; i += stride) {
+    const int co0 = static_cast<int>(i % cvec) * 8;
+    const long long pix = i / cvec;
     const int xo = static_cast<int>(pix % W2);
-    const int yo = static_cast<int>((pix / W2) % H2);
-    const long long to = pix / (static_cast<long long>(W2) * H2) + drop;
-    const int a = static_cast<int>(to % ft);
-    const int ci = (co * factor + a * 4 + (yo & 1) * 2 + (xo & 1)) / rep;
-    const float v = __bfloat162float(x[(((to / ft) * H + (yo >> 1)) * W + (xo >> 1)) * Cin + ci]);
-    main[i] = __float2bfloat16_rn(__bfloat162float(main[i]) + v);
+    const long long rest = pix / W2;
+    const int yo = static_cast<int>(rest % H2);
+    const long long to = rest / H2 + drop;
+    const int off = static_cast<int>(to % ft) * 4 + (yo & 1) * 2 + (xo & 1);
+    const __nv_bfloat16* xr = x + (((to / ft) * H + (yo >> 1)) * W + (xo >> 1)) * Cin;
+    uint4* mp = reinterpret_cast<uint4*>(main + pix * Cout + co0);
+    uint4 m = *mp;
+    uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = bf16_lo(mw[j]) + __bfloat162float(xr[((co0 + 2 * j) * factor + off) / rep]);
+      const float b = bf16_hi(mw[j]) + __bfloat162float(xr[((co0 + 2 * j + 1) * factor + off) / rep]);
+      mw[j] = pack_bf16x2(a, b);
+    }
+    *mp = make_uint4(mw[0], mw[1], mw[2], mw[3]);
   }
 }
 
@@ -301,11 +312,12 @@ extern "C" int fx_vae_dupup_add(void* main_io, const void* x, int Tout, int H, i
                                 void* stream) {
   using namespace fx;
   FX_CHECK_ARG(main_io && x && Tout > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (ft == 1 || ft == 2) && drop >= 0 &&
-                   drop < ft && (Cout * 4 * ft) % Cin == 0,
+                   drop < ft && (Cout * 4 * ft) % Cin == 0 && Cout % 8 == 0 &&
+                   reinterpret_cast<uintptr_t>(main_io) % 16 == 0,
                "fx_vae_dupup_add: bad arguments");
-  const long long nout = 4LL * Tout * H * W * Cout;
-  vae_dupup_add_kernel<<<vae_grid(nout), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<__nv_bfloat16*>(main_io), reinterpret_cast<const __nv_bfloat16*>(x), nout, H, W, Cin, Cout, ft,
+  const long long nvec = 4LL * Tout * H * W * (Cout / 8);
+  vae_dupup_add_kernel<<<vae_grid(nvec), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(main_io), reinterpret_cast<const __nv_bfloat16*>(x), nvec, H, W, Cin, Cout, ft,
       drop);
   FX_CHECK_LAUNCH("fx_vae_dupup_add");
   return FX_OK;
