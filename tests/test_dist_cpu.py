@@ -247,28 +247,30 @@ def _slab_worker(rank, world, port, q):
         m = AutoencoderKLWan3_8(latent_channels=cfg["z_dim"], c_dim=cfg["enc_dim"], dec_dim=cfg["dec_dim"], device="cpu")
         sd = {**V.encoder_state_dict(cfg), **V.state_dict(cfg)}
         m.load_state_dict({"model." + k: torch.from_numpy(v).bfloat16() for k, v in sd.items()}, strict=True)
-        z = torch.from_numpy(V.latents(cfg, 3, 4, 3)).bfloat16()
+        z = torch.from_numpy(V.latents(cfg, 3, 2 * world, 3)).bfloat16()
         want = m.decode(z).sample
         ex = m.enable_multi_gpus_inference()
         got = m.decode(z).sample
         again = m.decode(z).sample                      # history grids are cleared between clips
-        odd = m.decode(z[:, :, :, :3]).sample           # 3 rows over 2 ranks: replicated fallback
+        odd = m.decode(z[:, :, :, :world + 1]).sample   # world + 1 rows do not divide: replicated fallback
         q.put((rank, tuple(got.shape), torch.equal(got, want), torch.equal(again, want), ex.exchanges,
                tuple(odd.shape)))
     finally:
         dist.destroy_process_group()
 
 
-def test_vae_decode_in_row_bands_is_bit_identical():
+@pytest.mark.parametrize("world", [2, 3])
+def test_vae_decode_in_row_bands_is_bit_identical(world):
+    """world = 3: the middle rank exchanges halo rows with both neighbours."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_slab_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(timeout=600)
         assert p.exitcode == 0
-    for rank, shape, same, same2, exchanges, odd_shape in sorted(q.get(timeout=10) for _ in range(2)):
-        assert shape == (1, 3, 9, 64, 48) and same and same2, (rank, shape, same, same2)
-        assert exchanges > 0 and odd_shape == (1, 3, 9, 48, 48), (exchanges, odd_shape)
+    for rank, shape, same, same2, exchanges, odd_shape in sorted(q.get(timeout=10) for _ in range(world)):
+        assert shape == (1, 3, 9, 32 * world, 48) and same and same2, (rank, shape, same, same2)
+        assert exchanges > 0 and odd_shape == (1, 3, 9, 16 * (world + 1), 48), (exchanges, odd_shape)
