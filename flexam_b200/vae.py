@@ -1,16 +1,17 @@
 """Wan2.2 VAE (decoder and encoder) on the native kernels.
 
 ``AutoencoderKLWan3_8`` mirrors the reference wrapper (FlexAM/models/wan_vae3_8.py:892-1057, cited as :line) for what the
-pipeline's last step calls — ``vae.decode(latents).sample`` — with the reference's parameter names for ``model.conv2.*``
-and ``model.decoder.*``. The forward is ``VaeDecoderEngine.decode``: the reference's frame-by-frame loop with its
-per-convolution feature cache (:820-849), every convolution an implicit GEMM on the tcgen05 kernels
+pipeline calls — ``vae.encode(x).latent_dist`` and ``vae.decode(latents).sample`` — with the reference's parameter names
+(``model.encoder.*``, ``model.conv1.*``, ``model.conv2.*``, ``model.decoder.*``). The forward is
+``VaeDecoderEngine.decode``: the reference's frame-by-frame loop with its per-convolution feature cache (:820-849), every convolution an implicit GEMM on the tcgen05 kernels
 (``fx_conv_gemm_bf16``: causal 3x3x3, per-frame 3x3, (3,1,1) time convolution; 1x1 as plain GEMMs) reading zero-padded
 channel-last grids whose first two frames are the causal history, and the element-wise work between them (RMS_norm + SiLU,
 nearest 2x, temporal interleave, DupUp3D shortcut, residual adds, the attention block's softmax, unpatchify + clamp) as
 row kernels (csrc/vae.cu). ``encode`` (:788-819) is the mirror image: patchify, first frame alone then four frames per chunk
 through Encoder3d (:564-618) — the same residual / attention blocks, the stride-2 convolutions of ``Resample`` downsample2d /
 downsample3d as the stride forms of the implicit GEMM, AvgDown3D shortcuts — and ``conv1`` with the latent normalisation
-folded in. No torch compute, no CPU fallback.
+folded in. With a ``flexam_b200.dist.SlabExchange`` attached the decode runs on one band of image rows per rank (halo rows
+exchanged per 3x3 convolution). No torch compute, no CPU fallback.
 """
 from __future__ import annotations
 
@@ -554,9 +555,10 @@ WAN22_LATENTS_STD = [
 
 
 class AutoencoderKLWan3_8(nn.Module):
-    """Drop-in for the DECODE side of FlexAM.models.AutoencoderKLWan3_8 (:892-1057): ``decode(z).sample``. Parameters
-    carry the reference's names under ``model.`` (``model.encoder.*``, ``model.conv1.*``, ``model.conv2.*``,
-    ``model.decoder.*``): the reference checkpoint loads strictly. ``encode(x).latent_dist`` / ``decode(z).sample``."""
+    """Drop-in for FlexAM.models.AutoencoderKLWan3_8 (:892-1057) as the pipeline uses it: ``encode(x).latent_dist``
+    (``.mode()`` / ``.sample()``) and ``decode(z).sample``. Parameters carry the reference's names under ``model.``
+    (``model.encoder.*``, ``model.conv1.*``, ``model.conv2.*``, ``model.decoder.*``): the reference checkpoint loads
+    strictly. ``enable_multi_gpus_inference()`` splits the decode over the ranks of a box (not in the reference)."""
 
     def __init__(self, latent_channels=48, c_dim=160, vae_pth=None, dim_mult=(1, 2, 4, 4),
                  temperal_downsample=(False, True, True), temporal_compression_ratio=4, spatial_compression_ratio=8,
