@@ -864,6 +864,12 @@ def run_loop(args):
     ts, sig = flow_match_euler_schedule(n, 5.0)
 
     def one_loop():
+        # TeaCache / cfg_skip as the reference pipeline enables them (:843-846; ComfyUI turns TeaCache on by default):
+        # re-armed per video; the rescaling polynomial is the identity so the threshold reads as accumulated relative L1
+        if args.teacache > 0:
+            model.enable_teacache([1.0, 0.0], n, args.teacache, num_skip_start_steps=5, offload=False)
+        if args.cfg_skip > 0:
+            model.enable_cfg_skip(args.cfg_skip, n)
         loop = DenoiseLoop(model, to(lat), to(mask), to(masked_video), to(mask_lat), to(control), to(add), to(ref),
                            [to(u) for u in neg], [to(u) for u in pos], density=0.1, guidance_scale=6.0,
                            graph=args.graph and world == 1)
@@ -893,6 +899,12 @@ def run_loop(args):
             "loop_seconds": ms / 1e3, "ms_per_step": ms / n, "steps_per_s": n * 1e3 / ms,
             "host_enqueue_seconds": host_s, "device_to_host_reads_per_loop": loop.host_reads,
             "cuda_graph_replays": loop.graph_replays, "launches_outside_transformer": loop.launches,
+            "teacache": None if args.teacache <= 0 else {
+                "rel_l1_thresh": args.teacache, "num_skip_start_steps": 5, "coefficients": [1.0, 0.0],
+                "steps_that_ran_the_blocks": int(sum(loop.decisions)), "steps": len(loop.decisions),
+                "rel_l1_distance_min_median_max": [sorted(loop.teacache_distances[1:])[i] for i in
+                                                   (0, (len(loop.teacache_distances) - 1) // 2, -1)]},
+            "cfg_skip_ratio": args.cfg_skip if args.cfg_skip > 0 else None,
             "parity": {"checksum_sha256_16": output_checksum(out), "finite": bool(torch.isfinite(out.float()).all().item()),
                        "note": "final latents; equal across N iff bit-identical"}}))
     if world > 1:
@@ -1035,6 +1047,8 @@ if __name__ == "__main__":
                     "around every launch, 3 extra steps outside the timed regions)")
     ap.add_argument("--loop-steps", type=int, default=50, help="sampling steps of --workload loop50")
     ap.add_argument("--graph", action="store_true", help="loop50: replay the transformer call from CUDA graphs (N = 1)")
+    ap.add_argument("--teacache", type=float, default=0.0, help="loop50: TeaCache rel-L1 threshold (0 = off)")
+    ap.add_argument("--cfg-skip", type=float, default=0.0, help="loop50: cfg_skip_ratio (0 = off)")
     ap.add_argument("--vae-frames", type=int, default=0, help="--workload vae: latent frames (default: the clip's 25)")
     ap.add_argument("--workload", default="config2", choices=["config2", "long", "loop50", "t5", "vae", "video"],
                     help="config2 = the metric's workload (default); long = BASELINE config 5, 193 frames 704x1280 "

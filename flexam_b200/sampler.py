@@ -100,6 +100,7 @@ class DenoiseLoop:
         self.use_graph = bool(graph)
         self._graphs = {}            # (batch, run_blocks) -> [occurrences, CUDAGraph | None, static output]
         self.graph_replays = 0
+        self.teacache_distances: List[float] = []
         self.decisions: List[bool] = []   # per step: did the block stack run (False = TeaCache re-applied the residual)
 
     def _engine(self):
@@ -125,6 +126,7 @@ class DenoiseLoop:
             e0p = torch.cat([e0[:1], e0])
         d = ((e0p[1:] - e0p[:-1]).abs().mean(dim=1) / e0p[:-1].abs().mean(dim=1)).tolist()          # the one read-back
         self.host_reads += 1
+        self.teacache_distances = d            # relative L1 distance of consecutive steps' modulated inputs (diagnostics)
         acc, cnt, out = float(tc.accumulated_rel_l1_distance), int(tc.cnt), []
         for i in range(n):
             if cnt < tc.num_skip_start_steps:
