@@ -34,7 +34,7 @@ def test_committed_bench_lines_follow_the_contract():
     root = os.path.join(os.path.dirname(os.path.abspath(bench.__file__)), "profiles")
     for name, n in (("bench_r1l.json", 1), ("bench_r1t_n2.json", 2), ("bench_r1o_n4.json", 4), ("bench_r1p_n8.json", 8),
                     ("bench_r2b.json", 1), ("bench_r2c_cfg2.json", 2), ("bench_r2c_sp2.json", 2), ("bench_r2d_n8.json", 8),
-                    ("bench_r2s.json", 1), ("bench_r2g_sp2.json", 2), ("bench_r2m_n4.json", 4), ("bench_r2l_n8.json", 8)):
+                    ("bench_r2s.json", 1), ("bench_r2g_sp2.json", 2), ("bench_r2x_n2.json", 2), ("bench_r2m_n4.json", 4), ("bench_r2l_n8.json", 8)):
         text = open(os.path.join(root, name)).read().strip().splitlines()[-1]
         d = json.loads(text)
         for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -50,7 +50,7 @@ def test_committed_bench_lines_follow_the_contract():
             assert d["parity"]["ok"] and d["parity"]["rel_l2_vs_oracle"] <= 1e-2
             # the control fuser's implicit-GEMM convolution (run G onwards) sums its K range tap-major: new checksum, again
             # the same at every N
-            final = name in ("bench_r2s.json", "bench_r2g_sp2.json", "bench_r2m_n4.json", "bench_r2l_n8.json")
+            final = name in ("bench_r2s.json", "bench_r2g_sp2.json", "bench_r2x_n2.json", "bench_r2m_n4.json", "bench_r2l_n8.json")
             assert d["parity"]["checksum_sha256_16"] == ("66064cea93a14880" if final else "219599d7e176cae3")
             if n == 1:
                 assert d["library_baseline"]["ms_per_step"] > d["ms_per_step"] and d["cpu_baseline"]["config1_forward"]["finite"]
