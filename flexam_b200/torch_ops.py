@@ -16,7 +16,6 @@ from __future__ import annotations
 
 from typing import List, Optional
 
-import torch
 from torch import Tensor
 from torch.library import custom_op
 

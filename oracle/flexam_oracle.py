@@ -21,7 +21,6 @@ Precision policies
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, List, Optional, Sequence
 
 import torch
