@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <unordered_map>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -108,8 +109,42 @@ bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t
   return make_tmap(out, false, base, rank, dims, strides_bytes, box);
 }
 
+// Descriptor cache: a tensor map is a pure function of (type, base address, geometry, box), and a forward pass asks for the
+// same few hundred of them every step (weights, persistent workspaces), so the driver call (~1 us, four per GEMM launch)
+// is made once per distinct descriptor and thread. Entries never go stale — nothing in the key can change meaning — and
+// the table is simply dropped when it grows past kTmapCacheMax (workspaces re-allocated at new addresses).
+namespace {
+struct TmapKey {
+  uint64_t v[16];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.v) h = (h ^ x) * 1099511628211ull;
+    return static_cast<size_t>(h ^ (h >> 29));
+  }
+};
+constexpr size_t kTmapCacheMax = 16384;
+}  // namespace
+
 bool make_tmap(CUtensorMap* out, bool is_f32, const void* base, int rank, const uint64_t* dims,
                const uint64_t* strides_bytes, const uint32_t* box) {
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{};
+  const bool cacheable = rank >= 1 && rank <= 4;
+  if (cacheable) {
+    key.v[0] = reinterpret_cast<uint64_t>(base);
+    key.v[1] = (static_cast<uint64_t>(rank) << 1) | (is_f32 ? 1u : 0u);
+    for (int i = 0; i < rank; ++i) key.v[2 + i] = dims[i];
+    for (int i = 0; i + 1 < rank; ++i) key.v[6 + i] = strides_bytes[i];
+    for (int i = 0; i < rank; ++i) key.v[10 + i] = box[i];
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return true;
+    }
+  }
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return false;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -123,6 +158,10 @@ bool make_tmap(CUtensorMap* out, bool is_f32, const void* base, int rank, const 
               static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
               (unsigned long long)strides_bytes[0], box[0], box[1]);
     return false;
+  }
+  if (cacheable) {
+    if (cache.size() >= kTmapCacheMax) cache.clear();
+    cache.emplace(key, *out);
   }
   return true;
 }
