@@ -129,6 +129,7 @@ class VaeDecoderEngine:
                 raise FlexamNativeError(f"native VAE: channel widths must be multiples of 8, got {c}")
         self._ws: Dict[tuple, torch.Tensor] = {}
         self._hist: Dict[str, torch.Tensor] = {}
+        self._geom: Dict[str, tuple] = {}
         self.launches = 0
         self.slab = None            # flexam_b200.dist.SlabExchange: decode split into bands of image rows across the ranks
         self._slab_on = False
@@ -203,12 +204,16 @@ class VaeDecoderEngine:
         need = frames * Hp * Wp
         key = ("slab:" if self._slab_on else "") + name       # band-sized, peer-mapped grids live next to the full-size ones
         t = self._hist.get(key)
+        same_plane = self._geom.get(key) == (Hp, Wp)
+        self._geom[key] = (Hp, Wp)
         if t is None or t.shape[0] < need or t.shape[1] != C:
             if self._slab_on:
                 new = self.slab.alloc(key, need, C, self.device)       # zeroed; collective (every rank grows the same grid)
             else:
                 new = torch.zeros((need, C), dtype=bf16, device=self.device)
-            if t is not None and t.shape[1] == C and keep_rows:
+            # the history travels only when the grid grows inside one clip (same plane geometry); a grid left over from a
+            # clip of another size starts from zeros (decode / encode cleared it anyway)
+            if t is not None and t.shape[1] == C and keep_rows and same_plane and t.shape[0] >= keep_rows:
                 new[:keep_rows].copy_(t[:keep_rows])
             self._hist[key] = t = new
         return t

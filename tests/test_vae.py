@@ -104,6 +104,37 @@ def test_vae_decoder_host_logic_matches_oracle(monkeypatch, golden_dir):
     assert r_o < 2.5e-2 and r_g < 3e-2
 
 
+def test_vae_single_frame_and_ragged_shapes(monkeypatch):
+    """Edge cases of the chunk loops: a single latent frame / a single image (only the first, not time-resampled chunk
+    runs), a non-square odd-sized latent grid, and inputs the reference rejects too (frame counts that are not 1 + 4k)."""
+    from flexam_b200.lib import FlexamNativeError
+    from flexam_b200.vae import AutoencoderKLWan3_8
+    cpu_ops_emul.install(monkeypatch)
+    cfg = V.VAE_CONFIGS["tiny"]
+    scale = V.latent_scale(cfg)
+    m = AutoencoderKLWan3_8(latent_channels=cfg["z_dim"], c_dim=cfg["enc_dim"], dec_dim=cfg["dec_dim"],
+                            dim_mult=cfg["dim_mult"], temperal_downsample=cfg["temperal_downsample"],
+                            latents_mean=scale[0], latents_std=1.0 / scale[1], device="cpu")
+    np_sd = _full_sd(cfg)
+    sd = {k: torch.from_numpy(v) for k, v in np_sd.items()}
+    m.load_state_dict({"model." + k: v.bfloat16() for k, v in sd.items()}, strict=True)
+    for T, H, W in ((1, 2, 3), (2, 3, 5)):
+        z = torch.from_numpy(V.latents(cfg, T, H, W, tag=f"edge{T}"))
+        out = m.decode(z.bfloat16()).sample
+        want = V.decode(sd, cfg, z, m.scale, policy="bf16")
+        assert out.shape == want.shape == (1, 3, 1 + 4 * (T - 1), 16 * H, 16 * W) and _rel(out, want) < 2.5e-2
+    x = torch.from_numpy(V.video(cfg, 1, 32, 48, tag="edge_img"))
+    enc = m.encode(x.bfloat16()).latent_dist.parameters
+    want = V.encode(sd, cfg, x, m.scale, policy="bf16")
+    assert enc.shape == want.shape == (1, 2 * cfg["z_dim"], 1, 2, 3) and _rel(enc, want) < 2.5e-2
+    with pytest.raises(FlexamNativeError):
+        m.encode(torch.zeros(1, 3, 4, 32, 48, dtype=torch.bfloat16))          # 4 frames: not 1 + 4k
+    with pytest.raises(FlexamNativeError):
+        m.encode(torch.zeros(1, 3, 5, 40, 48, dtype=torch.bfloat16))          # height not a multiple of 16
+    with pytest.raises(FlexamNativeError):
+        m.decode(torch.zeros(1, cfg["z_dim"] + 1, 1, 2, 3, dtype=torch.bfloat16))
+
+
 def test_vae_from_pretrained_and_latent_statistics(tmp_path):
     """The wrapper loader (:1058-1079: inner-model checkpoint, keys prefixed with `model.`) and the Wan2.2 latent
     statistics the wrapper carries by default (:906-1008)."""
