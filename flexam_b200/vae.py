@@ -288,21 +288,25 @@ class VaeDecoderEngine:
             self.launches += 1
             return y[ex.rank * P:(ex.rank + 1) * P]
         out = self._buf("attn_out", (T * P, C))
+        # the score / probability matrices are GEMM operands: their key dimension is padded to a multiple of 8 (zero K and
+        # V rows, zero probabilities; the softmax runs over the P real keys only). No effect when H * W % 8 == 0.
+        Pp = -(-P // 8) * 8
+        pad = Pp != P
         for f in range(T):
             xf = x[f * P:(f + 1) * P]
             y = self._buf("attn_norm", (P, C))
             ops.vae_norm_act(xf, self.gamma[name + ".norm"], y, H, W, 0, 0, False)
-            qk = self._buf("attn_qk", (P, 2 * C))
-            v = self._buf("attn_v", (P, C))
+            qk = self._buf("attn_qk", (Pp, 2 * C), zero=pad)
+            v = self._buf("attn_v", (Pp, C), zero=pad)
             w_qk, b_qk, w_v, b_v = self.attn_w[name]
-            ops.gemm(y, w_qk, b_qk, qk, FX_EPI_BF16)
-            ops.gemm(y, w_v, b_v, v, FX_EPI_BF16)
-            s = self._buf("attn_s", (P, P), f32)
-            ops.gemm(qk[:, :C], qk[:, C:], None, s, FX_EPI_F32_EXACT)
-            p = self._buf("attn_p", (P, P))
-            ops.softmax_rows(s, p, 1.0 / math.sqrt(C))
-            vt = self._buf("attn_vt", (C, P))
-            ops.nchw_to_nhwc(v, vt, 0)                                    # [P, C] -> [C, P]
+            ops.gemm(y, w_qk, b_qk, qk[:P], FX_EPI_BF16)
+            ops.gemm(y, w_v, b_v, v[:P], FX_EPI_BF16)
+            s = self._buf("attn_s", (P, Pp), f32)
+            ops.gemm(qk[:P, :C], qk[:, C:], None, s, FX_EPI_F32_EXACT)
+            p = self._buf("attn_p", (P, Pp), zero=pad)
+            ops.softmax_rows(s[:, :P], p[:, :P], 1.0 / math.sqrt(C))
+            vt = self._buf("attn_vt", (C, Pp))
+            ops.nchw_to_nhwc(v, vt, 0)                                    # [Pp, C] -> [C, Pp]
             o = self._buf("attn_o", (P, C))
             ops.gemm(p, vt, None, o, FX_EPI_BF16)
             of = out[f * P:(f + 1) * P]

@@ -324,3 +324,30 @@ def test_weight_edits_are_picked_up(monkeypatch):
     assert torch.equal(got4, call(f, inp)[0]) and not torch.equal(got4, got3)
     fx.refresh(m)                                               # explicit form still works
     assert torch.equal(call(m, inp)[0], got4)
+
+
+def test_engine_edge_shapes_on_one_engine(monkeypatch):
+    """One engine, consecutive calls with different latent grids, batch sizes and prompt lengths — including a single
+    latent frame, a batch of one, a batch of three, prompts of length 1 and of the full text_len — each against the
+    oracle. Workspaces, RoPE position tables and the step-invariant caches are keyed by shape / content, so no call may
+    see state left by another."""
+    cpu_ops_emul.install(monkeypatch)
+    cfg = synth.CONFIGS["tiny"]
+    m, np_sd = build(cfg)
+    sd = O.to_torch_sd(np_sd)
+    cases = [dict(F=3, H=8, W=12, B=2, prompt_lens=(37, 120)),
+             dict(F=1, H=4, W=6, B=2, prompt_lens=(1, cfg["text_len"])),      # one latent frame (an image)
+             dict(F=5, H=4, W=4, B=1, prompt_lens=(9,)),                      # no CFG batch
+             dict(F=2, H=6, W=4, B=3, prompt_lens=(5, 6, 7)),                 # more than two samples
+             dict(F=3, H=8, W=12, B=2, prompt_lens=(37, 120))]                # the first shape again, after the others
+    outs = []
+    for i, c in enumerate(cases):
+        inp = synth.inputs(cfg, c["F"], c["H"], c["W"], B=c["B"], prompt_lens=c["prompt_lens"],
+                           tag="in" if i in (0, 4) else f"edge{i}")
+        out, tt, ctx = call(m, inp)
+        want = O.forward(sd, cfg, tt["x"], tt["t"], ctx, inp["seq_len"], tt["y"], tt["full_ref"],
+                         tt["additional_control"], tt["density"], policy="bf16")
+        assert out.shape == want.shape == (c["B"], cfg["out_dim"], c["F"], c["H"], c["W"]), (i, out.shape)
+        assert torch.isfinite(out.float()).all() and rel(out, want) < 4e-3, (i, rel(out, want))
+        outs.append(out)
+    assert torch.equal(outs[0], outs[4])

@@ -1027,6 +1027,68 @@ def test_vae_decode_in_row_bands_on_one_gpu(dev):
     print(f"slab decode, 2 bands on one GPU: bit-identical to the one-engine decode, {outs[0][1]} halo pushes per engine per decode x 2")
 
 
+def test_edge_shapes_on_one_engine(dev):
+    """Real kernels, ONE engine per model, consecutive calls with different shapes, each against the oracle run on the GPU:
+    DiT — one latent frame, batch of one (no CFG), batch of three, one-token and full-length prompts, the first shape
+    again; umT5 — sequence lengths that are no multiple of any tile, one and three prompts; VAE — one latent frame, odd
+    non-square grids, a single image through the encoder, a bigger clip after a smaller one (the history grids of one
+    clip must not leak into the next)."""
+    from oracle import flexam_oracle as O
+    from oracle import synth
+    from oracle import t5_oracle as T
+    from oracle import vae_oracle as V
+    model, cfg = _native_model("tiny", dev)
+    sd = synth.state_dict_torch(cfg, dev)
+    cases = [dict(F=3, H=8, W=12, B=2, prompt_lens=(37, 120)), dict(F=1, H=4, W=6, B=2, prompt_lens=(1, cfg["text_len"])),
+             dict(F=5, H=4, W=4, B=1, prompt_lens=(9,)), dict(F=2, H=6, W=4, B=3, prompt_lens=(5, 6, 7)),
+             dict(F=3, H=8, W=12, B=2, prompt_lens=(37, 120))]
+    outs = []
+    for i, c in enumerate(cases):
+        inp = synth.inputs(cfg, c["F"], c["H"], c["W"], B=c["B"], prompt_lens=c["prompt_lens"],
+                           tag="in" if i in (0, 4) else f"edge{i}")
+        tt = {k: torch.from_numpy(inp[k]).to(dev) for k in ("x", "y", "additional_control", "full_ref", "t", "density")}
+        ctx = [torch.from_numpy(u).to(dev) for u in inp["context"]]
+        out = model(x=tt["x"].bfloat16(), t=tt["t"], context=[u.bfloat16() for u in ctx], seq_len=inp["seq_len"],
+                    y=tt["y"].bfloat16(), full_ref=tt["full_ref"].bfloat16(),
+                    additional_control=tt["additional_control"].bfloat16(), density=tt["density"])
+        want = O.forward(sd, cfg, tt["x"], tt["t"], ctx, inp["seq_len"], tt["y"], tt["full_ref"], tt["additional_control"],
+                         tt["density"], policy="bf16")
+        assert out.shape == want.shape and torch.isfinite(out.float()).all() and _rel(out, want) < BF16_GATE, (i, _rel(out, want))
+        outs.append(out.clone())
+    assert torch.equal(outs[0], outs[4])
+    # umT5
+    m5, tcfg = _t5_model("tiny", dev)
+    sd5 = {k: v.float() for k, v in m5.state_dict().items()}
+    first = None
+    for L, lens in ((24, (7, 24)), (17, (17,)), (200, (1, 200, 13)), (24, (7, 24))):
+        ids, mask = T.inputs(tcfg, L=L, lens=lens)
+        ids, mask = torch.from_numpy(ids).to(dev), torch.from_numpy(mask).to(dev)
+        out = m5(ids, mask)[0]
+        want = T.forward(sd5, tcfg, ids, mask, policy="bf16")
+        assert out.shape == want.shape and torch.isfinite(out.float()).all() and _rel(out, want) < BF16_GATE, (L, lens)
+        first = out.clone() if first is None else first
+    assert torch.equal(out, first)
+    # VAE
+    mv, vcfg, sdv = _vae_model("tiny", dev)
+    sdf = {k: v.float() for k, v in sdv.items()}
+    first = None
+    for T_, H, W in ((1, 2, 3), (2, 3, 5), (3, 4, 6), (1, 2, 3)):
+        z = torch.from_numpy(V.latents(vcfg, T_, H, W, tag=f"edge{T_}{H}{W}")).to(dev)
+        out = mv.decode(z.bfloat16()).sample
+        fp32 = V.decode(sdf, vcfg, z, mv.scale)
+        lib_out = V.decode(sdv, vcfg, z.bfloat16(), mv.scale).float()
+        assert out.shape == fp32.shape == (1, 3, 1 + 4 * (T_ - 1), 16 * H, 16 * W)
+        assert _rel(out, fp32) < 1.5 * _rel(lib_out, fp32) + 5e-3, (T_, H, W, _rel(out, fp32), _rel(lib_out, fp32))
+        first = out.clone() if first is None else first
+    assert torch.equal(out, first)
+    x = torch.from_numpy(V.video(vcfg, 1, 32, 48, tag="edge_img")).to(dev)
+    enc = mv.encode(x.bfloat16()).latent_dist.parameters
+    fp32 = V.encode(sdf, vcfg, x, mv.scale)
+    lib_enc = V.encode(sdv, vcfg, x.bfloat16(), mv.scale).float()
+    assert enc.shape == fp32.shape == (1, 2 * vcfg["z_dim"], 1, 2, 3)
+    assert _rel(enc, fp32) < 1.5 * _rel(lib_enc, fp32) + 5e-3
+
+
 def test_missing_extension_fails_loudly(monkeypatch):
     from flexam_b200 import lib
     monkeypatch.setattr(lib, "_lib", None)

@@ -89,6 +89,28 @@ def test_t5_engine_host_logic_matches_oracle(monkeypatch, golden_dir):
     assert _rel(nomask, T.forward({k: torch.from_numpy(v) for k, v in np_sd.items()}, cfg, ids, None, policy="bf16")) < 5e-3
 
 
+def test_t5_engine_edge_shapes_on_one_engine(monkeypatch):
+    """One encoder, consecutive calls with different batch sizes and sequence lengths (a single prompt, a one-token
+    prompt next to a full-length one, a length that is not a multiple of any tile), each against the oracle."""
+    from flexam_b200.text_encoder import WanT5EncoderModel
+    cpu_ops_emul.install(monkeypatch)
+    cfg = T.T5_CONFIGS["tiny"]
+    m = WanT5EncoderModel(**cfg, device="cpu")
+    np_sd = T.state_dict(cfg)
+    sd = {k: torch.from_numpy(v) for k, v in np_sd.items()}
+    m.load_state_dict({k: v.bfloat16() for k, v in sd.items()}, strict=True)
+    first = None
+    for L, lens in ((24, (7, 24)), (17, (17,)), (40, (1, 40, 13)), (24, (7, 24))):
+        ids, mask = T.inputs(cfg, L=L, lens=lens)
+        ids, mask = torch.from_numpy(ids), torch.from_numpy(mask)
+        out = m(ids, mask)[0]
+        want = T.forward(sd, cfg, ids, mask, policy="bf16")
+        assert out.shape == want.shape == (len(lens), L, cfg["dim"]) and _rel(out, want) < 5e-3, (L, lens)
+        if first is None:
+            first = out.clone()
+    assert torch.equal(out, first)                       # the first shape again, after the others
+
+
 def test_t5_from_pretrained_follows_the_reference_contract(tmp_path):
     """.safetensors and torch.save checkpoints, kwargs filtered from the yaml's text_encoder_kwargs (which also carries
     tokenizer entries), non-strict load, dtype cast (reference :306-393)."""
