@@ -351,3 +351,51 @@ def test_engine_edge_shapes_on_one_engine(monkeypatch):
         assert torch.isfinite(out.float()).all() and rel(out, want) < 4e-3, (i, rel(out, want))
         outs.append(out)
     assert torch.equal(outs[0], outs[4])
+
+
+@pytest.mark.parametrize("kind", ["fg_bg", "no_pin"])
+def test_sampling_loop_with_other_masks(monkeypatch, kind):
+    """DenoiseLoop beyond the full_edit fixture, 4 Euler steps against the restated pipeline loop (oracle/sampler_oracle.py)
+    around the bf16-policy oracle forward: `fg_bg` — first frame pinned, the rest a fractional (trilinear-like) mask, so
+    most tokens carry their own timestep (pipeline :686-690, :891-898) and the per-token time MLP path runs inside the
+    loop; `no_pin` — the first latent frame is not fully masked out, so the loop must NOT re-pin it (:933)."""
+    from flexam_b200.sampler import DenoiseLoop
+    from oracle import make_golden, sampler_oracle
+    cpu_ops_emul.install(monkeypatch)
+    cfg = synth.CONFIGS["tiny"]
+    m, np_sd = build(cfg)
+    sd = O.to_torch_sd(np_sd)
+    F, H, W = 3, 8, 12
+    lt = make_golden.loop_tensors(cfg, F, H, W)
+    mask = torch.ones(1, 1, F, H, W)
+    if kind == "fg_bg":
+        ramp = torch.linspace(0, 1, W).view(1, 1, 1, 1, W) * torch.linspace(0.2, 1, H).view(1, 1, 1, H, 1)
+        mask = (mask * ramp).bfloat16().float()
+        mask[:, :, 0] = 0
+    else:
+        mask[:, :, 0, : H // 2] = 0                                      # half of the first frame stays editable
+    lt["mask"] = mask
+    lt["mask_latents"] = (1 - mask).expand(1, 4, F, H, W).contiguous()
+    ts, sig = sampler_oracle.euler_schedule(4, 5.0)
+    ts = synth.to_bf16_f32(ts)
+    sig = np.concatenate([ts / np.float32(1000.0), np.zeros(1, np.float32)]).astype(np.float32)
+
+    def oracle_loop(policy, dtype):
+        def fn(x, context, t, density, seq_len, y, full_ref, additional_control):
+            return O.forward(sd, cfg, x.float(), t.float(), [c.float() for c in context], seq_len, y.float(),
+                             full_ref.float(), additional_control.float(), density.float(), policy=policy)
+        return sampler_oracle.denoise_loop(fn, density=0.1, guidance_scale=6.0, timesteps=ts, sigmas=sig,
+                                           set_step=lambda i, n: None, dtype=dtype, **lt)
+    want, exact = oracle_loop("bf16", torch.bfloat16), oracle_loop("fp32", torch.float32)
+    loop = DenoiseLoop(m, lt["latents"], lt["mask"], lt["masked_video_latents"], lt["mask_latents"],
+                       lt["control_video_latents"], lt["additional_control"], lt["ref_image_latents"],
+                       lt["negative_prompt_embeds"], lt["prompt_embeds"], density=0.1, guidance_scale=6.0)
+    out = loop.run(ts, sig)
+    assert loop.repin == (kind == "fg_bg")
+    assert out.shape == want.shape and torch.isfinite(out.float()).all()
+    # 4 guided steps of two different bf16 emulations (nothing pinned in `no_pin`: every token accumulates the noise):
+    # the native loop must sit as close to the fp32 loop as the bf16-policy oracle loop does
+    gap = rel(want, exact)
+    assert rel(out, exact) < 1.25 * gap + 2e-3 and rel(out, want) < 2 * gap + 2e-3, (rel(out, exact), rel(out, want), gap)
+    if kind == "fg_bg":
+        assert torch.equal(out[:, :, 0].float(), lt["masked_video_latents"][:, :, 0].bfloat16().float())
