@@ -1056,6 +1056,20 @@ def test_edge_shapes_on_one_engine(dev):
         assert out.shape == want.shape and torch.isfinite(out.float()).all() and _rel(out, want) < BF16_GATE, (i, _rel(out, want))
         outs.append(out.clone())
     assert torch.equal(outs[0], outs[4])
+    # the real width (dim 3072, 24 heads, ffn 14336; 2 layers) on token counts that fill no tile: 45 and 18 tokens
+    model2, cfg2 = _native_model("real2", dev)
+    sd2 = synth.state_dict_torch(cfg2, dev)
+    for i, c in enumerate((dict(F=2, H=6, W=10, B=3, prompt_lens=(3, 200, 512)), dict(F=1, H=4, W=6, B=1, prompt_lens=(77,)))):
+        inp = synth.inputs(cfg2, c["F"], c["H"], c["W"], B=c["B"], prompt_lens=c["prompt_lens"], tag=f"edge_real{i}")
+        tt = {k: torch.from_numpy(inp[k]).to(dev) for k in ("x", "y", "additional_control", "full_ref", "t", "density")}
+        ctx = [torch.from_numpy(u).to(dev) for u in inp["context"]]
+        out = model2(x=tt["x"].bfloat16(), t=tt["t"], context=[u.bfloat16() for u in ctx], seq_len=inp["seq_len"],
+                     y=tt["y"].bfloat16(), full_ref=tt["full_ref"].bfloat16(),
+                     additional_control=tt["additional_control"].bfloat16(), density=tt["density"])
+        want = O.forward(sd2, cfg2, tt["x"], tt["t"], ctx, inp["seq_len"], tt["y"], tt["full_ref"],
+                         tt["additional_control"], tt["density"], policy="bf16")
+        assert out.shape == want.shape and torch.isfinite(out.float()).all() and _rel(out, want) < BF16_GATE, (i, _rel(out, want))
+    del model2, sd2
     # umT5
     m5, tcfg = _t5_model("tiny", dev)
     sd5 = {k: v.float() for k, v in m5.state_dict().items()}
