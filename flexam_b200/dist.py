@@ -311,18 +311,20 @@ class SlabExchange:
     def halo(self, grid: torch.Tensor, frame0: int, T: int, Hp: int, Wp: int) -> None:
         g = grid[:(frame0 + T) * Hp * Wp].view(frame0 + T, Hp, Wp * grid.shape[1])[frame0:]
         up, dn = self.rank - 1, self.rank + 1
-        reqs, recv = [], []
+        ops_, recv = [], []
         if up >= 0:
             buf = torch.empty_like(g[:, 0])
             recv.append((buf, 0))
-            reqs.append(dist.irecv(buf, src=self._global(up), group=self.group))
-            reqs.append(dist.isend(g[:, 1].contiguous(), dst=self._global(up), group=self.group))
+            ops_.append(dist.P2POp(dist.irecv, buf, self._global(up), self.group))
+            ops_.append(dist.P2POp(dist.isend, g[:, 1].contiguous(), self._global(up), self.group))
         if dn < self.world:
             buf = torch.empty_like(g[:, 0])
             recv.append((buf, Hp - 1))
-            reqs.append(dist.irecv(buf, src=self._global(dn), group=self.group))
-            reqs.append(dist.isend(g[:, Hp - 2].contiguous(), dst=self._global(dn), group=self.group))
-        for r in reqs:
+            ops_.append(dist.P2POp(dist.irecv, buf, self._global(dn), self.group))
+            ops_.append(dist.P2POp(dist.isend, g[:, Hp - 2].contiguous(), self._global(dn), self.group))
+        # one batch: under NCCL the sends and receives of a rank form one group (posted one by one, the receive-first
+        # order of two neighbours would wait on each other)
+        for r in dist.batch_isend_irecv(ops_):
             r.wait()
         for buf, row in recv:
             g[:, row].copy_(buf)
