@@ -1103,6 +1103,35 @@ def test_edge_shapes_on_one_engine(dev):
     assert _rel(enc, fp32) < 1.5 * _rel(lib_enc, fp32) + 5e-3
 
 
+def test_torch_library_operators_launch_the_native_kernels(dev):
+    """flexam_b200/torch_ops.py: the dispatcher operators torch.ops.flexam_b200.* run the same launches as flexam_b200.ops
+    on CUDA tensors (bit-identical results)."""
+    from flexam_b200 import ops, torch_ops  # noqa: F401  (importing registers the operators)
+    g = torch.Generator(device=dev).manual_seed(11)
+    M, N, K = 300, 384, 256
+    a = (torch.randn(M, K, device=dev, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).bfloat16()
+    b = torch.randn(N, device=dev, generator=g).bfloat16()
+    o1, o2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16), torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, b, o1, ops.FX_EPI_GELU_BF16)
+    torch.ops.flexam_b200.gemm(a, w, b, o2, ops.FX_EPI_GELU_BF16)
+    assert torch.equal(o1, o2)
+    x = torch.randn(M, K, device=dev, generator=g)
+    gam, bet = torch.randn(K, device=dev, generator=g).bfloat16(), torch.randn(K, device=dev, generator=g).bfloat16()
+    h1, h2 = torch.empty(M, K, device=dev, dtype=torch.bfloat16), torch.empty(M, K, device=dev, dtype=torch.bfloat16)
+    ops.ln_affine(x, h1, 1e-6, gam, bet)
+    torch.ops.flexam_b200.ln_affine(x, h2, 1e-6, gam, bet)
+    assert torch.equal(h1, h2)
+    B, L, H = 1, 200, 2
+    qkv = torch.randn(B, L, 3, H, 128, device=dev, generator=g).bfloat16()
+    a1, a2 = torch.empty(B, L, H, 128, device=dev, dtype=torch.bfloat16), torch.empty(B, L, H, 128, device=dev, dtype=torch.bfloat16)
+    ops.fmha(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], a1, 128 ** -0.5)
+    torch.ops.flexam_b200.fmha(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], a2, 128 ** -0.5)
+    assert torch.equal(a1, a2) and torch.isfinite(a1.float()).all()
+    with pytest.raises(Exception):                       # CUDA-only registration: no CPU kernel, no silent fallback
+        torch.ops.flexam_b200.ln_affine(x.cpu(), h1.cpu(), 1e-6, gam.cpu(), bet.cpu())
+
+
 def test_missing_extension_fails_loudly(monkeypatch):
     from flexam_b200 import lib
     monkeypatch.setattr(lib, "_lib", None)
